@@ -1,0 +1,275 @@
+"""Thin Python wrappers over the C-ABI (include/arn.h, include/arn_host.h).
+
+Names follow the reference's domain: a `HostScene` collects components (meshes, shaped
+primitives), `build()` is `BVH::new` + `Scene::new`; a `Context` is one GPU; `Context.upload`
+gives a device `Scene` on which `intersect_closest` (batched `Composable::intersect_ray`) and
+`render_pt` (`PTRenderer::render`) run.  numpy is used for host buffers only.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib as L
+
+
+class ArnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"arn error {code}: {msg}")
+        self.code = code
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def make_camera(parent_view, screen, znear, zfar, fov, res_x, res_y, lens=None):
+    """PerspecCam::new. `parent_view`: 4x4 given as 4 COLUMNS (cgmath / JSON order); screen = (pmin.x, pmin.y, pmax.x, pmax.y)."""
+    lib = L.load()
+    cam = L.Camera()
+    pv = _f32(parent_view).reshape(16)
+    sc = _f32(screen).reshape(4)
+    rc = lib.arn_camera_make(_ptr(pv), _ptr(sc), znear, zfar, fov, 1 if lens else 0,
+                             lens[0] if lens else 0.0, lens[1] if lens else 0.0, float(res_x), float(res_y), C.byref(cam))
+    if rc != 0:
+        raise ArnError(rc, lib.arn_hscene_last_error(None).decode())
+    return cam
+
+
+def make_film(res_x, res_y, crop=None, filter_radius=(4.0, 4.0)):
+    f = L.Film()
+    f.res_x, f.res_y = res_x, res_y
+    c = crop or (0, 0, res_x, res_y)
+    f.crop_min_x, f.crop_min_y, f.crop_max_x, f.crop_max_y = c
+    f.filter_radius_x, f.filter_radius_y = filter_radius
+    return f
+
+
+def make_sampler(sampledx, sampledy, ndim=8, seed=0):
+    s = L.Sampler()
+    s.sampledx, s.sampledy, s.ndim, s.seed = sampledx, sampledy, ndim, seed
+    return s
+
+
+def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, tiles=(16, 16)):
+    p = L.PTParams()
+    p.max_depth = max_depth
+    p.min_depth = max_depth // 2      # renderer/pt.rs:48
+    p.rr_threshold = 0.05             # renderer/pt.rs:47
+    p.tiles_x, p.tiles_y = tiles
+    p.rank, p.world_size = rank, world_size
+    p.spp_begin, p.spp_end = spp_begin, spp_end
+    return p
+
+
+def material(kind, kd=(0, 0, 0), ks=(0, 0, 0), sigma=0.0, roughness=0.0, eta=1.0, dissolve=1.0):
+    m = L.Material()
+    m.type = kind
+    m.kd[:] = kd
+    m.ks[:] = ks
+    m.sigma, m.roughness, m.eta, m.dissolve = sigma, roughness, eta, dissolve
+    return m
+
+
+class HostScene:
+    """Component list under construction (examples/arencli.rs:113-197)."""
+
+    def __init__(self):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        self._check(self.lib.arn_hscene_create(C.byref(self.h)))
+        self._keep = []
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ArnError(rc, self.lib.arn_hscene_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.arn_hscene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_material(self, m):
+        return self._check(self.lib.arn_hscene_add_material(self.h, C.byref(m)))
+
+    def add_mesh(self, positions, indices, material_id, normals=None, uvs=None, transform=None):
+        pos = _f32(positions).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        nrm = _f32(normals).reshape(-1, 3) if normals is not None else None
+        uv = _f32(uvs).reshape(-1, 2) if uvs is not None else None
+        tr = _f32(transform).reshape(16) if transform is not None else None
+        return self._check(self.lib.arn_hscene_add_mesh(self.h, _ptr(pos), pos.shape[0], _ptr(idx), idx.shape[0],
+                                                        _ptr(nrm), _ptr(uv), _ptr(tr), material_id))
+
+    def add_sphere(self, radius, zmin, zmax, phimax, material_id, emission=None, transform=None):
+        em = _f32(emission).reshape(3) if emission is not None else None
+        tr = _f32(transform).reshape(16) if transform is not None else None
+        return self._check(self.lib.arn_hscene_add_sphere(self.h, radius, zmin, zmax, phimax, material_id, _ptr(em), _ptr(tr)))
+
+    def load_obj(self, path, transform=None):
+        tr = _f32(transform).reshape(16) if transform is not None else _f32(IDENTITY).reshape(16)
+        return self._check(self.lib.arn_hscene_load_obj(self.h, str(path).encode(), _ptr(tr)))
+
+    def load_json(self, path, base_dir=None):
+        """arencli's parse_input. Returns (camera, film, sampler, pt_params, outputfilename)."""
+        cam, film, smp, prm = L.Camera(), L.Film(), L.Sampler(), L.PTParams()
+        out = C.create_string_buffer(1024)
+        self._check(self.lib.arn_hscene_load_json(self.h, str(path).encode(), str(base_dir).encode() if base_dir else None,
+                                                  C.byref(cam), C.byref(film), C.byref(smp), C.byref(prm), out, 1024))
+        return cam, film, smp, prm, out.value.decode()
+
+    def build(self, strategy=L.ARN_BVH_SAH):
+        self._check(self.lib.arn_hscene_build(self.h, strategy))
+        return self.desc()
+
+    def desc(self):
+        d = self.lib.arn_hscene_desc(self.h)
+        if not d:
+            raise ArnError(L.ARN_E_INVALID, "scene not built")
+        return d.contents
+
+    # numpy views of the flattened description (copies)
+    def nodes(self):
+        d = self.desc()
+        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.n_nodes, 8)).copy()
+
+    def order(self):
+        d = self.desc()
+        return np.ctypeslib.as_array(d.order, shape=(d.n_prims,)).copy()
+
+
+def bvh_build(bounds6, costs, strategy=L.ARN_BVH_SAH):
+    """arn_bvh_build on raw bounds. Returns (nodes as uint32 (n,8) bit patterns, order)."""
+    lib = L.load()
+    b = _f32(bounds6).reshape(-1, 6)
+    c = _f32(costs).reshape(-1)
+    n = b.shape[0]
+    nodes = np.zeros((2 * n, 8), dtype=np.uint32)
+    order = np.zeros(n, dtype=np.uint32)
+    nn = C.c_uint32(0)
+    rc = lib.arn_bvh_build(n, C.cast(_ptr(b), L.c_float_p), C.cast(_ptr(c), L.c_float_p), strategy,
+                           C.cast(_ptr(nodes), C.POINTER(L.Node)), C.cast(_ptr(order), L.c_u32_p), C.byref(nn))
+    if rc != 0:
+        raise ArnError(rc, "arn_bvh_build failed")
+    return nodes[:nn.value].copy(), order
+
+
+def film_finalize(film):
+    """TilePixel::finalize + u8 quantisation. film: (h, w, 4) float32 -> (rgb float (h,w,3), rgb8 (h,w,3))."""
+    lib = L.load()
+    f = _f32(film)
+    h, w = f.shape[0], f.shape[1]
+    rgb = np.zeros((h, w, 3), dtype=np.float32)
+    rgb8 = np.zeros((h, w, 3), dtype=np.uint8)
+    rc = lib.arn_film_finalize(_ptr(f), h * w, _ptr(rgb), _ptr(rgb8))
+    if rc != 0:
+        raise ArnError(rc, "arn_film_finalize failed")
+    return rgb, rgb8
+
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("tmax", np.float32)])
+HIT_DTYPE = np.dtype([("prim_id", np.int32), ("t", np.float32)])
+
+
+class Context:
+    """One GPU (arn_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = L.load()
+        self.c = C.c_void_p()
+        rc = self.lib.arn_ctx_create(device, C.byref(self.c))
+        if rc != 0:
+            raise ArnError(rc, self.lib.arn_last_error(None).decode())
+        self.device = device
+
+    def error(self):
+        return self.lib.arn_last_error(self.c).decode()
+
+    def close(self):
+        if self.c:
+            self.lib.arn_ctx_destroy(self.c)
+            self.c = C.c_void_p()
+
+    def synchronize(self):
+        rc = self.lib.arn_ctx_synchronize(self.c)
+        if rc != 0:
+            raise ArnError(rc, self.error())
+
+    def stream(self):
+        return self.lib.arn_ctx_stream(self.c)
+
+    def upload(self, desc):
+        s = C.c_void_p()
+        rc = self.lib.arn_scene_upload(self.c, C.byref(desc), C.byref(s))
+        if rc != 0:
+            raise ArnError(rc, self.error())
+        return Scene(self, s)
+
+
+class Scene:
+    """Device-resident flattened scene (arn_scene)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.s, self.lib = ctx, handle, ctx.lib
+
+    def close(self):
+        if self.s:
+            self.lib.arn_scene_destroy(self.s)
+            self.s = C.c_void_p()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ArnError(rc, self.ctx.error())
+
+    def intersect_closest(self, rays):
+        """rays: structured array RAY_DTYPE (host). Returns HIT_DTYPE array. H2D/D2H inside."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        self._check(self.lib.arn_intersect_closest(self.s, _ptr(rays), rays.shape[0], _ptr(hits)))
+        return hits
+
+    def intersect_any(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.empty(rays.shape[0], dtype=np.uint8)
+        self._check(self.lib.arn_intersect_any(self.s, _ptr(rays), rays.shape[0], _ptr(out)))
+        return out
+
+    def intersect_closest_dev(self, rays_ptr, n, hits_ptr, stats=None):
+        self._check(self.lib.arn_intersect_closest_dev(self.s, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr),
+                                                       C.byref(stats) if stats is not None else None))
+
+    def intersect_any_dev(self, rays_ptr, n, out_ptr, stats=None):
+        self._check(self.lib.arn_intersect_any_dev(self.s, C.c_void_p(rays_ptr), n, C.c_void_p(out_ptr),
+                                                   C.byref(stats) if stats is not None else None))
+
+    def intersect_closest_counted_dev(self, rays_ptr, n, hits_ptr):
+        ctr = (C.c_uint64 * 3)()
+        self._check(self.lib.arn_intersect_closest_counted_dev(self.s, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), ctr))
+        return int(ctr[0]), int(ctr[1]), int(ctr[2])
+
+    def render_pt(self, cam, film, sampler, params):
+        """PTRenderer::render up to the tile merge. Returns (film (h,w,4) float32 host array, Stats)."""
+        w = film.crop_max_x - film.crop_min_x
+        h = film.crop_max_y - film.crop_min_y
+        out = np.zeros((h, w, 4), dtype=np.float32)
+        st = L.Stats()
+        self._check(self.lib.arn_render_pt(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _ptr(out), C.byref(st)))
+        return out, st
+
+    def render_pt_dev(self, cam, film, sampler, params, film_dev_ptr, want_stats=True):
+        st = L.Stats()
+        self._check(self.lib.arn_render_pt_dev(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params),
+                                               C.c_void_p(film_dev_ptr), C.byref(st) if want_stats else None))
+        return st

@@ -1,0 +1,477 @@
+// C-ABI of the B200 path-tracing core (include/arn.h): contexts, scene upload, batched
+// intersection queries and the wavefront path tracer.  Compiled for sm_100a only, with
+// --fmad=false (see kernels/dev_math.cuh).  There is no CPU fallback: every entry point that
+// computes anything needs a CUDA device and fails with ARN_E_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/arn.h"
+#include "kernels/wavefront.cuh"
+
+using namespace arn;
+
+namespace {
+std::string g_last_error;
+std::mutex g_err_mutex;
+}
+
+struct arn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    std::string err;
+    std::mutex mu;
+    // wavefront buffers (allocated lazily, sized to wave capacity)
+    size_t wave_cap = 0;
+    PathBuf pb{};
+    Queues q{};
+    void* pool = nullptr;
+    size_t pool_bytes = 0;
+    // tile tables
+    int4* d_tile_rect = nullptr; unsigned long long* d_tile_prefix = nullptr; size_t tile_cap = 0;
+    // event pool for per-kernel timing
+    std::vector<cudaEvent_t> events;
+    // launch geometry (blocks per kernel, persistent grid-stride)
+    int g_generate = 0, g_extend = 0, g_shade = 0, g_connect = 0, g_accum = 0, g_closest = 0, g_any = 0;
+    // scratch for batched queries through host buffers
+    void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
+    unsigned long long* d_ctr = nullptr;
+};
+
+struct arn_scene {
+    arn_ctx* ctx = nullptr;
+    DevScene dev{};
+    std::vector<void*> allocs;
+    uint32_t max_depth = 0;
+    uint64_t bytes = 0;
+};
+
+namespace {
+
+int set_err(arn_ctx* c, int code, const std::string& msg) {
+    { std::lock_guard<std::mutex> g(g_err_mutex); g_last_error = msg; }
+    if (c) c->err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    return set_err(ctx, e_ == cudaErrorMemoryAllocation ? ARN_E_OOM : ARN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+template <typename T, typename P> int dev_upload(arn_scene* s, const T* host, size_t n, P* out) {
+    *out = nullptr;
+    if (n == 0 || !host) return ARN_OK;
+    void* d = nullptr;
+    CUDA_TRY(s->ctx, cudaMalloc(&d, n * sizeof(T)));
+    s->allocs.push_back(d);
+    CUDA_TRY(s->ctx, cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream));
+    s->bytes += n * sizeof(T);
+    *out = (P)d;
+    return ARN_OK;
+}
+
+int grid_for(arn_ctx* c, const void* kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ARN_BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return c->sm_count * per_sm;
+}
+
+cudaEvent_t get_event(arn_ctx* c, size_t i) {
+    while (c->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); c->events.push_back(e); }
+    return c->events[i];
+}
+
+int ensure_wave(arn_ctx* c, size_t cap) {
+    if (c->wave_cap >= cap) return ARN_OK;
+    if (c->pool) { cudaFree(c->pool); c->pool = nullptr; }
+    // one pool, carved into 256-byte aligned SoA streams
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_ray_o = carve(cap * 16), o_ray_d = carve(cap * 16), o_beta = carve(cap * 16), o_L = carve(cap * 16);
+    size_t o_pfilm = carve(cap * 8), o_pix = carve(cap * 4), o_smp = carve(cap * 4), o_st = carve(cap * 4);
+    size_t o_hp = carve(cap * 4), o_hit = carve(cap * 16);
+    size_t o_sho = carve(cap * 16), o_shd = carve(cap * 16), o_mo = carve(cap * 16), o_md = carve(cap * 16);
+    size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16);
+    size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4);
+    size_t o_counts = carve(64), o_stats = carve(64);
+    CUDA_TRY(c, cudaMalloc(&c->pool, off));
+    c->pool_bytes = off;
+    char* b = (char*)c->pool;
+    c->pb.ray_o = (float4*)(b + o_ray_o); c->pb.ray_d = (float4*)(b + o_ray_d); c->pb.beta = (float4*)(b + o_beta); c->pb.L = (float4*)(b + o_L);
+    c->pb.pfilm = (float2*)(b + o_pfilm); c->pb.pix = (uint32_t*)(b + o_pix); c->pb.smp = (uint32_t*)(b + o_smp); c->pb.st = (uint32_t*)(b + o_st);
+    c->pb.hit_prim = (int*)(b + o_hp); c->pb.hit = (float4*)(b + o_hit);
+    c->pb.sh_o = (float4*)(b + o_sho); c->pb.sh_d = (float4*)(b + o_shd); c->pb.mis_o = (float4*)(b + o_mo); c->pb.mis_d = (float4*)(b + o_md);
+    c->pb.a1 = (float4*)(b + o_a1); c->pb.a2 = (float4*)(b + o_a2); c->pb.beta_old = (float4*)(b + o_bo);
+    c->q.active[0] = (uint32_t*)(b + o_q0); c->q.active[1] = (uint32_t*)(b + o_q1); c->q.connect = (uint32_t*)(b + o_qc);
+    c->q.counts = (uint32_t*)(b + o_counts); c->q.stats = (unsigned long long*)(b + o_stats);
+    c->wave_cap = cap;
+    return ARN_OK;
+}
+
+size_t wave_capacity_default() {
+    const char* e = std::getenv("ARN_WAVE");
+    if (e) { long v = std::atol(e); if (v >= 1024) return (size_t)v; }
+    return (size_t)1 << 20;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* arn_version(void) { return "arendur_b200 0.1 sm_100a"; }
+
+const char* arn_last_error(const arn_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+int arn_ctx_create(int device, arn_ctx** out) {
+    if (!out) return set_err(nullptr, ARN_E_INVALID, "arn_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, ARN_E_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, ARN_E_INVALID, "arn_ctx_create: device index out of range");
+    arn_ctx* c = new arn_ctx;
+    c->device = device;
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { delete c; return set_err(nullptr, ARN_E_UNSUPPORTED, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor)); }
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->g_generate = grid_for(c, (const void*)k_generate);
+    c->g_extend = grid_for(c, (const void*)k_extend);
+    c->g_shade = grid_for(c, (const void*)k_shade);
+    c->g_connect = grid_for(c, (const void*)k_connect);
+    c->g_accum = grid_for(c, (const void*)k_accumulate);
+    c->g_closest = grid_for(c, (const void*)k_closest_batch<false>);
+    c->g_any = grid_for(c, (const void*)k_any_batch);
+    CUDA_TRY(nullptr, cudaMalloc(&c->d_ctr, 64));
+    *out = c;
+    return ARN_OK;
+}
+
+void arn_ctx_destroy(arn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->pool) cudaFree(c->pool);
+    if (c->d_tile_rect) cudaFree(c->d_tile_rect);
+    if (c->d_tile_prefix) cudaFree(c->d_tile_prefix);
+    if (c->d_rays) cudaFree(c->d_rays);
+    if (c->d_hits) cudaFree(c->d_hits);
+    if (c->d_ctr) cudaFree(c->d_ctr);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int arn_ctx_synchronize(arn_ctx* c) { if (!c) return ARN_E_INVALID; cudaSetDevice(c->device); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ARN_OK; }
+void* arn_ctx_stream(arn_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+void arn_scene_destroy(arn_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
+    if (!c || !d || !out) return set_err(c, ARN_E_INVALID, "arn_scene_upload: NULL argument");
+    if (!d->n_prims || !d->prims || !d->n_nodes || !d->nodes || !d->order) return set_err(c, ARN_E_INVALID, "arn_scene_upload: scene has no primitives or no BVH");
+    if (d->n_triangles && (!d->positions || !d->indices || !d->tri_mesh || !d->meshes)) return set_err(c, ARN_E_INVALID, "arn_scene_upload: triangle arrays missing");
+    if (d->n_prims >= 0x80000000u) return set_err(c, ARN_E_INVALID, "arn_scene_upload: too many primitives");
+    // validate references
+    for (uint32_t i = 0; i < d->n_prims; i++) {
+        uint32_t r = d->prims[i];
+        if (r & ARN_PRIM_SPHERE) { if ((r & ~ARN_PRIM_SPHERE) >= d->n_spheres) return set_err(c, ARN_E_INVALID, "component references a missing sphere"); }
+        else if (r >= d->n_triangles) return set_err(c, ARN_E_INVALID, "component references a missing triangle");
+        if (d->order[i] >= d->n_prims) return set_err(c, ARN_E_INVALID, "BVH order entry out of range");
+    }
+    for (size_t i = 0; i < (size_t)d->n_triangles * 3; i++) if (d->indices[i] >= d->n_vertices) return set_err(c, ARN_E_INVALID, "triangle index out of range");
+    for (uint32_t i = 0; i < d->n_triangles; i++) if (d->tri_mesh[i] >= d->n_meshes) return set_err(c, ARN_E_INVALID, "triangle mesh id out of range");
+    for (uint32_t i = 0; i < d->n_meshes; i++) {
+        if (d->meshes[i].material >= d->n_materials) return set_err(c, ARN_E_INVALID, "mesh material out of range");
+        if (d->meshes[i].has_normals && !d->normals) return set_err(c, ARN_E_INVALID, "mesh claims normals but none were passed");
+        if (d->meshes[i].has_uvs && !d->uvs) return set_err(c, ARN_E_INVALID, "mesh claims uvs but none were passed");
+    }
+    for (uint32_t i = 0; i < d->n_spheres; i++) if (d->spheres[i].material >= d->n_materials) return set_err(c, ARN_E_INVALID, "sphere material out of range");
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        if (d->light_prims[i] >= d->n_prims || !(d->prims[d->light_prims[i]] & ARN_PRIM_SPHERE))
+            return set_err(c, ARN_E_UNSUPPORTED, "lights must be emissive sphere primitives (triangle emitters do not work in arendur: surface_area() == 0, SURVEY.md Appendix A-2)");
+    }
+    // tree walk: bounds of child offsets, leaf ranges, maximum stack depth
+    uint32_t max_depth = 0;
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> st; st.push_back({0u, 1u});
+        size_t visited = 0;
+        while (!st.empty()) {
+            auto [idx, depth] = st.back(); st.pop_back();
+            if (idx >= d->n_nodes) return set_err(c, ARN_E_INVALID, "BVH child index out of range");
+            if (++visited > d->n_nodes) return set_err(c, ARN_E_INVALID, "BVH is not a tree");
+            max_depth = std::max(max_depth, depth);
+            const arn_node& nd = d->nodes[idx];
+            uint32_t len = nd.len_axis >> 2;
+            if (len == 0) { if (nd.offset < 2) return set_err(c, ARN_E_INVALID, "BVH interior offset invalid"); st.push_back({idx + nd.offset, depth + 1}); st.push_back({idx + 1, depth + 1}); }
+            else if ((uint64_t)nd.offset + len > d->n_prims) return set_err(c, ARN_E_INVALID, "BVH leaf range out of bounds");
+        }
+    }
+    if (max_depth > ARN_STACK) return set_err(c, ARN_E_UNSUPPORTED, "BVH deeper than the traversal stack (" + std::to_string(max_depth) + " > " + std::to_string(ARN_STACK) + ")");
+
+    cudaSetDevice(c->device);
+    arn_scene* s = new arn_scene; s->ctx = c; s->max_depth = max_depth;
+    auto fail = [&](int rc) { arn_scene_destroy(s); return rc; };
+    int rc;
+    // nodes: same 32-byte records, read on the device as float4 pairs
+    const arn_node* dn = nullptr;
+    if ((rc = dev_upload(s, d->nodes, d->n_nodes, &dn)) != ARN_OK) return fail(rc);
+    s->dev.nodes = (const float4*)dn;
+    // ordered 48-byte primitive slots
+    std::vector<float4> slots((size_t)d->n_prims * 3);
+    for (uint32_t k = 0; k < d->n_prims; k++) {
+        uint32_t comp = d->order[k], ref = d->prims[comp];
+        float4 a = make_float4(0, 0, 0, 0), b = a, cc = a;
+        if (ref & ARN_PRIM_SPHERE) { uint32_t w = comp | ARN_PRIM_SPHERE; std::memcpy(&a.w, &w, 4); }
+        else {
+            const float* p0 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref];
+            const float* p1 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref + 1];
+            const float* p2 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref + 2];
+            a = make_float4(p0[0], p0[1], p0[2], 0); std::memcpy(&a.w, &comp, 4);
+            b = make_float4(p1[0], p1[1], p1[2], 0); cc = make_float4(p2[0], p2[1], p2[2], 0);
+        }
+        slots[3 * (size_t)k] = a; slots[3 * (size_t)k + 1] = b; slots[3 * (size_t)k + 2] = cc;
+    }
+    if ((rc = dev_upload(s, slots.data(), slots.size(), &s->dev.tris)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->spheres, d->n_spheres, &s->dev.spheres)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->indices, (size_t)d->n_triangles * 3, &s->dev.indices)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->positions, (size_t)d->n_vertices * 3, &s->dev.positions)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->normals, d->normals ? (size_t)d->n_vertices * 3 : 0, &s->dev.normals)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->uvs, d->uvs ? (size_t)d->n_vertices * 2 : 0, &s->dev.uvs)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->tri_mesh, d->n_triangles, &s->dev.tri_mesh)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->meshes, d->n_meshes, &s->dev.meshes)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->materials, d->n_materials, &s->dev.materials)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->prims, d->n_prims, &s->dev.prims)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->light_prims, d->n_lights, &s->dev.light_prims)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->light_func, d->n_lights, &s->dev.light_func)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->light_cdf, d->n_lights ? d->n_lights + 1 : 0, &s->dev.light_cdf)) != ARN_OK) return fail(rc);
+    s->dev.light_integral = d->light_func_integral;
+    s->dev.n_lights = d->n_lights; s->dev.n_nodes = d->n_nodes; s->dev.n_prims = d->n_prims; s->dev.n_spheres = d->n_spheres;
+    cudaError_t e = cudaStreamSynchronize(c->stream);     // the staging vector `slots` dies here
+    if (e != cudaSuccess) { set_err(c, ARN_E_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); return fail(ARN_E_CUDA); }
+    *out = s;
+    return ARN_OK;
+}
+
+// ---------------------------------------------------------------- batched queries
+int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void* hits_dev, arn_stats* stats) {
+    if (!s || (n && (!rays_dev || !hits_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_dev: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    if (n == 0) return ARN_OK;
+    int grid = (int)std::min<size_t>((size_t)c->g_closest, (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
+    k_closest_batch<false><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    CUDA_TRY(c, cudaGetLastError());
+    if (stats) {
+        cudaEventRecord(e1, c->stream);
+        CUDA_TRY(c, cudaEventSynchronize(e1));
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        std::memset(stats, 0, sizeof *stats);
+        stats->extend_rays = n; stats->kernel_launches = 1; stats->gpu_ms = ms; stats->extend_ms = ms;
+    }
+    return ARN_OK;
+}
+int arn_intersect_any_dev(arn_scene* s, const void* rays_dev, size_t n, void* out_dev, arn_stats* stats) {
+    if (!s || (n && (!rays_dev || !out_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any_dev: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    if (n == 0) return ARN_OK;
+    int grid = (int)std::min<size_t>((size_t)c->g_any, (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
+    k_any_batch<<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    CUDA_TRY(c, cudaGetLastError());
+    if (stats) {
+        cudaEventRecord(e1, c->stream);
+        CUDA_TRY(c, cudaEventSynchronize(e1));
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        std::memset(stats, 0, sizeof *stats);
+        stats->shadow_rays = n; stats->kernel_launches = 1; stats->gpu_ms = ms;
+    }
+    return ARN_OK;
+}
+
+static int ensure_ray_scratch(arn_ctx* c, size_t n) {
+    if (c->rays_cap >= n) return ARN_OK;
+    if (c->d_rays) cudaFree(c->d_rays);
+    if (c->d_hits) cudaFree(c->d_hits);
+    c->d_rays = c->d_hits = nullptr; c->rays_cap = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_rays, n * sizeof(arn_ray)));
+    CUDA_TRY(c, cudaMalloc(&c->d_hits, n * sizeof(arn_hit)));
+    c->rays_cap = n;
+    return ARN_OK;
+}
+int arn_intersect_closest(arn_scene* s, const arn_ray* rays, size_t n, arn_hit* hits) {
+    if (!s || (n && (!rays || !hits))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest: NULL argument");
+    arn_ctx* c = s->ctx; std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    if (n == 0) return ARN_OK;
+    int rc = ensure_ray_scratch(c, n); if (rc != ARN_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_rays, rays, n * sizeof(arn_ray), cudaMemcpyHostToDevice, c->stream));
+    rc = arn_intersect_closest_dev(s, c->d_rays, n, c->d_hits, nullptr); if (rc != ARN_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(hits, c->d_hits, n * sizeof(arn_hit), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ARN_OK;
+}
+int arn_intersect_any(arn_scene* s, const arn_ray* rays, size_t n, uint8_t* out) {
+    if (!s || (n && (!rays || !out))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any: NULL argument");
+    arn_ctx* c = s->ctx; std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    if (n == 0) return ARN_OK;
+    int rc = ensure_ray_scratch(c, n); if (rc != ARN_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_rays, rays, n * sizeof(arn_ray), cudaMemcpyHostToDevice, c->stream));
+    rc = arn_intersect_any_dev(s, c->d_rays, n, c->d_hits, nullptr); if (rc != ARN_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->d_hits, n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ARN_OK;
+}
+
+// Instrumented closest-hit pass: counters_out[0..2] = nodes tested, triangles tested, spheres
+// tested, summed over the batch (the algorithmic-bytes figure of SURVEY.md §8(d)).  DEVICE buffers.
+int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t n, void* hits_dev, uint64_t* counters_out) {
+    if (!s || !rays_dev || !hits_dev || !counters_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_counted_dev: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 64, c->stream));
+    int grid = (int)std::min<size_t>((size_t)c->g_closest, (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    if (grid < 1) grid = 1;
+    k_closest_batch<true><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, c->d_ctr);
+    CUDA_TRY(c, cudaGetLastError());
+    unsigned long long h[3];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->d_ctr, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    counters_out[0] = h[0]; counters_out[1] = h[1]; counters_out[2] = h[2];
+    return ARN_OK;
+}
+
+// ---------------------------------------------------------------- path tracer
+int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                      const arn_pt_params* prm, void* film_dev, arn_stats* stats) {
+    if (!s || !cam || !film || !smp || !prm || !film_dev) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    if (s->dev.n_lights == 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: the scene has no lights (the reference indexes lights[0] and panics, renderer/scene.rs:53-55)");
+    int cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
+    if (cw <= 0 || chh <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty crop window");
+    if (film->crop_max_x > 65535 || film->crop_max_y > 65535 || film->crop_min_x < 0 || film->crop_min_y < 0) return set_err(c, ARN_E_UNSUPPORTED, "arn_render_pt: crop window must lie in [0, 65535]");
+    uint32_t spp = smp->sampledx * smp->sampledy;
+    uint32_t s0 = prm->spp_begin, s1 = prm->spp_end ? prm->spp_end : spp;
+    if (s1 <= s0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty sample range");
+    if (prm->max_depth == 0 || prm->max_depth > 80) return set_err(c, ARN_E_INVALID, "arn_render_pt: max_depth must be in 1..80");
+    uint32_t world = prm->world_size ? prm->world_size : 1;
+    if (prm->rank >= world) return set_err(c, ARN_E_INVALID, "arn_render_pt: rank >= world_size");
+    // Film::spawn_tiles(nx, ny) (filming/film.rs:104-135), ix-major order; this rank takes t % world == rank
+    long nx = prm->tiles_x ? prm->tiles_x : 16, ny = prm->tiles_y ? prm->tiles_y : 16;
+    long dx = cw / nx, dy = chh / ny;
+    if (dx <= 0 || dy <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: crop window smaller than the tile grid (spawn_tiles divides by zero)");
+    long lastx = dx + cw % dx, lasty = dy + chh % dy;
+    std::vector<int4> rects; std::vector<unsigned long long> prefix; prefix.push_back(0);
+    for (long ix = 0, t = 0; ix < nx; ix++) for (long iy = 0; iy < ny; iy++, t++) {
+        if ((uint32_t)(t % world) != prm->rank) continue;
+        long cdx = ix == nx - 1 ? lastx : dx, cdy = iy == ny - 1 ? lasty : dy;
+        // tile coordinates are relative to the crop window origin in the reference (ix*dx, iy*dy): crop_min is (0,0) in every config
+        rects.push_back(make_int4((int)(ix * dx), (int)(iy * dy), (int)cdx, (int)cdy));
+        prefix.push_back(prefix.back() + (unsigned long long)cdx * (unsigned long long)cdy);
+    }
+    std::lock_guard<std::mutex> guard(c->mu);
+    if (rects.empty()) { if (stats) std::memset(stats, 0, sizeof *stats); return ARN_OK; }
+    if (c->tile_cap < rects.size()) {
+        if (c->d_tile_rect) cudaFree(c->d_tile_rect);
+        if (c->d_tile_prefix) cudaFree(c->d_tile_prefix);
+        c->d_tile_rect = nullptr; c->d_tile_prefix = nullptr; c->tile_cap = 0;
+        CUDA_TRY(c, cudaMalloc(&c->d_tile_rect, rects.size() * sizeof(int4)));
+        CUDA_TRY(c, cudaMalloc(&c->d_tile_prefix, (rects.size() + 1) * sizeof(unsigned long long)));
+        c->tile_cap = rects.size();
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tile_rect, rects.data(), rects.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tile_prefix, prefix.data(), prefix.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+
+    unsigned long long total = prefix.back() * (unsigned long long)(s1 - s0);
+    size_t cap = wave_capacity_default();
+    if ((unsigned long long)cap > total) cap = (size_t)((total + ARN_BLOCK - 1) / ARN_BLOCK * ARN_BLOCK);
+    int rc = ensure_wave(c, cap); if (rc != ARN_OK) return rc;
+
+    WaveParams wp;
+    std::memcpy(wp.raster_view, cam->raster_view, 64); std::memcpy(wp.view_parent, cam->view_parent, 64);
+    wp.has_lens = cam->has_lens; wp.lens_radius = cam->lens_radius; wp.focal_distance = cam->focal_distance;
+    wp.crop_x0 = film->crop_min_x; wp.crop_y0 = film->crop_min_y; wp.crop_w = cw; wp.crop_h = chh;
+    wp.fr_x = film->filter_radius_x; wp.fr_y = film->filter_radius_y;
+    wp.seed = smp->seed; wp.max_depth = prm->max_depth; wp.min_depth = prm->min_depth; wp.rr_threshold = prm->rr_threshold;
+    wp.n_tiles = (uint32_t)rects.size(); wp.tile_rect = c->d_tile_rect; wp.tile_prefix = c->d_tile_prefix;
+    wp.spp_begin = s0; wp.spp_count = s1 - s0;
+
+    CUDA_TRY(c, cudaMemsetAsync(c->q.stats, 0, 64, c->stream));
+    size_t ev = 0;
+    cudaEvent_t e_begin = get_event(c, ev++), e_end = get_event(c, ev++);
+    const bool time_kernels = stats != nullptr;
+    std::vector<std::pair<size_t, int>> ext_events;      // (event index, bounce)
+    uint64_t launches = 0;
+    cudaEventRecord(e_begin, c->stream);
+    for (unsigned long long base = 0; base < total; base += cap) {
+        uint32_t n = (uint32_t)std::min<unsigned long long>(cap, total - base);
+        k_begin_wave<<<1, 1, 0, c->stream>>>(c->q, n);
+        k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, base, n);
+        launches += 2;
+        int cur = 0;
+        for (uint32_t b = 0; b < prm->max_depth; b++) {
+            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, (int)b}); }
+            k_extend<<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
+            if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
+            k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur);
+            k_connect<<<c->g_connect, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q);
+            k_next_bounce<<<1, 1, 0, c->stream>>>(c->q, cur);
+            launches += 4;
+            cur ^= 1;
+        }
+        k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
+        launches += 1;
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    cudaEventRecord(e_end, c->stream);
+    if (stats) {
+        unsigned long long hs[8];
+        CUDA_TRY(c, cudaMemcpyAsync(hs, c->q.stats, 64, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        std::memset(stats, 0, sizeof *stats);
+        stats->camera_rays = total; stats->extend_rays = hs[0]; stats->shadow_rays = hs[1]; stats->mis_rays = hs[2];
+        stats->invalid_samples = hs[3]; stats->extend_bounce_rays = hs[4]; stats->kernel_launches = launches;
+        float ms = 0.f; cudaEventElapsedTime(&ms, e_begin, e_end); stats->gpu_ms = ms;
+        double ext = 0.0, extb = 0.0;
+        for (auto& pr : ext_events) { float m = 0.f; cudaEventElapsedTime(&m, c->events[pr.first], c->events[pr.first + 1]); ext += m; if (pr.second > 0) extb += m; }
+        stats->extend_ms = ext; stats->extend_bounce_ms = extb;
+    }
+    return ARN_OK;
+}
+
+int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                  const arn_pt_params* prm, float* film_out, arn_stats* stats) {
+    if (!s || !film || !film_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    long cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
+    if (cw <= 0 || chh <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty crop window");
+    size_t bytes = (size_t)cw * (size_t)chh * 16;
+    void* d_film = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d_film, bytes));
+    cudaMemsetAsync(d_film, 0, bytes, c->stream);
+    arn_stats local;
+    int rc = arn_render_pt_dev(s, cam, film, smp, prm, d_film, stats ? stats : &local);
+    if (rc == ARN_OK) {
+        cudaError_t e = cudaMemcpyAsync(film_out, d_film, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_err(c, ARN_E_CUDA, std::string("film download: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_film);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// BVH traversal + ray/primitive intersection for sm_100a (kernels K2 / K4 of SURVEY.md §2.1).
+//
+// Replaces, per ray: BVH::intersect_ray (src/component/bvh.rs:97-128),
+// BBox3f::intersect_ray_cached (src/geometry/bbox.rs:549-580), ShearingTransformCache
+// (src/geometry/ray.rs:190-235), TriangleInstance::intersect_ray up to the acceptance test
+// (src/shape/triangle.rs:396-451), Sphere::intersect_ray (src/shape/sphere.rs:193-297) and the
+// TransformedComposable ray round trip (src/component/transformed.rs:73-83).
+//
+// Layout in HBM (built at upload):
+//   nodes : 32 B each, 32-B aligned, read as two 128-bit loads
+//           q0 = (bmin.x, bmin.y, bmin.z, bmax.x)  q1 = (bmax.y, bmax.z, offset, len_axis)
+//   tris  : one 48-B record per ORDERED primitive slot (BVH leaf order), three 128-bit loads
+//           (p0.xyz, component id) (p1.xyz, -) (p2.xyz, -); sphere slots carry the component id
+//           with ARN_PRIM_SPHERE set and no vertices.
+// Traversal order, the strict `<` acceptance and the `t0 < tmax` re-check at pop time
+// reproduce the reference exactly; the slab test of a child is evaluated when its parent is
+// expanded (its t0 travels on the stack) instead of after the pop — the outcome is identical
+// because only the final `t0 < tmax` comparison depends on the shrinking tmax.
+#pragma once
+#include "dev_math.cuh"
+#include "../../../include/arn.h"
+
+namespace arn {
+
+typedef arn_sphere DevSphere;   // same POD on host and device (176 B)
+
+struct DevScene {
+    const float4* __restrict__ nodes;     // 2 per node
+    const float4* __restrict__ tris;      // 3 per ordered slot
+    const DevSphere* __restrict__ spheres;
+    // shading data, indexed by triangle id (input order)
+    const uint32_t* __restrict__ indices;    // 3 per triangle
+    const float* __restrict__ positions;     // 3 per vertex
+    const float* __restrict__ normals;       // 3 per vertex (or null)
+    const float* __restrict__ uvs;           // 2 per vertex (or null)
+    const uint32_t* __restrict__ tri_mesh;   // triangle -> mesh
+    const arn_mesh* __restrict__ meshes;
+    const arn_material* __restrict__ materials;
+    const uint32_t* __restrict__ prims;      // component -> triangle id | sphere bit
+    const uint32_t* __restrict__ light_prims;
+    const float* __restrict__ light_func;
+    const float* __restrict__ light_cdf;
+    float light_integral;
+    uint32_t n_lights, n_nodes, n_prims, n_spheres;
+};
+
+#define ARN_STACK 64           /* upload rejects trees deeper than this */
+
+// Ray state used by traversal: the slab cache keeps the ORIGINAL origin / 1/dir
+// (bvh.rs:101,112 refreshes only tmax), the shear cache follows the CURRENT ray
+// (ray.rs:136-139), which differs only after a transformed-sphere hit.
+struct TravRay {
+    float3 co, inv;            // cache: origin, 1/dir
+    float3 o, d;               // current ray
+    float tmax;
+    int kz;                    // 0 = XZ perm, 1 = YZ, 2 = ZZ
+    float3 shear;
+};
+
+ARN_DEV void shear_setup(TravRay& r) {                     // ShearingTransformCache::from_ray
+    float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+    float3 dd;
+    if (ax > ay && ax > az) { r.kz = 0; dd = f3(r.d.y, r.d.z, r.d.x); }
+    else if (ay > az)       { r.kz = 1; dd = f3(r.d.z, r.d.x, r.d.y); }
+    else                    { r.kz = 2; dd = r.d; }
+    r.shear = f3(-dd.x / dd.z, -dd.y / dd.z, 1.f / dd.z);
+}
+ARN_DEV void trav_init(TravRay& r, float3 o, float3 d, float tmax) {
+    r.o = o; r.d = d; r.tmax = tmax; r.co = o;
+    r.inv = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);            // construct_ray_cache (bbox.rs:583-592)
+    shear_setup(r);
+}
+
+// Slab test without the tmax comparison: returns false on a definite miss, else t0.
+ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_out) {
+    const float k = 1.f + 2.f * gamma_n(3.f);
+    const bool nx = r.inv.x < 0.f, ny = r.inv.y < 0.f, nz = r.inv.z < 0.f;
+    const float bminx = q0.x, bminy = q0.y, bminz = q0.z, bmaxx = q0.w, bmaxy = q1.x, bmaxz = q1.y;
+    float t0 = ((nx ? bmaxx : bminx) - r.co.x) * r.inv.x;
+    float t1 = ((nx ? bminx : bmaxx) - r.co.x) * r.inv.x;
+    float ty0 = ((ny ? bmaxy : bminy) - r.co.y) * r.inv.y;
+    float ty1 = ((ny ? bminy : bmaxy) - r.co.y) * r.inv.y;
+    t1 *= k; ty1 *= k;
+    if (t0 > ty1 || ty0 > t1) return false;
+    if (ty0 > t0) t0 = ty0;
+    if (ty1 < t1) t1 = ty1;
+    float tz0 = ((nz ? bmaxz : bminz) - r.co.z) * r.inv.z;
+    float tz1 = ((nz ? bminz : bmaxz) - r.co.z) * r.inv.z;
+    tz1 *= k;
+    if (t0 > tz1 || tz0 > t1) return false;
+    if (tz0 > t0) t0 = tz0;
+    if (tz1 < t1) t1 = tz1;
+    t0_out = t0;
+    return t1 > 0.f;           // caller adds `t0 < tmax` (NaN t0 fails it, as in the reference)
+}
+
+ARN_DEV float3 perm_point(float3 p, int kz) {
+    return kz == 0 ? f3(p.y, p.z, p.x) : (kz == 1 ? f3(p.z, p.x, p.y) : p);
+}
+
+// Watertight ray/triangle acceptance test (triangle.rs:398-451).  Returns true and t, b0..b2.
+ARN_DEV bool tri_test(float3 p0, float3 p1, float3 p2, const TravRay& r, float& t, float& b0, float& b1, float& b2) {
+    float3 no = -r.o;
+    float3 q0 = perm_point(p0 + no, r.kz), q1 = perm_point(p1 + no, r.kz), q2 = perm_point(p2 + no, r.kz);
+    q0.x += r.shear.x * q0.z; q0.y += r.shear.y * q0.z;
+    q1.x += r.shear.x * q1.z; q1.y += r.shear.y * q1.z;
+    q2.x += r.shear.x * q2.z; q2.y += r.shear.y * q2.z;
+    float e0 = q1.x * q2.y - q1.y * q2.x;
+    float e1 = q2.x * q0.y - q2.y * q0.x;
+    float e2 = q0.x * q1.y - q0.y * q1.x;
+    if ((e0 < 0.f || e1 < 0.f || e2 < 0.f) && (e0 > 0.f || e1 > 0.f || e2 > 0.f)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0.f) return false;
+    q0.z *= r.shear.z; q1.z *= r.shear.z; q2.z *= r.shear.z;
+    float ts = e0 * q0.z + e1 * q1.z + e2 * q2.z;
+    if (det < 0.f && (ts >= 0.f || ts < r.tmax * det)) return false;
+    else if (det > 0.f && (ts <= 0.f || ts > r.tmax * det)) return false;
+    float inv_det = 1.f / det;
+    b0 = e0 * inv_det; b1 = e1 * inv_det; b2 = e2 * inv_det;
+    t = ts * inv_det;
+    float maxxt = fmaxf(fmaxf(q0.x, q1.x), q2.x);
+    float maxyt = fmaxf(fmaxf(q0.y, q1.y), q2.y);
+    float maxzt = fmaxf(fmaxf(q0.z, q1.z), q2.z);
+    float maxe = fmaxf(fmaxf(e0, e1), e2);
+    float deltax = maxxt * gamma_n(5.f);
+    float deltay = maxyt * gamma_n(5.f);
+    float deltaz = maxzt * gamma_n(3.f);
+    float delta_err = 2.f * (gamma_n(2.f) * maxxt * maxyt + deltay * maxxt + deltax * maxyt);
+    float delta_t = 3.f * (gamma_n(3.f) * maxe * maxzt + delta_err * maxzt + deltaz * maxe) * fabsf(inv_det);
+    if (t <= delta_t) return false;
+    return true;
+}
+
+// Sphere::intersect_ray_full + refinement + clipping (sphere.rs:193-250), local space.
+// On a hit returns t and the refined local hit point p.
+ARN_DEV bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, float& t_out, float3& p_out) {
+    float a = dot(d, d);
+    float3 m = (d * o) * 2.f;
+    float b = m.x + m.y + m.z;
+    float c = dot(o, o) - sp.radius * sp.radius;
+    float delta = b * b - 4.f * a * c;
+    if (delta < 0.f) return false;
+    float invert_2a = 1.f / (2.f * a);
+    float d1 = sqrtf(delta) * invert_2a;
+    float d0 = -b * invert_2a;
+    float t0, t1;
+    if (invert_2a > 0.f) { t0 = d0 - d1; t1 = d0 + d1; } else { t0 = d0 + d1; t1 = d0 - d1; }
+    if (t0 > tmax || t1 < 0.f) return false;
+    float t;
+    if (t0 > 0.f) t = t0; else if (t1 > tmax) return false; else t = t1;
+    float3 p = o + d * t;
+    p = p * sp.radius / length(p);
+    if (p.x == 0.f && p.y == 0.f) p.x = 1e-5f * sp.radius;
+    float phi = atan2f(p.y, p.x);
+    if (phi < 0.f) phi += 2.f * ARN_PI;
+    if (p.z < sp.zmin || p.z > sp.zmax || phi > sp.phimax) return false;
+    t_out = t; p_out = p;
+    return true;
+}
+
+struct HitRec {               // what shading needs from the final hit
+    int prim;                 // component index, -1 = miss
+    float t;
+    float a, b, c;            // triangle: b0,b1,b2; sphere: refined local hit point
+};
+
+// Component test for a sphere slot inside traversal.  Mirrors `iray = ray.clone();
+// element.intersect_ray(&mut iray); if ray.tmax > iray.tmax { *ray = iray }` (bvh.rs:108-113)
+// through TransformedComposable (transformed.rs:73-83): on an accepted hit the traversal ray
+// becomes the round-tripped one.
+static __device__ __noinline__ void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& h) {
+    const DevSphere& sp = sc.spheres[sc.prims[comp] & ~ARN_PRIM_SPHERE];
+    float3 lo = r.o, ld = r.d;
+    if (sp.has_transform) { lo = xform_point(sp.parent_local, r.o); ld = xform_vector(sp.parent_local, r.d); }
+    float t; float3 p;
+    if (!sphere_test(sp, lo, ld, r.tmax, t, p)) return;
+    if (!(r.tmax > t)) return;
+    if (sp.has_transform) {
+        r.o = xform_point(sp.local_parent, lo); r.d = xform_vector(sp.local_parent, ld);
+        shear_setup(r);
+    }
+    r.tmax = t;
+    h.prim = (int)comp; h.t = t; h.a = p.x; h.b = p.y; h.c = p.z;
+}
+
+// Closest hit (ANY = false) or any hit (ANY = true: stops at the first accepted primitive —
+// the reference's shadow rays run the closest-hit query and only look at is_some(),
+// component/mod.rs:35-38, so the boolean is identical).
+// COUNT: accumulate nodes/primitives tested into ctr[0..2] (for the algorithmic-bytes figure).
+template <bool ANY, bool COUNT>
+ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
+    h.prim = -1; h.t = ARN_INF; h.a = h.b = h.c = 0.f;
+    uint2 stack[ARN_STACK];
+    int sp = 0;
+    // root: tested like any popped node
+    float4 q0 = __ldg(&sc.nodes[0]), q1 = __ldg(&sc.nodes[1]);
+    float t0;
+    if (COUNT) ctr[0]++;
+    if (!slab(q0, q1, r, t0) || !(t0 < r.tmax)) return;
+    uint32_t idx = 0;
+    uint32_t offset = __float_as_uint(q1.z), len_axis = __float_as_uint(q1.w);
+    for (;;) {
+        uint32_t len = len_axis >> 2;
+        if (len == 0) {
+            // interior: expand both children (first child = idx+1, second = idx+offset)
+            uint32_t ia = idx + 1, ib = idx + offset;
+            float4 a0 = __ldg(&sc.nodes[2 * ia]), a1 = __ldg(&sc.nodes[2 * ia + 1]);
+            float4 b0 = __ldg(&sc.nodes[2 * ib]), b1 = __ldg(&sc.nodes[2 * ib + 1]);
+            if (COUNT) ctr[0] += 2;
+            float ta, tb;
+            bool ha = slab(a0, a1, r, ta) && ta < r.tmax;
+            bool hb = slab(b0, b1, r, tb) && tb < r.tmax;
+            uint32_t axis = len_axis & 3u;
+            bool neg = axis_of(r.inv, (int)axis) < 0.f;       // dir_is_neg[split_axis]: second child first
+            if (ha && hb) {
+                if (neg) { stack[sp++] = make_uint2(ia, __float_as_uint(ta)); idx = ib; offset = __float_as_uint(b1.z); len_axis = __float_as_uint(b1.w); }
+                else     { stack[sp++] = make_uint2(ib, __float_as_uint(tb)); idx = ia; offset = __float_as_uint(a1.z); len_axis = __float_as_uint(a1.w); }
+                continue;
+            } else if (ha) { idx = ia; offset = __float_as_uint(a1.z); len_axis = __float_as_uint(a1.w); continue; }
+            else if (hb) { idx = ib; offset = __float_as_uint(b1.z); len_axis = __float_as_uint(b1.w); continue; }
+        } else {
+            for (uint32_t k = offset; k < offset + len; k++) {
+                float4 v0 = __ldg(&sc.tris[3 * k]);
+                uint32_t comp = __float_as_uint(v0.w);          // component id, sphere bit set for sphere slots
+                if (comp & ARN_PRIM_SPHERE) { if (COUNT) ctr[2]++; sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h); }
+                else {
+                    float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
+                    if (COUNT) ctr[1]++;
+                    float t, b0, b1, b2;
+                    if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
+                        r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
+                    }
+                }
+                if (ANY && h.prim >= 0) return;
+            }
+        }
+        // pop: skip entries whose entry distance is no longer below tmax
+        for (;;) {
+            if (sp == 0) return;
+            uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) < r.tmax) {
+                idx = e.x;
+                float4 n1 = __ldg(&sc.nodes[2 * idx + 1]);
+                offset = __float_as_uint(n1.z); len_axis = __float_as_uint(n1.w);
+                break;
+            }
+        }
+    }
+}
+
+}  // namespace arn

@@ -1,0 +1,388 @@
+// Wavefront path-tracing kernels for sm_100a (K1..K7 of SURVEY.md §2.1).
+//
+// One "wave" = up to W camera samples processed bounce by bounce:
+//   k_generate -> [ k_extend -> k_shade -> k_connect ] x max_depth -> k_accumulate
+// Stages are separate kernels linked by compacted queues of path ids; the queues are built
+// in k_shade with warp ballots + shared-memory staging (one global atomic per block
+// iteration).  All launches are grid-stride over DEVICE-side counters, so a whole wave is
+// enqueued without a host round trip.
+//
+// Replaces: PTRenderer::render's per-sample loop and calculate_lighting
+// (src/renderer/pt.rs:55-176), Scene::uniform_sample_one_light / evaluate_direct
+// (src/renderer/scene.rs:58-167), Sampler::get_camera_sample (src/sample/mod.rs:38-43),
+// PerspecCam::generate_path_differential (src/filming/perspective.rs:292-320),
+// FilmTile::add_sample (src/filming/film.rs:297-319).
+#pragma once
+#include "shade.cuh"
+
+namespace arn {
+
+#define ARN_BLOCK 256
+
+struct PathBuf {                 // SoA over path slots, capacity W
+    float4* ray_o;               // origin xyz
+    float4* ray_d;               // direction xyz
+    float4* beta;                // throughput rgb
+    float4* L;                   // radiance rgb
+    float2* pfilm;               // film position of the camera sample
+    uint32_t* pix;               // x | y << 16
+    uint32_t* smp;               // sample index
+    uint32_t* st;                // bounces | specular << 8 | n1d << 16 | n2d << 24
+    int* hit_prim;
+    float4* hit;                 // t, a, b, c
+    // next-event-estimation state between k_shade and k_connect
+    float4* sh_o;                // shadow ray origin xyz, tmax
+    float4* sh_d;                // shadow ray direction
+    float4* mis_o;               // BSDF-sampled light ray origin
+    float4* mis_d;               // ... direction (= wi)
+    float4* a1;                  // light-sampling term rgb, w = light choice pdf
+    float4* a2;                  // BSDF-sampling term rgb, w = light component id (bits)
+    float4* beta_old;            // throughput before this bounce's BSDF sample, w = flags (bits)
+};
+#define NEE_DONE 1u
+#define NEE_SHADOW 2u
+#define NEE_MIS 4u
+
+struct Queues {
+    uint32_t* active[2];         // path ids for the current / next bounce
+    uint32_t* connect;           // path ids with a pending direct-light term
+    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size
+    unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1
+};
+
+struct WaveParams {
+    float raster_view[16], view_parent[16];
+    uint32_t has_lens; float lens_radius, focal_distance;
+    int crop_x0, crop_y0, crop_w, crop_h;
+    float fr_x, fr_y;
+    uint32_t seed;
+    uint32_t max_depth, min_depth; float rr_threshold;
+    uint32_t n_tiles;
+    const int4* tile_rect;                  // x0, y0, w, h of each of this rank's tiles
+    const unsigned long long* tile_prefix;  // pixels before tile i (n_tiles + 1 entries)
+    uint32_t spp_begin, spp_count;
+};
+
+// ---- block-level queue append: warp ballots + shared-memory staging ----------------
+// Every thread of the block calls this once per iteration with `keep` and its path id.
+ARN_DEV void queue_append(bool keep, uint32_t pid, uint32_t* __restrict__ queue, uint32_t* __restrict__ count) {
+    __shared__ uint32_t warp_tot[ARN_BLOCK / 32];
+    __shared__ uint32_t block_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    unsigned rank = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < ARN_BLOCK / 32; w++) { uint32_t c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
+        block_base = tot ? atomicAdd(count, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) queue[block_base + warp_tot[warp] + rank] = pid;
+    __syncthreads();
+}
+
+// ---- K1 generate ------------------------------------------------------------------------
+__global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q,
+                                                         unsigned long long wave_base, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long g = wave_base + i;
+        unsigned long long pl = g / p.spp_count;
+        uint32_t s = p.spp_begin + (uint32_t)(g % p.spp_count);
+        // tile lookup: largest t with prefix[t] <= pl
+        uint32_t lo = 0, hi = p.n_tiles;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (p.tile_prefix[mid] <= pl) lo = mid; else hi = mid; }
+        int4 tr = p.tile_rect[lo];
+        uint32_t off = (uint32_t)(pl - p.tile_prefix[lo]);
+        uint32_t px = (uint32_t)tr.x + off % (uint32_t)tr.z, py = (uint32_t)tr.y + off / (uint32_t)tr.z;   // row-major in the tile
+        Sampler sm; sm.init(p.seed, px, py, s, 0, 0);
+        float2 j = sm.next_2d();
+        float2 pfilm = f2(j.x + (float)px, j.y + (float)py);
+        float2 plens = sm.next_2d();
+        // PerspecCam::generate_path_differential, main ray
+        float3 pview = xform_point(p.raster_view, f3(pfilm.x, pfilm.y, 0.f));
+        float3 o = f3(0.f, 0.f, 0.f), d = normalize(pview);
+        if (p.has_lens) {
+            float2 dl = sample_concentric_disk(plens);
+            float2 pln = f2(p.lens_radius * dl.x, p.lens_radius * dl.y);
+            float ft = p.focal_distance / d.z;
+            float3 pfocus = o + d * ft;
+            o = f3(pln.x, pln.y, 0.f);
+            d = normalize(pfocus - o);
+        }
+        o = xform_point(p.view_parent, o); d = xform_vector(p.view_parent, d);
+        pb.ray_o[i] = make_float4(o.x, o.y, o.z, 0.f);
+        pb.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+        pb.beta[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+        pb.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb.pfilm[i] = pfilm;
+        pb.pix[i] = px | (py << 16);
+        pb.smp[i] = s;
+        pb.st[i] = (0u) | (0u << 8) | (0u << 16) | (2u << 24);
+        q.active[0][i] = i;
+    }
+}
+
+// ---- K2 extend: closest hit for every active path ------------------------------------------
+__global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
+    const uint32_t n = q.counts[cur];
+    const uint32_t* __restrict__ ids = q.active[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t pid = ids[i];
+        float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
+        TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
+        HitRec h;
+        traverse<false, false>(sc, r, h, nullptr);
+        pb.hit_prim[pid] = h.prim;
+        pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
+        if (h.prim >= 0 && (sc.prims[h.prim] & ARN_PRIM_SPHERE))   // `*ray = iray`: the ray leaves traversal round-tripped
+            pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&q.stats[0], (unsigned long long)n);
+        if (bounce > 0) atomicAdd(&q.stats[4], (unsigned long long)n);
+    }
+}
+
+// ---- K3 shade ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ARN_BLOCK) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
+    const uint32_t n = q.counts[cur];
+    const uint32_t* __restrict__ ids = q.active[cur];
+    uint32_t* next = q.active[cur ^ 1];
+    const uint32_t n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool alive = false, nee = false;
+        uint32_t pid = 0;
+        if (i < n) {
+            pid = ids[i];
+            int prim = pb.hit_prim[pid];
+            if (prim >= 0) {
+                float4 hr = pb.hit[pid];
+                float4 d4 = pb.ray_d[pid];
+                float3 raydir = f3(d4.x, d4.y, d4.z);
+                uint32_t st = pb.st[pid];
+                uint32_t bounces = st & 0xffu; bool spec = ((st >> 8) & 1u) != 0;
+                uint32_t pix = pb.pix[pid];
+                Sampler sm; sm.init(p.seed, pix & 0xffffu, pix >> 16, pb.smp[pid], (st >> 16) & 0xffu, st >> 24);
+                float4 b4 = pb.beta[pid]; float3 beta = f3(b4.x, b4.y, b4.z);
+                float4 l4 = pb.L[pid]; float3 L = f3(l4.x, l4.y, l4.z);
+                uint32_t ref = sc.prims[prim];
+                Surf s; uint32_t mat;
+                if (ref & ARN_PRIM_SPHERE) {
+                    const DevSphere& sp = sc.spheres[ref & ~ARN_PRIM_SPHERE];
+                    surf_sphere(sp, f3(hr.y, hr.z, hr.w), raydir, s);
+                    mat = sp.material;
+                    if ((bounces == 0 || spec) && sp.emissive) L = L + beta * light_le(sp, s.pos, -raydir);   // pt.rs:72-78
+                } else {
+                    surf_triangle(sc, ref, hr.y, hr.z, hr.w, raydir, s);
+                    mat = sc.meshes[sc.tri_mesh[ref]].material;
+                }
+                Bsdf bsdf; bsdf_build(sc.materials[mat], s, bsdf);
+                uint32_t flags = 0;
+                if (bsdf.n > 0) {                                           // pt.rs:85-91 (have_n(ALL-SPECULAR) > 0 <=> any lobe)
+                    // Scene::uniform_sample_one_light (scene.rs:58-66)
+                    float u1 = sm.next();
+                    float2 ulight = sm.next_2d();
+                    float2 uscatter = sm.next_2d();
+                    if (u1 == 0.f) u1 += ARN_EPS;                            // Distribution1D::search_offset
+                    uint32_t lo = 0, hi = sc.n_lights + 1;
+                    while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if (sc.light_cdf[mid] < u1) lo = mid + 1; else hi = mid; }
+                    uint32_t lidx = lo - 1;
+                    float lightpdf = sc.light_integral > 0.f ? sc.light_func[lidx] / sc.light_integral : 0.f;
+                    uint32_t lcomp = sc.light_prims[lidx];
+                    const DevSphere& light = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
+                    flags = NEE_DONE;
+                    // Scene::evaluate_direct (scene.rs:83-167): light sampling half
+                    LightSample ls = light_sample(light, s.pos, ulight);
+                    float3 wi = normalize(ls.pfrom - ls.pto);
+                    float3 A1 = grey(0.f);
+                    if (!(ls.pdf == 0.f || is_black(ls.radiance))) {
+                        float3 f = bsdf_eval(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns));
+                        float spdf = bsdf_pdf(bsdf, s.wo, wi);
+                        if (spdf == 0.f) f = grey(0.f);
+                        float weight = power_heuristic(ls.pdf, spdf);
+                        A1 = ls.radiance * f * weight / ls.pdf;
+                        if (!is_black(f)) {
+                            // LightSample::occluded (lighting/mod.rs:125-133) + RawRay::spawn (ray.rs:93-98)
+                            const float eps = ARN_EPS * 2.0f;
+                            float3 dir = ls.pto - ls.pfrom;
+                            float3 a = ls.pfrom + dir * eps;
+                            float3 b = ls.pto + (-dir * eps);
+                            float3 v = b - a;
+                            float len = length(v);
+                            float3 vd = v / len;
+                            pb.sh_o[pid] = make_float4(a.x, a.y, a.z, len);
+                            pb.sh_d[pid] = make_float4(vd.x, vd.y, vd.z, 0.f);
+                            flags |= NEE_SHADOW;
+                        }
+                    }
+                    // BSDF sampling half
+                    float3 A2 = grey(0.f);
+                    Sampled bs = bsdf_sample(bsdf, s.wo, uscatter);
+                    float3 f2v = bs.f * fabsf(dot(bs.wi, s.ns));
+                    if (!is_black(f2v) && bs.pdf > 0.f) {
+                        float weight = 1.f; bool skip = false;
+                        if (!(bs.type & BXDF_SPECULAR)) {
+                            float lpdf = light_pdf(light, s.pos, bs.wi);
+                            if (lpdf == 0.f) skip = true; else weight = power_heuristic(bs.pdf, lpdf);
+                        }
+                        if (!skip) {
+                            float3 mo = offset_towards(s, bs.wi);
+                            A2 = f2v * sphere_emission(light) * weight / bs.pdf;
+                            pb.mis_o[pid] = make_float4(mo.x, mo.y, mo.z, 0.f);
+                            pb.mis_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                            flags |= NEE_MIS;
+                        }
+                    }
+                    pb.a1[pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
+                    pb.a2[pid] = make_float4(A2.x, A2.y, A2.z, __uint_as_float(lcomp));
+                    pb.beta_old[pid] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(flags));
+                    nee = true;
+                }
+                // sample the BSDF for the next direction (pt.rs:92-107)
+                float3 wo = -raydir;
+                Sampled bs = bsdf_sample(bsdf, wo, sm.next_2d());
+                spec = (bs.type & BXDF_SPECULAR) != 0;
+                alive = !(is_black(bs.f) || bs.pdf == 0.f);
+                if (alive) {
+                    beta = beta * (bs.f * (fabsf(dot(bs.wi, s.ns)) / bs.pdf));
+                    bool valid = !(isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) && !(isinf(beta.x) || isinf(beta.y) || isinf(beta.z))
+                                 && beta.x >= 0.f && beta.y >= 0.f && beta.z >= 0.f;
+                    if (!valid) alive = false;
+                }
+                if (alive) {
+                    float3 no = offset_towards(s, bs.wi);
+                    pb.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f);
+                    pb.ray_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                    bounces += 1;
+                    if (bounces >= p.max_depth) alive = false;
+                }
+                if (alive) {                                               // Russian roulette (pt.rs:117-122)
+                    float y = 0.212671f * beta.x + 0.715160f * beta.y + 0.072169f * beta.z;
+                    if (y < p.rr_threshold && bounces >= p.min_depth) {
+                        float qq = fmaxf(p.rr_threshold, 0.05f);
+                        if (sm.next() < qq) alive = false;
+                        else beta = beta / (1.f - qq);
+                    }
+                }
+                pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
+                if (alive) {
+                    pb.beta[pid] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    pb.st[pid] = (bounces & 0xffu) | ((spec ? 1u : 0u) << 8) | ((sm.i1d & 0xffu) << 16) | (sm.i2d << 24);
+                }
+            }
+        }
+        queue_append(alive, pid, next, &q.counts[cur ^ 1]);
+        queue_append(nee, pid, q.connect, &q.counts[2]);
+    }
+}
+
+// ---- K4 connect: shadow ray (any hit) + BSDF-sampled light ray (closest hit), then resolve -----
+__global__ void __launch_bounds__(ARN_BLOCK) k_connect(DevScene sc, PathBuf pb, Queues q) {
+    const uint32_t n = q.counts[2];
+    unsigned long long n_sh = 0, n_mis = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t pid = q.connect[i];
+        float4 bo = pb.beta_old[pid];
+        uint32_t flags = __float_as_uint(bo.w);
+        float4 a1 = pb.a1[pid], a2 = pb.a2[pid];
+        float3 ret = f3(a1.x, a1.y, a1.z);
+        if (flags & NEE_SHADOW) {
+            float4 o = pb.sh_o[pid], d = pb.sh_d[pid];
+            TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
+            HitRec h; traverse<true, false>(sc, r, h, nullptr);
+            if (h.prim >= 0) ret = grey(0.f);
+            n_sh++;
+        }
+        if (flags & NEE_MIS) {
+            float4 o = pb.mis_o[pid], d = pb.mis_d[pid];
+            float3 wi = f3(d.x, d.y, d.z);
+            TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
+            HitRec h; traverse<false, false>(sc, r, h, nullptr);
+            uint32_t lcomp = __float_as_uint(a2.w);
+            n_mis++;
+            if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
+                const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
+                float3 pos = f3(h.a, h.b, h.c);
+                if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
+                float3 li = light_le(sp, pos, -wi);                       // lsi.le(-wi)
+                if (!is_black(li)) ret = ret + f3(a2.x, a2.y, a2.z);
+            }
+        }
+        float3 term = ret / a1.w;                                        // evaluate_direct(..) / lightpdf
+        float4 l4 = pb.L[pid];
+        float3 L = f3(l4.x, l4.y, l4.z) + f3(bo.x, bo.y, bo.z) * term;   // ret += beta * term (pt.rs:89)
+        pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
+    }
+    // warp-aggregated statistics
+    for (int off = 16; off > 0; off >>= 1) { n_sh += __shfl_down_sync(0xffffffffu, n_sh, off); n_mis += __shfl_down_sync(0xffffffffu, n_mis, off); }
+    if ((threadIdx.x & 31) == 0) { if (n_sh) atomicAdd(&q.stats[1], n_sh); if (n_mis) atomicAdd(&q.stats[2], n_mis); }
+}
+
+// resets the queue counters between bounces (single thread)
+__global__ void k_next_bounce(Queues q, int cur) { q.counts[cur] = 0; q.counts[2] = 0; }
+__global__ void k_begin_wave(Queues q, uint32_t n) { q.counts[0] = n; q.counts[1] = 0; q.counts[2] = 0; }
+
+// ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
+ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return sinf(xpi) / xpi; }
+ARN_DEV float lanczos1(float x) { return sinc1(x * (1.f / 3.f)) * sinc1(x); }        // tau = 3 (film.rs:47-51)
+
+__global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
+    unsigned long long invalid = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 l4 = pb.L[i];
+        float3 L = f3(l4.x, l4.y, l4.z);
+        bool valid = !(isnan(L.x) || isnan(L.y) || isnan(L.z)) && !(isinf(L.x) || isinf(L.y) || isinf(L.z)) && L.x >= 0.f && L.y >= 0.f && L.z >= 0.f;
+        if (!valid) { L = grey(0.f); invalid++; }                       // pt.rs:152-156
+        float2 pos = pb.pfilm[i];
+        float cx = pos.x - p.fr_x + 0.5f, cy = pos.y - p.fr_y + 0.5f;
+        float fx = pos.x + p.fr_x - 0.5f, fy = pos.y + p.fr_y - 0.5f;
+        int x0 = (int)cx, y0 = (int)cy, x1 = (int)fx + 1, y1 = (int)fy + 1;   // truncation toward zero
+        if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
+        if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
+        // the tile sink (tile grown by the radius, clipped to the crop window) never clips more
+        // than the crop window does for samples inside the tile (DESIGN.md "Film")
+        x0 = max(x0, p.crop_x0); y0 = max(y0, p.crop_y0); x1 = min(x1, p.crop_x0 + p.crop_w); y1 = min(y1, p.crop_y0 + p.crop_h);
+        for (int y = y0; y < y1; y++) {
+            float wy = lanczos1(((float)y + 0.5f) - pos.y);
+            for (int x = x0; x < x1; x++) {
+                float wx = lanczos1(((float)x + 0.5f) - pos.x);
+                float w = wx * wy;
+                float3 c = L * w;
+                atomicAdd(&film[(size_t)(y - p.crop_y0) * (size_t)p.crop_w + (size_t)(x - p.crop_x0)], make_float4(c.x, c.y, c.z, w));
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) invalid += __shfl_down_sync(0xffffffffu, invalid, off);
+    if ((threadIdx.x & 31) == 0 && invalid) atomicAdd(&q.stats[3], invalid);
+}
+
+// ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(ARN_BLOCK) k_closest_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
+                                                             unsigned long long* ctr_out) {
+    uint32_t ctr[3] = {0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        arn_ray ry = rays[i];
+        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        HitRec h; traverse<false, COUNT>(sc, r, h, ctr);
+        arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? h.t : ARN_INF;
+        hits[i] = o;
+    }
+    if (COUNT) {
+        unsigned long long a = ctr[0], b = ctr[1], c = ctr[2];
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); c += __shfl_down_sync(0xffffffffu, c, off); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr_out[0], a); atomicAdd(&ctr_out[1], b); atomicAdd(&ctr_out[2], c); }
+    }
+}
+__global__ void __launch_bounds__(ARN_BLOCK) k_any_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        arn_ray ry = rays[i];
+        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        HitRec h; traverse<true, false>(sc, r, h, nullptr);
+        out[i] = h.prim >= 0 ? 1 : 0;
+    }
+}
+
+}  // namespace arn

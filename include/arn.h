@@ -1,0 +1,273 @@
+/* arn.h — C-ABI of the B200-native path-tracing core for arendur.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * C++/torch types.  A Rust shim implementing arendur's `Renderer` / `Composable`
+ * traits binds exactly these entry points (see INTEGRATION.md for the `extern "C"`
+ * block).  Every entry point cites the reference interface it replaces
+ * (paths relative to the arendur source tree).
+ *
+ * Conventions
+ *   - every function returns an `int` status: ARN_OK (0) or a negative ARN_E_* code;
+ *     a human-readable message for the last failure on a context is available through
+ *     arn_last_error().  Nothing ever unwinds across this boundary (the reference
+ *     panics instead: `assert!/expect/unwrap`, e.g. component/bvh.rs:103,117).
+ *   - all floating point is IEEE f32 (reference: geometry/foundamental.rs:15).
+ *   - matrices are 16 floats, COLUMN-major, as cgmath's Matrix4 (x,y,z,w columns).
+ *   - a miss is prim_id = -1, t = +inf.
+ *   - handles are opaque; the caller owns every host buffer it passes in; uploads copy.
+ */
+#ifndef ARN_H_
+#define ARN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARN_OK             0
+#define ARN_E_INVALID     -1   /* bad argument / inconsistent description          */
+#define ARN_E_CUDA        -2   /* CUDA runtime error (message has the cuda string) */
+#define ARN_E_OOM         -3   /* host or device allocation failed                 */
+#define ARN_E_IO          -4   /* file could not be read / parsed                  */
+#define ARN_E_UNSUPPORTED -5   /* valid in arendur but outside this hot path       */
+
+/* ---------------------------------------------------------------- flattened scene */
+
+/* One BVH node, 32 bytes, 32-byte aligned on the device.
+ * Replaces `LinearNode` (component/bvh.rs:136-146; 48 B in Rust).
+ *   interior: (len_axis >> 2) == 0, `offset` = distance to the second child
+ *             (first child is the next node, pre-order), axis = len_axis & 3 in 0..2
+ *   leaf    : len = len_axis >> 2 > 0, `offset` = first slot in the ordered primitive
+ *             list, len_axis & 3 == 3 (the reference stores split_axis = 4). */
+typedef struct arn_node {
+    float    bmin[3];
+    float    bmax[3];
+    uint32_t offset;
+    uint32_t len_axis;
+} arn_node;
+
+#define ARN_PRIM_SPHERE 0x80000000u   /* component reference: high bit = sphere table */
+
+/* BVH build strategy — `BVHStrategy` (component/bvh.rs:40-47). */
+#define ARN_BVH_SAH         0
+#define ARN_BVH_MIDDLECOUNT 1
+#define ARN_BVH_MIDPOINT    2
+
+/* Material record — the four materials `load_obj`/arencli can produce
+ * (component/mod.rs:139-164, material/{matte,plastic,glass,translucent}.rs), with
+ * constant textures only (texturing/textures/mod.rs:16-33).
+ * `alpha` = roughness_to_alpha(roughness) (bxdf/microfacet.rs:57-63), evaluated once
+ * on the host. */
+#define ARN_MAT_MATTE       0
+#define ARN_MAT_PLASTIC     1
+#define ARN_MAT_GLASS       2
+#define ARN_MAT_TRANSLUCENT 3
+typedef struct arn_material {
+    uint32_t type;
+    float    kd[3];       /* Matte kd / diffuse                                  */
+    float    ks[3];       /* specular                                            */
+    float    sigma;       /* Matte: Oren–Nayar sigma, already clamped to [0,90]  */
+    float    roughness;
+    float    alpha;
+    float    eta;         /* Glass: optical density                              */
+    float    dissolve;    /* Translucent                                         */
+} arn_material;           /* 48 bytes */
+
+/* Mesh record: one `TriangleMesh` (shape/triangle.rs:26-36).  Vertices are already
+ * in world space (from_model_transformed, triangle.rs:120-160). */
+typedef struct arn_mesh {
+    uint32_t material;
+    uint32_t has_normals;
+    uint32_t has_uvs;
+    uint32_t reserved;
+} arn_mesh;
+
+/* Sphere primitive: `ShapedPrimitive<Sphere, _>` (component/shape.rs:21-26) optionally
+ * wrapped in `TransformedComposable` (component/transformed.rs:20-24). */
+typedef struct arn_sphere {
+    float    radius, zmin, zmax, phimax, thetamin, thetamax;  /* shape/sphere.rs:19-31 */
+    uint32_t material;
+    uint32_t has_transform;   /* 0: bare ShapedPrimitive (no ray round trip)           */
+    uint32_t emissive;        /* lighting_profile.is_some()                            */
+    float    emission[3];     /* constant emission texture value                       */
+    float    local_parent[16];
+    float    parent_local[16];
+} arn_sphere;
+
+/* Everything `Scene::new(lights, BVH::new(components, SAH))` holds
+ * (renderer/scene.rs:23-51, component/bvh.rs:49-79), flattened. */
+typedef struct arn_scene_desc {
+    /* triangle soup: TriangleMesh::{vertices, indices, normals, uvs}            */
+    uint32_t        n_vertices;
+    const float*    positions;     /* n_vertices * 3, world space                */
+    const float*    normals;       /* n_vertices * 3 or NULL (per-mesh flag says if valid) */
+    const float*    uvs;           /* n_vertices * 2 or NULL                     */
+    uint32_t        n_triangles;
+    const uint32_t* indices;       /* n_triangles * 3 into the vertex arrays     */
+    const uint32_t* tri_mesh;      /* n_triangles: mesh id of each triangle      */
+    uint32_t        n_meshes;
+    const arn_mesh* meshes;
+    uint32_t        n_spheres;
+    const arn_sphere* spheres;
+    uint32_t        n_materials;
+    const arn_material* materials;
+    /* component list in the order handed to BVH::new: entry = triangle index, or
+     * ARN_PRIM_SPHERE | sphere index.  prim_id in every hit indexes THIS list.   */
+    uint32_t        n_prims;
+    const uint32_t* prims;
+    /* flattened BVH (arn_bvh_build output, or the Rust side's own BVH flattened) */
+    uint32_t        n_nodes;
+    const arn_node* nodes;
+    const uint32_t* order;         /* n_prims: ordered slot -> index into prims   */
+    /* lights = emissive primitives, in `Scene.lights` order, with the power
+     * distribution of Scene::new (renderer/scene.rs:31-51, sample/distribution.rs:25-63) */
+    uint32_t        n_lights;
+    const uint32_t* light_prims;   /* n_lights: index into prims                  */
+    const float*    light_func;    /* n_lights: power().to_xyz().y                */
+    const float*    light_cdf;     /* n_lights + 1                                */
+    float           light_func_integral;
+} arn_scene_desc;
+
+/* `PerspecCam` (filming/perspective.rs:25-38) reduced to what ray generation reads
+ * (perspective.rs:292-320): raster_view = inverse(view_screen) * raster_screen
+ * (filming/projective.rs:29-37) and view_parent. */
+typedef struct arn_camera {
+    float    raster_view[16];
+    float    view_parent[16];
+    uint32_t has_lens;
+    float    lens_radius;
+    float    focal_distance;
+} arn_camera;
+
+/* `Film` (filming/film.rs:38-45); the filter is always Lanczos(radius (4,4), tau 3)
+ * after deserialisation (film.rs:42,47-51); filter_radius only sizes the splat box. */
+typedef struct arn_film {
+    uint32_t res_x, res_y;
+    int32_t  crop_min_x, crop_min_y, crop_max_x, crop_max_y;  /* pixels, max exclusive */
+    float    filter_radius_x, filter_radius_y;
+} arn_film;
+
+/* Sampler: `StrataSampler{sampledx, sampledy, ndim}` (sample/strata.rs:25-31) gives the
+ * sample count; the draws themselves come from the counter-based ParitySampler
+ * (DESIGN.md "Sampler"). */
+typedef struct arn_sampler {
+    uint32_t sampledx, sampledy, ndim;
+    uint32_t seed;
+} arn_sampler;
+
+/* `PTRenderer` constants (renderer/pt.rs:37-52): rr_threshold = 0.05,
+ * min_depth = max_depth / 2. Tiles: film.spawn_tiles(16,16) (pt.rs:131). */
+typedef struct arn_pt_params {
+    uint32_t max_depth;
+    uint32_t min_depth;
+    float    rr_threshold;
+    uint32_t tiles_x, tiles_y;   /* tile grid for multi-GPU partitioning (16,16)       */
+    uint32_t rank, world_size;   /* this context renders tiles t with t % world == rank */
+    uint32_t spp_begin, spp_end; /* sample index range to render, [0, spp) for all      */
+} arn_pt_params;
+
+typedef struct arn_ray {
+    float o[3];
+    float d[3];
+    float tmax;
+} arn_ray;                       /* 28 bytes: RawRay (geometry/ray.rs:64-69) minus the cache */
+
+typedef struct arn_hit {
+    int32_t prim_id;             /* index into arn_scene_desc.prims, -1 = miss */
+    float   t;
+} arn_hit;
+
+typedef struct arn_stats {
+    uint64_t camera_rays;        /* camera samples generated                               */
+    uint64_t extend_rays;        /* closest-hit traversals on path rays (incl. camera rays) */
+    uint64_t shadow_rays;        /* LightSample::occluded traversals                        */
+    uint64_t mis_rays;           /* BSDF-sampled light rays (scene.rs:146)                  */
+    uint64_t invalid_samples;    /* radiance replaced by black (pt.rs:152-156)              */
+    uint64_t kernel_launches;    /* kernels of this library launched by the call            */
+    double   gpu_ms;             /* device time of the call, CUDA events                    */
+    double   extend_ms;          /* device time spent in closest-hit kernels (path rays)    */
+    double   extend_bounce_ms;   /* ... of which for bounces >= 1 (incoherent)              */
+    uint64_t extend_bounce_rays; /* path rays of bounces >= 1                               */
+} arn_stats;
+
+typedef struct arn_ctx   arn_ctx;
+typedef struct arn_scene arn_scene;
+
+/* ---------------------------------------------------------------- host-only pieces */
+
+/* Build the reference's BVH over `n` components given their parent-space bounds
+ * (bounds6 = pmin.xyz, pmax.xyz per component) and `intersection_cost()` values.
+ * Replaces BVH::new + recursive_build + BuildNode::flatten
+ * (component/bvh.rs:58-79,246-465,219-243) INCLUDING its SAH quirks, so that the
+ * tree, the primitive order and therefore every tie-break equal the reference's.
+ * nodes_out must hold 2*n-1 nodes, order_out n entries. */
+int arn_bvh_build(uint32_t n, const float* bounds6, const float* costs, int strategy,
+                  arn_node* nodes_out, uint32_t* order_out, uint32_t* n_nodes_out);
+
+/* Scene::new's light distribution: Distribution1D::new (sample/distribution.rs:25-63).
+ * cdf_out has n+1 entries. */
+int arn_light_distribution(uint32_t n, const float* func, float* cdf_out, float* integral_out);
+
+/* TilePixel::finalize + ToNorm<u8> (filming/film.rs:338-344, spectrum/macros.rs:164-180):
+ * film = n_pixels * float4 (sum r,g,b, weight sum).  rgb_out (n*3 floats) and/or
+ * rgb8_out (n*3 bytes) may be NULL. */
+int arn_film_finalize(const float* film, size_t n_pixels, float* rgb_out, uint8_t* rgb8_out);
+
+/* ---------------------------------------------------------------- device contexts */
+
+/* One context per GPU / rank; owns a stream set and the wavefront queues. */
+int  arn_ctx_create(int device, arn_ctx** out);
+void arn_ctx_destroy(arn_ctx* ctx);
+const char* arn_last_error(const arn_ctx* ctx);   /* ctx may be NULL: last global error */
+
+/* Upload a flattened scene (copies; desc buffers may be freed afterwards).
+ * The handle is immutable and may be used from any host thread. */
+int  arn_scene_upload(arn_ctx* ctx, const arn_scene_desc* desc, arn_scene** out);
+void arn_scene_destroy(arn_scene* scene);
+
+/* Batched `Composable::intersect_ray` on the aggregate (component/bvh.rs:97-128):
+ * closest hit for n rays.  HOST buffers; copies are part of the call. */
+int arn_intersect_closest(arn_scene* scene, const arn_ray* rays, size_t n, arn_hit* hits_out);
+/* Batched `Composable::can_intersect` (component/mod.rs:35-38): 1 = occluded. */
+int arn_intersect_any(arn_scene* scene, const arn_ray* rays, size_t n, uint8_t* out);
+
+/* Same with DEVICE buffers, asynchronous on the context's stream; `stats` may be NULL.
+ * rays_dev: n * 28 B, hits_dev: n * 8 B. */
+int arn_intersect_closest_dev(arn_scene* scene, const void* rays_dev, size_t n, void* hits_dev,
+                              arn_stats* stats);
+int arn_intersect_any_dev(arn_scene* scene, const void* rays_dev, size_t n, void* out_dev,
+                          arn_stats* stats);
+
+/* Instrumented closest-hit pass over DEVICE buffers: counters_out[0..2] = BVH nodes tested,
+ * triangles tested, spheres tested, summed over the batch — the Nn / Nt of the
+ * algorithmic-bytes figure.  Synchronous. */
+int arn_intersect_closest_counted_dev(arn_scene* scene, const void* rays_dev, size_t n, void* hits_dev,
+                                      uint64_t* counters_out);
+
+/* `PTRenderer::render` (renderer/pt.rs:128-176) up to and including the tile merge
+ * (`Film::collect_into`, film.rs:171-183) but before finalize: accumulates
+ * (sum r, sum g, sum b, weight sum) per crop-window pixel, row-major, into `film_out`
+ * (HOST, crop_w * crop_h * 4 floats, overwritten). */
+int arn_render_pt(arn_scene* scene, const arn_camera* cam, const arn_film* film,
+                  const arn_sampler* sampler, const arn_pt_params* params,
+                  float* film_out, arn_stats* stats);
+/* Device-resident variant: film_dev is a DEVICE buffer that is ACCUMULATED into
+ * (caller zeroes it); used for multi-GPU, where the caller reduces the per-rank films
+ * (Film::merge_into semantics, film.rs:82-101) with NCCL. */
+int arn_render_pt_dev(arn_scene* scene, const arn_camera* cam, const arn_film* film,
+                      const arn_sampler* sampler, const arn_pt_params* params,
+                      void* film_dev, arn_stats* stats);
+
+int arn_ctx_synchronize(arn_ctx* ctx);
+/* The context's CUDA stream as a cudaStream_t cast to void* (for event timing). */
+void* arn_ctx_stream(arn_ctx* ctx);
+
+/* Library identification: "arendur_b200 <version> sm_100a". */
+const char* arn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARN_H_ */
