@@ -91,7 +91,7 @@ ARN_H_SYMBOLS = [
     "arn_bvh_build", "arn_light_distribution", "arn_film_finalize", "arn_ctx_create", "arn_ctx_destroy",
     "arn_last_error", "arn_scene_upload", "arn_scene_destroy", "arn_intersect_closest", "arn_intersect_any",
     "arn_intersect_closest_dev", "arn_intersect_any_dev", "arn_intersect_closest_counted_dev",
-    "arn_render_pt", "arn_render_pt_dev", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
+    "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
@@ -129,6 +129,7 @@ def load():
         "arn_intersect_closest_counted_dev": (C.c_int, [vp, vp, C.c_size_t, vp, C.POINTER(C.c_uint64)]),
         "arn_render_pt": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, C.POINTER(Stats)]),
         "arn_render_pt_dev": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, C.POINTER(Stats)]),
+        "arn_render_pt_samples": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, vp, C.POINTER(Stats)]),
         "arn_ctx_synchronize": (C.c_int, [vp]),
         "arn_ctx_stream": (vp, [vp]),
         "arn_version": (C.c_char_p, []),

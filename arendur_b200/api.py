@@ -268,6 +268,18 @@ class Scene:
         self._check(self.lib.arn_render_pt(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _ptr(out), C.byref(st)))
         return out, st
 
+    def render_pt_samples(self, cam, film, sampler, params):
+        """Diagnostic: (film, per-sample radiance (h, w, n_spp, 4), Stats)."""
+        w = film.crop_max_x - film.crop_min_x
+        h = film.crop_max_y - film.crop_min_y
+        spp = sampler.sampledx * sampler.sampledy
+        n = (params.spp_end or spp) - params.spp_begin
+        out = np.zeros((h, w, 4), dtype=np.float32)
+        rad = np.zeros((h, w, n, 4), dtype=np.float32)
+        st = L.Stats()
+        self._check(self.lib.arn_render_pt_samples(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _ptr(out), _ptr(rad), C.byref(st)))
+        return out, rad, st
+
     def render_pt_dev(self, cam, film, sampler, params, film_dev_ptr, want_stats=True):
         st = L.Stats()
         self._check(self.lib.arn_render_pt_dev(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params),

@@ -48,6 +48,7 @@ struct arn_scene {
     DevScene dev{};
     std::vector<void*> allocs;
     uint32_t max_depth = 0;
+    uint32_t class_mask = 0;     // shading classes present in the material table
     uint64_t bytes = 0;
 };
 
@@ -96,6 +97,7 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     size_t o_sho = carve(cap * 16), o_shd = carve(cap * 16), o_mo = carve(cap * 16), o_md = carve(cap * 16);
     size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16);
     size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4);
+    size_t o_cls[ARN_NCLS]; for (int k = 0; k < ARN_NCLS; k++) o_cls[k] = carve(cap * 4);
     size_t o_counts = carve(64), o_stats = carve(64);
     CUDA_TRY(c, cudaMalloc(&c->pool, off));
     c->pool_bytes = off;
@@ -106,6 +108,7 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     c->pb.sh_o = (float4*)(b + o_sho); c->pb.sh_d = (float4*)(b + o_shd); c->pb.mis_o = (float4*)(b + o_mo); c->pb.mis_d = (float4*)(b + o_md);
     c->pb.a1 = (float4*)(b + o_a1); c->pb.a2 = (float4*)(b + o_a2); c->pb.beta_old = (float4*)(b + o_bo);
     c->q.active[0] = (uint32_t*)(b + o_q0); c->q.active[1] = (uint32_t*)(b + o_q1); c->q.connect = (uint32_t*)(b + o_qc);
+    for (int k = 0; k < ARN_NCLS; k++) c->q.cls[k] = (uint32_t*)(b + o_cls[k]);
     c->q.counts = (uint32_t*)(b + o_counts); c->q.stats = (unsigned long long*)(b + o_stats);
     c->wave_cap = cap;
     return ARN_OK;
@@ -259,6 +262,11 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if ((rc = dev_upload(s, d->light_prims, d->n_lights, &s->dev.light_prims)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_func, d->n_lights, &s->dev.light_func)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_cdf, d->n_lights ? d->n_lights + 1 : 0, &s->dev.light_cdf)) != ARN_OK) return fail(rc);
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const arn_material& m = d->materials[i];
+        int cls = m.type == ARN_MAT_MATTE ? (!(m.sigma >= 0.f && m.sigma != 0.f) && !(m.sigma != m.sigma) ? 0 : 1) : (m.type == ARN_MAT_PLASTIC ? 2 : (m.type == ARN_MAT_GLASS ? 3 : 4));
+        s->class_mask |= 1u << cls;
+    }
     s->dev.light_integral = d->light_func_integral;
     s->dev.n_lights = d->n_lights; s->dev.n_nodes = d->n_nodes; s->dev.n_prims = d->n_prims; s->dev.n_spheres = d->n_spheres;
     cudaError_t e = cudaStreamSynchronize(c->stream);     // the staging vector `slots` dies here
@@ -356,8 +364,8 @@ int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t
 }
 
 // ---------------------------------------------------------------- path tracer
-int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
-                      const arn_pt_params* prm, void* film_dev, arn_stats* stats) {
+static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                          const arn_pt_params* prm, void* film_dev, arn_stats* stats, float4* radiance_dev) {
     if (!s || !cam || !film || !smp || !prm || !film_dev) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt: NULL argument");
     arn_ctx* c = s->ctx; cudaSetDevice(c->device);
     if (s->dev.n_lights == 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: the scene has no lights (the reference indexes lights[0] and panics, renderer/scene.rs:53-55)");
@@ -427,14 +435,16 @@ int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film,
             if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, (int)b}); }
             k_extend<<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
-            k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur);
+            for (int cls = 0; cls < ARN_NCLS; cls++)
+                if (s->class_mask & (1u << cls)) { k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur, cls); launches++; }
             k_connect<<<c->g_connect, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q);
             k_next_bounce<<<1, 1, 0, c->stream>>>(c->q, cur);
-            launches += 4;
+            launches += 3;
             cur ^= 1;
         }
         k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
         launches += 1;
+        if (radiance_dev) { k_store_radiance<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, radiance_dev, n); launches += 1; }
         CUDA_TRY(c, cudaGetLastError());
     }
     cudaEventRecord(e_end, c->stream);
@@ -451,6 +461,37 @@ int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film,
         stats->extend_ms = ext; stats->extend_bounce_ms = extb;
     }
     return ARN_OK;
+}
+
+int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                      const arn_pt_params* prm, void* film_dev, arn_stats* stats) {
+    return render_pt_impl(s, cam, film, smp, prm, film_dev, stats, nullptr);
+}
+
+// Diagnostic twin of arn_render_pt: additionally returns the radiance of every camera sample,
+// radiance_out[((y*crop_w + x)*n_spp + s)*4 .. +3] (HOST, pixels of other ranks' tiles stay 0).
+int arn_render_pt_samples(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                          const arn_pt_params* prm, float* film_out, float* radiance_out, arn_stats* stats) {
+    if (!s || !film || !smp || !prm || !film_out || !radiance_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt_samples: NULL argument");
+    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    long cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
+    uint32_t spp = smp->sampledx * smp->sampledy; uint32_t s0 = prm->spp_begin, s1 = prm->spp_end ? prm->spp_end : spp;
+    if (cw <= 0 || chh <= 0 || s1 <= s0) return set_err(c, ARN_E_INVALID, "arn_render_pt_samples: empty crop window or sample range");
+    size_t fbytes = (size_t)cw * chh * 16, rbytes = fbytes * (s1 - s0);
+    void *d_film = nullptr, *d_rad = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d_film, fbytes));
+    if (cudaMalloc(&d_rad, rbytes) != cudaSuccess) { cudaFree(d_film); return set_err(c, ARN_E_OOM, "arn_render_pt_samples: radiance buffer"); }
+    cudaMemsetAsync(d_film, 0, fbytes, c->stream); cudaMemsetAsync(d_rad, 0, rbytes, c->stream);
+    arn_stats local;
+    int rc = render_pt_impl(s, cam, film, smp, prm, d_film, stats ? stats : &local, (float4*)d_rad);
+    if (rc == ARN_OK) {
+        cudaMemcpyAsync(film_out, d_film, fbytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(radiance_out, d_rad, rbytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_err(c, ARN_E_CUDA, std::string("download: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_film); cudaFree(d_rad);
+    return rc;
 }
 
 int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,

@@ -185,7 +185,7 @@ extern "C" int arn_bvh_build(uint32_t n, const float* bounds6, const float* cost
 
 // Distribution1D::new (src/sample/distribution.rs:25-63)
 extern "C" int arn_light_distribution(uint32_t n, const float* func, float* cdf_out, float* integral_out) {
-    if (!func || !cdf_out || !integral_out) return ARN_E_INVALID;
+    if ((n && !func) || !cdf_out || !integral_out) return ARN_E_INVALID;
     for (uint32_t i = 0; i < n; i++) if (!(func[i] >= 0.f)) return ARN_E_INVALID;   // assert!(curfunc >= 0)
     cdf_out[0] = 0.f;
     for (uint32_t i = 0; i < n; i++) cdf_out[i + 1] = cdf_out[i] + func[i];

@@ -14,7 +14,7 @@ namespace arnhost {
 // bxdf/microfacet.rs:57-63
 inline float roughness_to_alpha(float roughness) {
     float r = roughness > 1e-3f ? roughness : 1e-3f;   // f32::max
-    float x = std::log(r);
+    float x = (float)std::log((double)r);              // correctly-rounded f32 (see kernels/dev_math.cuh)
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
@@ -104,7 +104,7 @@ public:
         const float twopi = 3.14159265358979323846f * 2.0f;
         if (phimax > twopi) phimax = twopi;
         s.radius = radius; s.zmin = zmin; s.zmax = zmax; s.phimax = phimax;
-        s.thetamin = std::acos(zmin / radius); s.thetamax = std::acos(zmax / radius);
+        s.thetamin = (float)std::acos((double)(zmin / radius)); s.thetamax = (float)std::acos((double)(zmax / radius));
         s.material = material;
         if (emission3) { s.emissive = 1; s.emission[0] = emission3[0]; s.emission[1] = emission3[1]; s.emission[2] = emission3[2]; }
         Mat4 lp = Mat4::identity(), pl = Mat4::identity();

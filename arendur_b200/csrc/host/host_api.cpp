@@ -171,7 +171,7 @@ int arn_camera_make(const float* parent_view16, const float* screen4, float znea
     Mat4 persp; std::memset(&persp, 0, sizeof persp);
     persp.c[0][0] = 1.f; persp.c[1][1] = 1.f; persp.c[2][2] = zfar / (zfar - znear); persp.c[2][3] = 1.f;
     persp.c[3][2] = -zfar * znear / (zfar - znear); persp.c[3][3] = 0.f;
-    float inv_tan = 1.f / std::tan(fov * 0.5f);
+    float inv_tan = 1.f / (float)std::tan((double)(fov * 0.5f));
     Mat4 view_screen = Mat4::scale(inv_tan, inv_tan, 1.f) * persp;
     // ProjCameraInfo::new (filming/projective.rs:24-45)
     Mat4 raster_screen = Mat4::translation(screen4[0], screen4[3], 0.f)

@@ -9,6 +9,8 @@
 
 #define ARN_DEV __device__ __forceinline__
 #define ARN_INF __int_as_float(0x7f800000)
+// one out-of-line copy per translation unit: keeps the shade kernel inside the instruction cache
+#define ARN_NOINL static __device__ __noinline__
 
 namespace arn {
 
@@ -65,6 +67,19 @@ ARN_DEV bool relative_eq(float a, float b) {     // approx::relative_eq!, eps = 
     float la = fabsf(a), lb = fabsf(b);
     return d <= (lb > la ? lb : la) * ARN_EPS;
 }
+
+// Transcendentals that can steer a discrete decision (ray geometry, lobe / branch choice) are
+// evaluated as correctly-rounded f32 via f64, exactly like the oracle (oracle/geom.hpp): the
+// f32 libdevice versions differ from libm by an ulp, which flips ~1 % of the paths through
+// borderline shadow-ray self-intersections (the reference pulls shadow-ray ends in by only
+// 2*eps).  B200's FP64 pipe runs at half the FP32 rate, so this costs a few % of shading time.
+ARN_NOINL float cr_sinf(float x) { return (float)sin((double)x); }
+ARN_NOINL float cr_cosf(float x) { return (float)cos((double)x); }
+ARN_NOINL float cr_acosf(float x) { return (float)acos((double)x); }
+ARN_NOINL float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+ARN_NOINL float cr_logf(float x) { return (float)log((double)x); }
+ARN_NOINL float cr_expf(float x) { return (float)exp((double)x); }
+ARN_NOINL float cr_powf(float a, float b) { return (float)pow((double)a, (double)b); }
 
 // column-major 4x4 (cgmath): transform_point with homogeneous divide, transform_vector
 struct Mat4 { float m[16]; };

@@ -95,11 +95,11 @@ ARN_DEV void surf_triangle(const DevScene& sc, uint32_t tri, float b0, float b1,
 ARN_DEV void surf_sphere(const DevSphere& sp, float3 p, float3 raydir_after, Surf& s) {
     float phimax = sp.phimax;
     float thetadelta = sp.thetamax - sp.thetamin;
-    float theta = acosf(p.z / sp.radius);
+    float theta = cr_acosf(p.z / sp.radius);
     float inv_z_radius = 1.f / sqrtf(p.x * p.x + p.y * p.y);
     float cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
     float3 dpdu = f3(-phimax * p.y, phimax * p.x, 0.f);
-    float3 dpdv = thetadelta * f3(p.z * cos_phi, p.z * sin_phi, -sp.radius * sinf(theta));
+    float3 dpdv = thetadelta * f3(p.z * cos_phi, p.z * sin_phi, -sp.radius * cr_sinf(theta));
     float3 n = normalize(cross(dpdu, dpdv));
     if (sp.has_transform) {
         s.pos = xform_point(sp.local_parent, p);
@@ -152,7 +152,7 @@ ARN_DEV float2 sample_concentric_disk(float2 u) {
     float r, theta;
     if (fabsf(w.x) > fabsf(w.y)) { r = w.x; theta = ARN_PI_4 * (w.y / w.x); }
     else { r = w.y; theta = ARN_PI_2 - ARN_PI_4 * (w.x / w.y); }
-    return f2(r * cosf(theta), r * sinf(theta));
+    return f2(r * cr_cosf(theta), r * cr_sinf(theta));
 }
 ARN_DEV float3 sample_cosw_hemisphere(float2 u) {
     float2 d = sample_concentric_disk(u);
@@ -168,7 +168,7 @@ ARN_DEV float power_heuristic(float pdff, float pdfg) {
 ARN_DEV float powi5(float x) { float x2 = x * x; float x4 = x2 * x2; return x * x4; }   // llvm.powi(x, 5)
 ARN_DEV float erf_inv(float x) {
     x = fminf(fmaxf(x, -0.99999f), 0.99999f);
-    float w = -logf((1.f - x) * (1.f + x));
+    float w = -cr_logf((1.f - x) * (1.f + x));
     float p;
     if (w < 5.f) {
         w = w - 2.5f;
@@ -188,14 +188,14 @@ ARN_DEV float erf_approx(float x) {
     float sign = signum(x);
     x = x * sign;
     float t = 1.f / (1.f + P * x);
-    float y = 1.f - (((((A5 * t + A4) * t) + A3) * t + A2) * t + A1) * t * expf(-x * x);
+    float y = 1.f - (((((A5 * t + A4) * t) + A3) * t + A2) * t + A1) * t * cr_expf(-x * x);
     return sign * y;
 }
 template <bool BECK> ARN_DEV float dist_D(float ax, float ay, float3 wh) {
     float c2t = cos2_theta(wh), t2t = tan2_theta(wh);
     if (BECK) {
         float c2p = cos2_phi(wh), s2p = sin2_phi(wh);
-        return expf(-t2t * (c2p / (ax * ax) + s2p / (ay * ay))) / (ARN_PI * ax * ay * c2t * c2t);
+        return cr_expf(-t2t * (c2p / (ax * ax) + s2p / (ay * ay))) / (ARN_PI * ax * ay * c2t * c2t);
     }
     if (isinf(t2t)) return 0.f;
     float c2p = cos2_phi(wh), s2p = sin2_phi(wh);
@@ -229,24 +229,24 @@ static __device__ __noinline__ float3 sample_wh_beckmann(float3 wo, float2 u, fl
     float ct = fabsf(cos_theta(ws));
     float sx, sy;
     if (ct > 0.9999f) {
-        float r = sqrtf(-logf(u.x));
+        float r = sqrtf(-cr_logf(u.x));
         float phi = 2.f * u.y * ARN_PI;
-        sx = r * cosf(phi); sy = r * sinf(phi);
+        sx = r * cr_cosf(phi); sy = r * cr_sinf(phi);
     } else {
         float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
         float tant = st / ct, cott = ct / st;
         float a = -1.f;
         float c = erf_approx(cott);
         float ux = fmaxf(u.x, 1e-6f);
-        float theta = acosf(ct);
+        float theta = cr_acosf(ct);
         float fit = 1.f + theta * (-0.876f + theta * (0.4265f - 0.0594f * theta));
-        float b = c - (1.f + c) * powf(1.f - ux, fit);
+        float b = c - (1.f + c) * cr_powf(1.f - ux, fit);
         float sqrt_pi_inv = 1.f / sqrtf(ARN_PI);
-        float norm = 1.f / (1.f + c + sqrt_pi_inv * tant * expf(-cott * cott));
+        float norm = 1.f / (1.f + c + sqrt_pi_inv * tant * cr_expf(-cott * cott));
         for (int it = 1; it < 10; it++) {
             if (b < a || b > c) b = 0.5f * (a + c);
             float inv = erf_inv(b);
-            float value = norm * (1.f + b + sqrt_pi_inv * tant * expf(-inv * inv)) - ux;
+            float value = norm * (1.f + b + sqrt_pi_inv * tant * cr_expf(-inv * inv)) - ux;
             if (fabsf(value) < 1e-5f) break;
             float derivation = norm * (1.f - inv * tant);
             if (value > 0.f) c = b; else a = b;
@@ -270,7 +270,7 @@ static __device__ __noinline__ float3 sample_wh_trowbridge(float3 wo_in, float2 
     if (ct > 0.9999f) {
         float r = sqrtf(u.x / (1.f - u.x));
         float phi = 2.f * u.y * ARN_PI;
-        sx = r * cosf(phi); sy = r * sinf(phi);
+        sx = r * cr_cosf(phi); sy = r * cr_sinf(phi);
     } else {
         float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
         float tant = st / ct, cott = ct / st;
@@ -343,7 +343,7 @@ template <bool BECK> ARN_DEV float3 as_eval(const Lobe& x, float3 wo, float3 wi)
         / (4.f * fabsf(dot(wi, wh)) * fmaxf(fabsf(cos_theta(wi)), fabsf(cos_theta(wo))));
     return diffuse + specular;
 }
-ARN_DEV float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
+ARN_NOINL float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
     switch (x.kind) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: return wo.z * wi.z > 0.f ? fabsf(cos_theta(wi)) * ARN_INV_PI : 0.f;
     case LOBE_LAMBERT_T: return wo.z * wi.z >= 0.f ? 0.f : fabsf(cos_theta(wi)) * ARN_INV_PI;
@@ -366,7 +366,7 @@ ARN_DEV float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
     default: return as_pdf<false>(x, wo, wi);
     }
 }
-ARN_DEV float3 lobe_eval(const Lobe& x, float3 wo, float3 wi) {
+ARN_NOINL float3 lobe_eval(const Lobe& x, float3 wo, float3 wi) {
     switch (x.kind) {
     case LOBE_LAMBERT_R: case LOBE_LAMBERT_T: return x.a * ARN_INV_PI;
     case LOBE_OREN_NAYAR: {
@@ -422,7 +422,7 @@ template <bool BECK> ARN_DEV Sampled as_sample(const Lobe& x, float3 wo, float2 
     r.f = as_eval<BECK>(x, wo, wi); r.wi = wi; r.pdf = as_pdf<BECK>(x, wo, wi);
     return r;
 }
-ARN_DEV Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
+ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
     Sampled r; r.type = lobe_type(x.kind);
     switch (x.kind) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
@@ -546,7 +546,7 @@ ARN_DEV float bsdf_pdf(const Bsdf& b, float3 wow, float3 wiw) {
     return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
 }
 // Bsdf::evaluate_sampled with BXDF_ALL (bsdf.rs:100-145)
-ARN_DEV Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
+ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
     int match_count = b.n;
     if (match_count == 0) return ret;
@@ -577,7 +577,7 @@ ARN_DEV Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
 ARN_DEV float3 sphere_emission(const DevSphere& sp) { return f3(sp.emission[0], sp.emission[1], sp.emission[2]); }
 ARN_DEV float sphere_area(const DevSphere& sp) { return sp.phimax * sp.radius * (sp.zmax - sp.zmin); }
 // Light::evaluate_path: emission if the shape is re-hit from pos+dir going back (shape.rs:91-103)
-ARN_DEV float3 light_le(const DevSphere& sp, float3 pos, float3 dir) {
+ARN_NOINL float3 light_le(const DevSphere& sp, float3 pos, float3 dir) {
     if (!sp.emissive) return grey(0.f);
     if (sp.has_transform) { pos = xform_point(sp.parent_local, pos); dir = xform_vector(sp.parent_local, dir); }
     float3 p = pos + dir;
@@ -586,11 +586,11 @@ ARN_DEV float3 light_le(const DevSphere& sp, float3 pos, float3 dir) {
 }
 struct LightSample { float3 radiance, pfrom, pto; float pdf; };
 // evaluate_sampled (shape.rs:108-130 via transformed.rs:120-124) with Shape::sample_wrt (shape/mod.rs:52-64)
-ARN_DEV LightSample light_sample(const DevSphere& sp, float3 pos, float2 u) {
+ARN_NOINL LightSample light_sample(const DevSphere& sp, float3 pos, float2 u) {
     if (sp.has_transform) pos = xform_point(sp.parent_local, pos);
     float phi = u.x * sp.phimax;                                            // Sphere::sample (sphere.rs:304-311)
     float theta = u.y * (sp.thetamax - sp.thetamin) + sp.thetamin;
-    float st = sinf(theta), ct = cosf(theta), sph = sinf(phi), cph = cosf(phi);
+    float st = cr_sinf(theta), ct = cr_cosf(theta), sph = cr_sinf(phi), cph = cr_cosf(phi);
     float3 dir = f3(st * cph, st * sph, ct);
     float3 lp = dir * sp.radius;
     float lpdf = 1.f / sphere_area(sp);
@@ -614,16 +614,16 @@ ARN_DEV LightSample light_sample(const DevSphere& sp, float3 pos, float2 u) {
     return ls;
 }
 // Light::pdf = Shape::pdf_wrt (shape/mod.rs:67-75): needs the local hit normal
-ARN_DEV float light_pdf(const DevSphere& sp, float3 pos, float3 wi) {
+ARN_NOINL float light_pdf(const DevSphere& sp, float3 pos, float3 wi) {
     if (sp.has_transform) { pos = xform_point(sp.parent_local, pos); wi = xform_vector(sp.parent_local, wi); }
     float t; float3 p;
     if (!sphere_test(sp, pos, wi, ARN_INF, t, p)) return 0.f;
     float thetadelta = sp.thetamax - sp.thetamin;
-    float theta = acosf(p.z / sp.radius);
+    float theta = cr_acosf(p.z / sp.radius);
     float inv_z_radius = 1.f / sqrtf(p.x * p.x + p.y * p.y);
     float cphi = p.x * inv_z_radius, sphi = p.y * inv_z_radius;
     float3 dpdu = f3(-sp.phimax * p.y, sp.phimax * p.x, 0.f);
-    float3 dpdv = thetadelta * f3(p.z * cphi, p.z * sphi, -sp.radius * sinf(theta));
+    float3 dpdv = thetadelta * f3(p.z * cphi, p.z * sphi, -sp.radius * cr_sinf(theta));
     float3 n = normalize(cross(dpdu, dpdv));
     return length2(p - pos) / (fabsf(dot(wi, n)) * sphere_area(sp));
 }

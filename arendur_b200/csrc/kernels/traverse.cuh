@@ -133,7 +133,7 @@ ARN_DEV bool tri_test(float3 p0, float3 p1, float3 p2, const TravRay& r, float& 
 
 // Sphere::intersect_ray_full + refinement + clipping (sphere.rs:193-250), local space.
 // On a hit returns t and the refined local hit point p.
-ARN_DEV bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, float& t_out, float3& p_out) {
+ARN_NOINL bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, float& t_out, float3& p_out) {
     float a = dot(d, d);
     float3 m = (d * o) * 2.f;
     float b = m.x + m.y + m.z;
@@ -151,7 +151,7 @@ ARN_DEV bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, fl
     float3 p = o + d * t;
     p = p * sp.radius / length(p);
     if (p.x == 0.f && p.y == 0.f) p.x = 1e-5f * sp.radius;
-    float phi = atan2f(p.y, p.x);
+    float phi = cr_atan2f(p.y, p.x);
     if (phi < 0.f) phi += 2.f * ARN_PI;
     if (p.z < sp.zmin || p.z > sp.zmax || phi > sp.phimax) return false;
     t_out = t; p_out = p;

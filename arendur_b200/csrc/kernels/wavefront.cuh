@@ -43,10 +43,12 @@ struct PathBuf {                 // SoA over path slots, capacity W
 #define NEE_SHADOW 2u
 #define NEE_MIS 4u
 
+#define ARN_NCLS 5                // shading classes: Lambert, Oren-Nayar, Plastic, Glass, Translucent
 struct Queues {
     uint32_t* active[2];         // path ids for the current / next bounce
     uint32_t* connect;           // path ids with a pending direct-light term
-    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size
+    uint32_t* cls[ARN_NCLS];     // hits of the current bounce, sorted by shading class (material sort)
+    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size, [3+c] = class c size
     unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1
 };
 
@@ -63,24 +65,44 @@ struct WaveParams {
     uint32_t spp_begin, spp_count;
 };
 
-// ---- block-level queue append: warp ballots + shared-memory staging ----------------
-// Every thread of the block calls this once per iteration with `keep` and its path id.
-ARN_DEV void queue_append(bool keep, uint32_t pid, uint32_t* __restrict__ queue, uint32_t* __restrict__ count) {
-    __shared__ uint32_t warp_tot[ARN_BLOCK / 32];
-    __shared__ uint32_t block_base;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// ---- queue append: warp ballots + per-warp shared-memory staging -------------------
+// Each warp compacts the ids it keeps into its own 64-entry staging row in shared memory
+// (ballot + popc give the slots); whenever a row holds >= 32 ids the warp reserves 32 queue
+// slots with ONE atomic and writes them as one aligned 128-byte store.  No block barrier:
+// warps in a shading kernel finish at very different times.
+struct WarpStage {
+    uint32_t* row;       // 64 entries of this warp
+    uint32_t fill;       // warp-uniform
+};
+ARN_DEV void stage_push(WarpStage& st, bool keep, uint32_t pid, uint32_t* __restrict__ queue, uint32_t* __restrict__ count) {
+    const unsigned lane = threadIdx.x & 31u;
     unsigned ballot = __ballot_sync(0xffffffffu, keep);
-    unsigned rank = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < ARN_BLOCK / 32; w++) { uint32_t c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
-        block_base = tot ? atomicAdd(count, tot) : 0u;
+    if (keep) st.row[st.fill + __popc(ballot & ((1u << lane) - 1u))] = pid;
+    st.fill += __popc(ballot);
+    __syncwarp();
+    if (st.fill >= 32u) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        queue[base + lane] = st.row[lane];
+        __syncwarp();
+        uint32_t rest = st.fill - 32u;
+        uint32_t v = lane < rest ? st.row[32u + lane] : 0u;
+        __syncwarp();
+        if (lane < rest) st.row[lane] = v;
+        st.fill = rest;
+        __syncwarp();
     }
-    __syncthreads();
-    if (keep) queue[block_base + warp_tot[warp] + rank] = pid;
-    __syncthreads();
+}
+ARN_DEV void stage_flush(WarpStage& st, uint32_t* __restrict__ queue, uint32_t* __restrict__ count) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (st.fill) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, st.fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < st.fill) queue[base + lane] = st.row[lane];
+        st.fill = 0;
+    }
 }
 
 // ---- K1 generate ------------------------------------------------------------------------
@@ -124,21 +146,47 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ 
     }
 }
 
-// ---- K2 extend: closest hit for every active path ------------------------------------------
+// ---- K2 extend: closest hit for every active path, hits sorted into per-material-class queues ----
+ARN_DEV int shading_class(const arn_material& m) {
+    switch (m.type) {
+    case ARN_MAT_MATTE: return clampf(m.sigma, 0.f, 90.f) == 0.f ? 0 : 1;
+    case ARN_MAT_PLASTIC: return 2;
+    case ARN_MAT_GLASS: return 3;
+    default: return 4;
+    }
+}
 __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
     const uint32_t n = q.counts[cur];
     const uint32_t* __restrict__ ids = q.active[cur];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t pid = ids[i];
-        float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
-        TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
-        HitRec h;
-        traverse<false, false>(sc, r, h, nullptr);
-        pb.hit_prim[pid] = h.prim;
-        pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
-        if (h.prim >= 0 && (sc.prims[h.prim] & ARN_PRIM_SPHERE))   // `*ray = iray`: the ray leaves traversal round-tripped
-            pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);
+    __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
+    WarpStage st[ARN_NCLS];
+#pragma unroll
+    for (int c = 0; c < ARN_NCLS; c++) { st[c].row = stage_rows[c][threadIdx.x >> 5]; st[c].fill = 0; }
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        uint32_t pid = 0; int cls = -1;
+        if (i < n) {
+            pid = ids[i];
+            float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
+            TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
+            HitRec h;
+            traverse<false, false>(sc, r, h, nullptr);
+            pb.hit_prim[pid] = h.prim;
+            pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
+            if (h.prim >= 0) {
+                uint32_t ref = sc.prims[h.prim], mat;
+                if (ref & ARN_PRIM_SPHERE) {
+                    mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
+                    pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
+                } else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                cls = shading_class(sc.materials[mat]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < ARN_NCLS; c++) stage_push(st[c], cls == c, pid, q.cls[c], &q.counts[3 + c]);
     }
+#pragma unroll
+    for (int c = 0; c < ARN_NCLS; c++) stage_flush(st[c], q.cls[c], &q.counts[3 + c]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&q.stats[0], (unsigned long long)n);
         if (bounce > 0) atomicAdd(&q.stats[4], (unsigned long long)n);
@@ -146,11 +194,16 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Q
 }
 
 // ---- K3 shade ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ARN_BLOCK) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
-    const uint32_t n = q.counts[cur];
-    const uint32_t* __restrict__ ids = q.active[cur];
+// launched once per shading class: every warp shades one kind of material
+__global__ void __launch_bounds__(ARN_BLOCK) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur, int cls) {
+    const uint32_t n = q.counts[3 + cls];
+    const uint32_t* __restrict__ ids = q.cls[cls];
     uint32_t* next = q.active[cur ^ 1];
-    const uint32_t n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
+    __shared__ uint32_t stage_rows[2][ARN_BLOCK / 32][64];
+    WarpStage st_next, st_conn;
+    st_next.row = stage_rows[0][threadIdx.x >> 5]; st_next.fill = 0;
+    st_conn.row = stage_rows[1][threadIdx.x >> 5]; st_conn.fill = 0;
+    const uint32_t n_round = (n + 31u) & ~31u;          // warp-uniform trip count
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false, nee = false;
         uint32_t pid = 0;
@@ -273,9 +326,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_shade(DevScene sc, const __grid_c
                 }
             }
         }
-        queue_append(alive, pid, next, &q.counts[cur ^ 1]);
-        queue_append(nee, pid, q.connect, &q.counts[2]);
+        stage_push(st_next, alive, pid, next, &q.counts[cur ^ 1]);
+        stage_push(st_conn, nee, pid, q.connect, &q.counts[2]);
     }
+    stage_flush(st_next, next, &q.counts[cur ^ 1]);
+    stage_flush(st_conn, q.connect, &q.counts[2]);
 }
 
 // ---- K4 connect: shadow ray (any hit) + BSDF-sampled light ray (closest hit), then resolve -----
@@ -321,8 +376,8 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_connect(DevScene sc, PathBuf pb, 
 }
 
 // resets the queue counters between bounces (single thread)
-__global__ void k_next_bounce(Queues q, int cur) { q.counts[cur] = 0; q.counts[2] = 0; }
-__global__ void k_begin_wave(Queues q, uint32_t n) { q.counts[0] = n; q.counts[1] = 0; q.counts[2] = 0; }
+__global__ void k_next_bounce(Queues q, int cur) { q.counts[cur] = 0; q.counts[2] = 0; for (int c = 0; c < ARN_NCLS; c++) q.counts[3 + c] = 0; }
+__global__ void k_begin_wave(Queues q, uint32_t n) { q.counts[0] = n; q.counts[1] = 0; q.counts[2] = 0; for (int c = 0; c < ARN_NCLS; c++) q.counts[3 + c] = 0; }
 
 // ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
 ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return sinf(xpi) / xpi; }
@@ -356,6 +411,15 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant_
     }
     for (int off = 16; off > 0; off >>= 1) invalid += __shfl_down_sync(0xffffffffu, invalid, off);
     if ((threadIdx.x & 31) == 0 && invalid) atomicAdd(&q.stats[3], invalid);
+}
+
+// diagnostic: per-sample radiance, indexed ((y*crop_w + x)*spp_count + (s - spp_begin)) (parity tests)
+__global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_constant__ WaveParams p, PathBuf pb, float4* __restrict__ out, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t pix = pb.pix[i]; uint32_t x = pix & 0xffffu, y = pix >> 16;
+        size_t idx = ((size_t)(y - p.crop_y0) * p.crop_w + (x - p.crop_x0)) * p.spp_count + (pb.smp[i] - p.spp_begin);
+        out[idx] = pb.L[i];
+    }
 }
 
 // ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------

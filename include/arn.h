@@ -260,6 +260,13 @@ int arn_render_pt_dev(arn_scene* scene, const arn_camera* cam, const arn_film* f
                       const arn_sampler* sampler, const arn_pt_params* params,
                       void* film_dev, arn_stats* stats);
 
+/* Diagnostic twin of arn_render_pt (parity tests): additionally returns the radiance
+ * `calculate_lighting` produced for every camera sample (renderer/pt.rs:144-148),
+ * radiance_out[((y*crop_w + x)*n_spp + s)*4 + {0,1,2}], HOST buffer of crop_w*crop_h*n_spp*4 floats. */
+int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_film* film,
+                          const arn_sampler* sampler, const arn_pt_params* params,
+                          float* film_out, float* radiance_out, arn_stats* stats);
+
 int arn_ctx_synchronize(arn_ctx* ctx);
 /* The context's CUDA stream as a cudaStream_t cast to void* (for event timing). */
 void* arn_ctx_stream(arn_ctx* ctx);

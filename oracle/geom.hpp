@@ -36,6 +36,19 @@ inline Float frac_1_pi() { return 0.318309886183790671537767526745028724f; }
 inline Float frac_pi_2() { return 1.57079632679489661923132169163975144f; }
 inline Float frac_pi_4() { return 0.785398163397448309615660845819875721f; }
 
+// Transcendentals.  Rust's f32::{sin,cos,tan,acos,atan2,ln,exp,powf} call the platform libm,
+// whose results are only defined up to its own error bound.  The oracle AND the GPU evaluate them
+// as correctly-rounded f32 (computed in f64, rounded once), so both sides agree bit for bit
+// (up to ~1e-8 double-rounding cases) and stay within 0.5 ulp of any faithful libm.  DESIGN.md.
+inline Float fsin(Float x) { return (Float)std::sin((double)x); }
+inline Float fcos(Float x) { return (Float)std::cos((double)x); }
+inline Float ftan(Float x) { return (Float)std::tan((double)x); }
+inline Float facos(Float x) { return (Float)std::acos((double)x); }
+inline Float fatan2(Float y, Float x) { return (Float)std::atan2((double)y, (double)x); }
+inline Float flog(Float x) { return (Float)std::log((double)x); }
+inline Float fexp(Float x) { return (Float)std::exp((double)x); }
+inline Float fpow(Float a, Float b) { return (Float)std::pow((double)a, (double)b); }
+
 inline uint32_t to_bits(Float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline Float from_bits(uint32_t u) { Float f; std::memcpy(&f, &u, 4); return f; }
 inline bool sign_positive(Float f) { return (to_bits(f) >> 31) == 0; }
@@ -402,7 +415,7 @@ inline void get_basis_from(V3 dir, V3* u, V3* v) {                              
 
 // Sphericalf::to_vec (foundamental.rs:151-163)
 inline V3 spherical_to_vec(Float theta, Float phi) {
-    Float st = std::sin(theta), ct = std::cos(theta), sp = std::sin(phi), cp = std::cos(phi);
+    Float st = fsin(theta), ct = fcos(theta), sp = fsin(phi), cp = fcos(phi);
     return v3(st * cp, st * sp, ct);
 }
 

@@ -114,6 +114,14 @@ int arn_oracle_render_pt(arn_oracle_scene* h, const arn_camera* cam, const arn_f
     return ARN_OK;
 }
 
+int arn_oracle_render_pt_samples(arn_oracle_scene* h, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
+                                 const arn_pt_params* prm, float* film_out, float* radiance_out, int nthreads) {
+    if (!h || !cam || !film || !smp || !prm || !film_out || !radiance_out || h->s.light_prims.empty()) return ARN_E_INVALID;
+    RayStats st;
+    render_pt(h->s, *cam, *film, *smp, *prm, film_out, &st, nthreads, radiance_out);
+    return ARN_OK;
+}
+
 int arn_oracle_film_finalize(const float* film, size_t n_pixels, float* rgb_out, uint8_t* rgb8_out) {
     film_finalize(film, n_pixels, rgb_out, rgb8_out); return ARN_OK;
 }
@@ -145,7 +153,7 @@ int arn_oracle_sphere_new(float radius, float zmin, float zmax, float phimax, ar
     Float twopi = pi() * 2.f;
     if (phimax > twopi) phimax = twopi;
     out->radius = radius; out->zmin = zmin; out->zmax = zmax; out->phimax = phimax;
-    out->thetamin = std::acos(zmin / radius); out->thetamax = std::acos(zmax / radius);
+    out->thetamin = facos(zmin / radius); out->thetamax = facos(zmax / radius);
     return ARN_OK;
 }
 

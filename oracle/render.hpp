@@ -18,7 +18,7 @@ inline M4 perspective_transform(Float fov, Float znear, Float zfar) {
     persp.m[0] = 1.f; persp.m[5] = 1.f;
     persp.m[10] = zfar / (zfar - znear); persp.m[11] = 1.f;
     persp.m[14] = -zfar * znear / (zfar - znear); persp.m[15] = 0.f;
-    Float inv_tan = 1.f / std::tan(fov * 0.5f);
+    Float inv_tan = 1.f / ftan(fov * 0.5f);
     return m4_mul(m4_from_nonuniform_scale(inv_tan, inv_tan, 1.f), persp);
 }
 // ProjCameraInfo::new (filming/projective.rs:24-45) + PerspecCam::new (perspective.rs:42-90)
@@ -267,7 +267,7 @@ inline void tile_add_sample(FilmTile& t, const arn_film& film, V2 pos, RGB spect
 
 // PTRenderer::render (renderer/pt.rs:128-176) up to collect_into's merge (film.rs:171-183, 82-101)
 inline void render_pt(const Scene& s, const arn_camera& cam, const arn_film& film, const arn_sampler& smp,
-                      const arn_pt_params& prm, Float* film_out, RayStats* stats, int nthreads) {
+                      const arn_pt_params& prm, Float* film_out, RayStats* stats, int nthreads, Float* radiance_out = nullptr) {
     long nx = prm.tiles_x ? prm.tiles_x : 16, ny = prm.tiles_y ? prm.tiles_y : 16;
     std::vector<FilmTile> tiles = spawn_tiles(film, nx, ny);
     uint32_t spp = smp.sampledx * smp.sampledy;
@@ -294,6 +294,10 @@ inline void render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
                     RawRay ray = camera_generate(cam, pfilm, plens);
                     tstats[tid].camera++;
                     RGB L = calculate_lighting(s, ray, sampler, prm.max_depth, prm.min_depth, prm.rr_threshold, &tstats[tid]);
+                    if (radiance_out) {
+                        size_t ri = (((size_t)(y - film.crop_min_y) * (size_t)(film.crop_max_x - film.crop_min_x) + (size_t)(x - film.crop_min_x)) * (s1 - s0) + (si - s0)) * 4;
+                        radiance_out[ri] = L.x; radiance_out[ri + 1] = L.y; radiance_out[ri + 2] = L.z; radiance_out[ri + 3] = 0.f;
+                    }
                     if (rgb_valid(L)) tile_add_sample(tile, film, pfilm, L);
                     else { tile_add_sample(tile, film, pfilm, grey(0.f)); tstats[tid].invalid++; }
                 }

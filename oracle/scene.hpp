@@ -184,7 +184,7 @@ inline bool sphere_intersect(const arn_sphere& sp, const RawRay& ray, Float* t_o
     V3 p = ray_evaluate(ray, t);
     p = p * sp.radius / magnitude(p);
     if (p.x == 0.f && p.y == 0.f) p.x = 1e-5f * sp.radius;
-    Float phi = std::atan2(p.y, p.x);
+    Float phi = fatan2(p.y, p.x);
     if (phi < 0.f) phi += 2.f * pi();
     if (p.z < sp.zmin || p.z > sp.zmax || phi > sp.phimax) return false;
     *t_out = t;
@@ -192,12 +192,12 @@ inline bool sphere_intersect(const arn_sphere& sp, const RawRay& ray, Float* t_o
     Float phimax = sp.phimax, thetamax = sp.thetamax, thetamin = sp.thetamin;
     Float thetadelta = thetamax - thetamin;
     Float u = phi / phimax;
-    Float theta = std::acos(p.z / sp.radius);
+    Float theta = facos(p.z / sp.radius);
     Float v = (theta - thetamin) / thetadelta;
     Float inv_z_radius = 1.f / std::sqrt(p.x * p.x + p.y * p.y);
     Float cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
     V3 dpdu = v3(-phimax * p.y, phimax * p.x, 0.f);
-    V3 dpdv = thetadelta * v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * std::sin(theta));
+    V3 dpdv = thetadelta * v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * fsin(theta));
     V3 dppduu = -phimax * phimax * v3(p.x, p.y, 0.f);
     V3 dppduv = thetadelta * p.z * phimax * v3(-sin_phi, cos_phi, 0.f);
     V3 dppdvv = -thetadelta * thetadelta * v3(p.x, p.y, p.z);

@@ -52,7 +52,7 @@ inline V2 sample_concentric_disk(V2 u) {                                        
     Float r, theta;
     if (std::fabs(w.x) > std::fabs(w.y)) { r = w.x; theta = frac_pi_4() * (w.y / w.x); }
     else { r = w.y; theta = frac_pi_2() - frac_pi_4() * (w.x / w.y); }
-    return r * v2(std::cos(theta), std::sin(theta));
+    return r * v2(fcos(theta), fsin(theta));
 }
 inline V3 sample_cosw_hemisphere(V2 u) {                                          // :203-207
     V2 d = sample_concentric_disk(u);
@@ -85,7 +85,7 @@ inline void distribution_new(const Float* func, uint32_t n, Float* cdf, Float* i
 }
 
 // LanczosSincFilter (sample/filters.rs:193-241), evaluated with SIGNED offsets (quirk A-4)
-inline Float lanczos_sinc1(Float x) { if (x < 1.0e-5f) return 1.f; Float xpi = x * pi(); return std::sin(xpi) / xpi; }
+inline Float lanczos_sinc1(Float x) { if (x < 1.0e-5f) return 1.f; Float xpi = x * pi(); return fsin(xpi) / xpi; }
 inline Float lanczos_sinc(Float x, Float inv_tau) { return lanczos_sinc1(x * inv_tau) * lanczos_sinc1(x); }
 inline Float lanczos_evaluate(V2 p, Float inv_tau) { return lanczos_sinc(p.x, inv_tau) * lanczos_sinc(p.y, inv_tau); }
 
@@ -117,12 +117,12 @@ inline bool bxdf_is(const Bxdf& x, uint32_t t) { return (bxdf_type(x) & t) != 0;
 
 // microfacet helpers (bxdf/microfacet.rs)
 inline Float roughness_to_alpha(Float roughness) {                                // :57-63
-    Float x = std::log(fmax_(roughness, 1e-3f));
+    Float x = flog(fmax_(roughness, 1e-3f));
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 inline Float erf_inv(Float x) {                                                    // :313-343
     x = fmin_(fmax_(x, -0.99999f), 0.99999f);
-    Float w = -std::log((1.f - x) * (1.f + x));
+    Float w = -flog((1.f - x) * (1.f + x));
     Float p;
     if (w < 5.f) {
         w = w - 2.5f;
@@ -142,14 +142,14 @@ inline Float erf_approx(Float x) {                                              
     Float sign = signum(x);
     x = x * sign;
     Float t = 1.f / (1.f + P * x);
-    Float y = 1.f - (((((A5 * t + A4) * t) + A3) * t + A2) * t + A1) * t * std::exp(-x * x);
+    Float y = 1.f - (((((A5 * t + A4) * t) + A3) * t + A2) * t + A1) * t * fexp(-x * x);
     return sign * y;
 }
 inline Float dist_D(DistKind k, Float ax, Float ay, V3 wh) {
     Float cos2_theta = nrm::cos2_theta(wh), tan2_theta = nrm::tan2_theta(wh);
     if (k == DIST_BECKMANN) {                                                      // :84-93
         Float cos2_phi = nrm::cos2_phi(wh), sin2_phi = nrm::sin2_phi(wh);
-        return std::exp(-tan2_theta * (cos2_phi / (ax * ax) + sin2_phi / (ay * ay))) / (pi() * ax * ay * cos2_theta * cos2_theta);
+        return fexp(-tan2_theta * (cos2_phi / (ax * ax) + sin2_phi / (ay * ay))) / (pi() * ax * ay * cos2_theta * cos2_theta);
     }
     if (std::isinf(tan2_theta)) return 0.f;                                        // :145-158
     Float cos2_phi = nrm::cos2_phi(wh), sin2_phi = nrm::sin2_phi(wh);
@@ -183,9 +183,9 @@ inline V3 sample_wh_beckmann(V3 wo, V2 u, Float ax, Float ay) {                 
     Float cos_theta = std::fabs(nrm::cos_theta(wo_stretched));
     Float sx, sy;
     if (cos_theta > 0.9999f) {
-        Float r = std::sqrt(-std::log(u.x));
+        Float r = std::sqrt(-flog(u.x));
         Float phi = 2.f * u.y * pi();
-        sx = r * std::cos(phi); sy = r * std::sin(phi);
+        sx = r * fcos(phi); sy = r * fsin(phi);
     } else {
         Float sin_theta = std::sqrt(fmax_(1.f - cos_theta * cos_theta, 0.f));
         Float tan_theta = sin_theta / cos_theta;
@@ -193,15 +193,15 @@ inline V3 sample_wh_beckmann(V3 wo, V2 u, Float ax, Float ay) {                 
         Float a = -1.f;
         Float c = erf_approx(cot_theta);
         Float ux = fmax_(u.x, 1e-6f);
-        Float theta = std::acos(cos_theta);
+        Float theta = facos(cos_theta);
         Float fit = 1.f + theta * (-0.876f + theta * (0.4265f - 0.0594f * theta));
-        Float b = c - (1.f + c) * std::pow(1.f - ux, fit);
+        Float b = c - (1.f + c) * fpow(1.f - ux, fit);
         Float sqrt_pi_inv = 1.f / std::sqrt(pi());
-        Float norm = 1.f / (1.f + c + sqrt_pi_inv * tan_theta * std::exp(-cot_theta * cot_theta));
+        Float norm = 1.f / (1.f + c + sqrt_pi_inv * tan_theta * fexp(-cot_theta * cot_theta));
         for (int it = 1; it < 10; it++) {
             if (b < a || b > c) b = 0.5f * (a + c);
             Float inv = erf_inv(b);
-            Float value = norm * (1.f + b + sqrt_pi_inv * tan_theta * std::exp(-inv * inv)) - ux;
+            Float value = norm * (1.f + b + sqrt_pi_inv * tan_theta * fexp(-inv * inv)) - ux;
             if (std::fabs(value) < 1e-5f) break;
             Float derivation = norm * (1.f - inv * tan_theta);
             if (value > 0.f) c = b; else a = b;
@@ -224,7 +224,7 @@ inline V3 sample_wh_trowbridge_pos(V3 wo, V2 u, Float ax, Float ay) {           
     if (cos_theta > 0.9999f) {
         Float r = std::sqrt(u.x / (1.f - u.x));
         Float phi = 2.f * u.y * pi();
-        sx = r * std::cos(phi); sy = r * std::sin(phi);
+        sx = r * fcos(phi); sy = r * fsin(phi);
     } else {
         Float sin_theta = std::sqrt(fmax_(1.f - cos_theta * cos_theta, 0.f));
         Float tan_theta = sin_theta / cos_theta;

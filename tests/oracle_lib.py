@@ -49,6 +49,8 @@ def load():
     lib.arn_oracle_camera_rays.argtypes = [C.POINTER(L.Camera), vp, C.c_size_t, vp]
     lib.arn_oracle_render_pt.restype = C.c_int
     lib.arn_oracle_render_pt.argtypes = [vp, C.POINTER(L.Camera), C.POINTER(L.Film), C.POINTER(L.Sampler), C.POINTER(L.PTParams), vp, C.POINTER(L.Stats), vp, C.c_int]
+    lib.arn_oracle_render_pt_samples.restype = C.c_int
+    lib.arn_oracle_render_pt_samples.argtypes = [vp, C.POINTER(L.Camera), C.POINTER(L.Film), C.POINTER(L.Sampler), C.POINTER(L.PTParams), vp, vp, C.c_int]
     lib.arn_oracle_film_finalize.argtypes = [vp, C.c_size_t, vp, vp]
     lib.arn_oracle_mesh_transform.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
     lib.arn_oracle_m4_invert.restype = C.c_int
@@ -132,6 +134,20 @@ class OracleScene:
         rc = self.lib.arn_oracle_render_pt(self.h, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _p(out), C.byref(st), _p(trav), nt)
         assert rc == 0, rc
         return out, st, trav
+
+
+def _render_pt_samples(self, cam, film, sampler, params, nthreads=None):
+    w = film.crop_max_x - film.crop_min_x
+    h = film.crop_max_y - film.crop_min_y
+    n = (params.spp_end or sampler.sampledx * sampler.sampledy) - params.spp_begin
+    out = np.zeros((h, w, 4), np.float32)
+    rad = np.zeros((h, w, n, 4), np.float32)
+    rc = self.lib.arn_oracle_render_pt_samples(self.h, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _p(out), _p(rad), nthreads or (os.cpu_count() or 1))
+    assert rc == 0, rc
+    return out, rad
+
+
+OracleScene.render_pt_samples = _render_pt_samples
 
 
 def camera_make(parent_view, screen, znear, zfar, fov, res_x, res_y, lens=None):
