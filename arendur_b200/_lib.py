@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libarn_b200.so")
 ARN_OK, ARN_E_INVALID, ARN_E_CUDA, ARN_E_OOM, ARN_E_IO, ARN_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ARN_PRIM_SPHERE = 0x80000000
 ARN_BVH_SAH, ARN_BVH_MIDDLECOUNT, ARN_BVH_MIDPOINT = 0, 1, 2
+ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY = 1, 2
 ARN_MAT_MATTE, ARN_MAT_PLASTIC, ARN_MAT_GLASS, ARN_MAT_TRANSLUCENT = 0, 1, 2, 3
 
 c_float_p = C.POINTER(C.c_float)
@@ -83,7 +84,8 @@ class Stats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("mis_rays", C.c_uint64), ("invalid_samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("gpu_ms", C.c_double), ("extend_ms", C.c_double), ("extend_bounce_ms", C.c_double),
-                ("extend_bounce_rays", C.c_uint64)]
+                ("extend_bounce_rays", C.c_uint64), ("extend_nodes", C.c_uint64), ("extend_tris", C.c_uint64),
+                ("extend_spheres", C.c_uint64)]
 
 
 # every symbol include/arn.h and include/arn_host.h declare (checked by tests/test_abi.py)
@@ -91,7 +93,7 @@ ARN_H_SYMBOLS = [
     "arn_bvh_build", "arn_light_distribution", "arn_film_finalize", "arn_ctx_create", "arn_ctx_destroy",
     "arn_last_error", "arn_scene_upload", "arn_scene_destroy", "arn_intersect_closest", "arn_intersect_any",
     "arn_intersect_closest_dev", "arn_intersect_any_dev", "arn_intersect_closest_counted_dev",
-    "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
+    "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_set_option", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
@@ -130,6 +132,7 @@ def load():
         "arn_render_pt": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, C.POINTER(Stats)]),
         "arn_render_pt_dev": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, C.POINTER(Stats)]),
         "arn_render_pt_samples": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), vp, vp, C.POINTER(Stats)]),
+        "arn_ctx_set_option": (C.c_int, [vp, C.c_int, C.c_longlong]),
         "arn_ctx_synchronize": (C.c_int, [vp]),
         "arn_ctx_stream": (vp, [vp]),
         "arn_version": (C.c_char_p, []),

@@ -202,6 +202,11 @@ class Context:
             self.lib.arn_ctx_destroy(self.c)
             self.c = C.c_void_p()
 
+    def set_option(self, option, value):
+        rc = self.lib.arn_ctx_set_option(self.c, option, int(value))
+        if rc != 0:
+            raise ArnError(rc, self.error())
+
     def synchronize(self):
         rc = self.lib.arn_ctx_synchronize(self.c)
         if rc != 0:

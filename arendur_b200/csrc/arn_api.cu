@@ -41,6 +41,8 @@ struct arn_ctx {
     // scratch for batched queries through host buffers
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
+    bool opt_count = false;
+    size_t opt_wave = 0;
 };
 
 struct arn_scene {
@@ -147,7 +149,7 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->g_generate = grid_for(c, (const void*)k_generate);
-    c->g_extend = grid_for(c, (const void*)k_extend);
+    c->g_extend = grid_for(c, (const void*)k_extend<false>);
     c->g_shade = grid_for(c, (const void*)k_shade);
     c->g_connect = grid_for(c, (const void*)k_connect);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
@@ -171,6 +173,15 @@ void arn_ctx_destroy(arn_ctx* c) {
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
+    if (!c) return ARN_E_INVALID;
+    switch (option) {
+    case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
+    case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
+    default: return set_err(c, ARN_E_INVALID, "unknown option");
+    }
 }
 
 int arn_ctx_synchronize(arn_ctx* c) { if (!c) return ARN_E_INVALID; cudaSetDevice(c->device); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ARN_OK; }
@@ -405,7 +416,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     CUDA_TRY(c, cudaMemcpyAsync(c->d_tile_prefix, prefix.data(), prefix.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
 
     unsigned long long total = prefix.back() * (unsigned long long)(s1 - s0);
-    size_t cap = wave_capacity_default();
+    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default();
     if ((unsigned long long)cap > total) cap = (size_t)((total + ARN_BLOCK - 1) / ARN_BLOCK * ARN_BLOCK);
     int rc = ensure_wave(c, cap); if (rc != ARN_OK) return rc;
 
@@ -433,7 +444,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         int cur = 0;
         for (uint32_t b = 0; b < prm->max_depth; b++) {
             if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, (int)b}); }
-            k_extend<<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
+            if (c->opt_count) k_extend<true><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
+            else k_extend<false><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
             for (int cls = 0; cls < ARN_NCLS; cls++)
                 if (s->class_mask & (1u << cls)) { k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur, cls); launches++; }
@@ -455,6 +467,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         std::memset(stats, 0, sizeof *stats);
         stats->camera_rays = total; stats->extend_rays = hs[0]; stats->shadow_rays = hs[1]; stats->mis_rays = hs[2];
         stats->invalid_samples = hs[3]; stats->extend_bounce_rays = hs[4]; stats->kernel_launches = launches;
+        stats->extend_nodes = hs[5]; stats->extend_tris = hs[6]; stats->extend_spheres = hs[7];
         float ms = 0.f; cudaEventElapsedTime(&ms, e_begin, e_end); stats->gpu_ms = ms;
         double ext = 0.0, extb = 0.0;
         for (auto& pr : ext_events) { float m = 0.f; cudaEventElapsedTime(&m, c->events[pr.first], c->events[pr.first + 1]); ext += m; if (pr.second > 0) extb += m; }

@@ -49,7 +49,7 @@ struct Queues {
     uint32_t* connect;           // path ids with a pending direct-light term
     uint32_t* cls[ARN_NCLS];     // hits of the current bounce, sorted by shading class (material sort)
     uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size, [3+c] = class c size
-    unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1
+    unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1 [5..7] nodes/tris/spheres tested by extend (COUNT builds)
 };
 
 struct WaveParams {
@@ -155,7 +155,9 @@ ARN_DEV int shading_class(const arn_material& m) {
     default: return 4;
     }
 }
+template <bool COUNT>
 __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
+    uint32_t ctr[3] = {0, 0, 0};
     const uint32_t n = q.counts[cur];
     const uint32_t* __restrict__ ids = q.active[cur];
     __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Q
             float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
             TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
             HitRec h;
-            traverse<false, false>(sc, r, h, nullptr);
+            traverse<false, COUNT>(sc, r, h, ctr);
             pb.hit_prim[pid] = h.prim;
             pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
             if (h.prim >= 0) {
@@ -190,6 +192,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Q
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&q.stats[0], (unsigned long long)n);
         if (bounce > 0) atomicAdd(&q.stats[4], (unsigned long long)n);
+    }
+    if (COUNT) {
+        unsigned long long a = ctr[0], b = ctr[1], c = ctr[2];
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); c += __shfl_down_sync(0xffffffffu, c, off); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&q.stats[5], a); atomicAdd(&q.stats[6], b); atomicAdd(&q.stats[7], c); }
     }
 }
 

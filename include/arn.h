@@ -190,6 +190,10 @@ typedef struct arn_stats {
     double   extend_ms;          /* device time spent in closest-hit kernels (path rays)    */
     double   extend_bounce_ms;   /* ... of which for bounces >= 1 (incoherent)              */
     uint64_t extend_bounce_rays; /* path rays of bounces >= 1                               */
+    /* filled only when ARN_OPT_COUNT_TRAVERSAL is on (instrumented kernels, not for timing):
+     * BVH nodes / triangles / spheres tested by the path-ray (extend) traversals — the Nn, Nt
+     * of the algorithmic-bytes figure, SURVEY.md §8(d) */
+    uint64_t extend_nodes, extend_tris, extend_spheres;
 } arn_stats;
 
 typedef struct arn_ctx   arn_ctx;
@@ -266,6 +270,11 @@ int arn_render_pt_dev(arn_scene* scene, const arn_camera* cam, const arn_film* f
 int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_film* film,
                           const arn_sampler* sampler, const arn_pt_params* params,
                           float* film_out, float* radiance_out, arn_stats* stats);
+
+/* Context options. */
+#define ARN_OPT_COUNT_TRAVERSAL 1   /* value != 0: arn_render_pt* use instrumented extend kernels          */
+#define ARN_OPT_WAVE_CAPACITY   2   /* camera samples per wave (default 1 << 20; also env ARN_WAVE)       */
+int arn_ctx_set_option(arn_ctx* ctx, int option, long long value);
 
 int arn_ctx_synchronize(arn_ctx* ctx);
 /* The context's CUDA stream as a cudaStream_t cast to void* (for event timing). */

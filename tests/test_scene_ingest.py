@@ -1,0 +1,167 @@
+"""Host layer (product): scene ingest and flattening vs the committed fixture and the oracle.
+Covers TriangleMesh::from_model_transformed, load_obj's tobj semantics and material choice,
+arencli's JSON reader, PerspecCam::new, Scene::new's light distribution."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from arendur_b200 import api, scenes, _lib as L
+
+REF = "/root/reference/examples/cornellbox"
+have_ref = os.path.exists(os.path.join(REF, "cb.json"))
+
+
+def _desc_arrays(d):
+    return dict(
+        positions=np.ctypeslib.as_array(d.positions, shape=(d.n_vertices, 3)).copy(),
+        normals=np.ctypeslib.as_array(d.normals, shape=(d.n_vertices, 3)).copy() if d.normals else None,
+        uvs=np.ctypeslib.as_array(d.uvs, shape=(d.n_vertices, 2)).copy() if d.uvs else None,
+        indices=np.ctypeslib.as_array(d.indices, shape=(d.n_triangles, 3)).copy(),
+        tri_mesh=np.ctypeslib.as_array(d.tri_mesh, shape=(d.n_triangles,)).copy(),
+        prims=np.ctypeslib.as_array(d.prims, shape=(d.n_prims,)).copy(),
+        materials=bytes(C.string_at(d.materials, d.n_materials * 48)),
+        spheres=bytes(C.string_at(d.spheres, d.n_spheres * 176)),
+        meshes=bytes(C.string_at(d.meshes, d.n_meshes * 16)),
+    )
+
+
+def test_cornell_fixture_scene_shape():
+    hs, cam, film, smp, prm = scenes.cornell_scene(256, 256, 4, 4)
+    d = hs.desc()
+    assert (d.n_triangles, d.n_spheres, d.n_prims, d.n_meshes, d.n_lights) == (1112, 2, 1114, 8, 2)
+    a = _desc_arrays(d)
+    # component order of BASELINE.md C1: OBJ triangles, light_sphere, blue_sphere
+    assert np.array_equal(a["prims"][:1112], np.arange(1112)) and a["prims"][1112] == L.ARN_PRIM_SPHERE and a["prims"][1113] == L.ARN_PRIM_SPHERE | 1
+    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 12)
+    # sphere Plastic, shortBox Glass, floor Plastic, ceiling/backWall/leftWall/rightWall/light Matte, fallback Matte, sphere light Matte
+    assert mats[:, 0].tolist() == [1, 2, 1, 0, 0, 0, 0, 0, 0, 0]
+    # Scene::new power distribution (Y-power 994.6 / 685.1 -> pdf 0.592 / 0.408)
+    assert abs(d.light_func[0] - 994.6) < 0.1 and abs(d.light_func[1] - 685.1) < 0.1
+    assert abs(d.light_cdf[1] - 0.592) < 1e-3 and d.light_cdf[2] == 1.0
+    assert prm.max_depth == 8 and prm.min_depth == 4 and abs(prm.rr_threshold - 0.05) < 1e-9
+
+
+def test_mesh_transform_matches_oracle():
+    """from_model_transformed with the projective cb.json matrix (quirk A-12): positions through
+    the homogeneous divide, normals through the normalised inverse-transpose — vs the oracle."""
+    z = np.load(scenes.CORNELL_FIXTURE)
+    t = z["mesh_transform"]
+    pos, nrm, idx = z["m0_positions"], z["m0_normals"], z["m0_indices"]
+    hs = api.HostScene()
+    m = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+    hs.add_mesh(pos, idx, m, normals=nrm, transform=t)
+    d = hs.build()
+    a = _desc_arrays(d)
+    op, on = np.zeros_like(pos), np.zeros_like(nrm)
+    O.load().arn_oracle_mesh_transform(O._p(np.ascontiguousarray(t, np.float32)), pos.shape[0], O._p(pos), O._p(nrm), O._p(op), O._p(on))
+    assert np.array_equal(a["positions"].view(np.uint32), op.view(np.uint32))
+    assert np.array_equal(a["normals"].view(np.uint32), on.view(np.uint32))
+    assert abs(np.linalg.norm(a["normals"], axis=1) - 1).max() < 1e-6
+
+
+def test_camera_matches_oracle():
+    for (w, h, screen, fov) in ((1024, 768, (-1.0, -0.75, 1.0, 0.7), 1.2707964), (1920, 1080, (-16 / 9, -1.0, 16 / 9, 1.0), math.pi / 2), (3840, 2160, (-1.0, -0.75, 1.0, 0.7), 1.2707964)):
+        view = np.eye(4, dtype=np.float32); view[3, :3] = (0.5, -0.25, 3.0)
+        for pv in (np.eye(4, dtype=np.float32), view):
+            assert bytes(api.make_camera(pv, screen, 0.1, 1000.0, fov, w, h)) == bytes(O.camera_make(pv, screen, 0.1, 1000.0, fov, w, h))
+    with pytest.raises(api.ArnError):
+        api.make_camera(np.zeros((4, 4), np.float32), (-1, -1, 1, 1), 0.1, 1000.0, 1.0, 64, 64)     # "matrix inversion failure"
+    with pytest.raises(api.ArnError):
+        api.make_camera(np.eye(4), (-1, -1, 1, 1), 10.0, 1.0, 1.0, 64, 64)                            # assert!(znear < zfar)
+
+
+def test_sphere_construction_matches_oracle():
+    hs = api.HostScene()
+    m = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5), sigma=3.0))
+    hs.add_sphere(1.5, -2.0, 2.0, 6.28, m, emission=(15.5, 10.5, 5.5), transform=np.float32([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [-3, 0, -4.5, 1]]))
+    hs.add_sphere(1.0, -0.5, 0.25, 9.0, m)            # clamps phimax to 2 pi, keeps z range
+    d = hs.build()
+    s0, s1 = d.spheres[0], d.spheres[1]
+    o = L.Sphere(); O.load().arn_oracle_sphere_new(1.5, -2.0, 2.0, 6.28, C.byref(o))
+    assert (s0.radius, s0.zmin, s0.zmax, s0.phimax, s0.thetamin, s0.thetamax) == (o.radius, o.zmin, o.zmax, o.phimax, o.thetamin, o.thetamax)
+    assert s0.zmin == -1.5 and s0.zmax == 1.5 and s0.has_transform == 1 and s0.emissive == 1
+    inv = np.zeros(16, np.float32)
+    assert O.load().arn_oracle_m4_invert(O._p(np.ascontiguousarray(s0.local_parent, np.float32)), O._p(inv)) == 0
+    assert np.array_equal(inv, np.array(s0.parent_local, np.float32))
+    assert s1.phimax == np.float32(2 * np.float32(math.pi)) and s1.has_transform == 0 and s1.emissive == 0
+    assert abs(O.load().arn_oracle_light_power_y(C.byref(s0)) - d.light_func[0]) == 0.0
+    # sphere bounds through BBox3::apply_transform vs the oracle's ComponentInfo::new
+    ob, oc = O.prim_bounds(d)
+    assert np.array_equal(ob[0], np.float32([-4.5, -1.5, -6.0, -1.5, 1.5, -3.0])) and oc.tolist() == [2.0, 1.0]
+    with pytest.raises(api.ArnError):
+        hs.add_sphere(-1.0, -1, 1, 1, m)              # assert!(radius > 0)
+    with pytest.raises(api.ArnError):
+        hs.add_sphere(1.0, 0.5, 0.5, 1, m)            # assert!(zmin < zmax)
+
+
+def test_obj_loader_small(tmp_path):
+    """tobj semantics on a hand-written file: groups, usemtl split, (v,vt,vn) re-indexing, quad fan,
+    negative indices, material choice rules of load_obj (component/mod.rs:118-164)."""
+    (tmp_path / "t.mtl").write_text(
+        "newmtl glass\nNs 10\nNi 1.5\nd 0.5\nillum 4\nKd 0.7 0.7 0.7\nKs 1 1 1\n"
+        "newmtl shiny\nNs 200\nKd 0.1 0.2 0.3\nKs 0.5 0.5 0.5\n"
+        "newmtl dull\nKd 0.4 0.4 0.4\nKs 0 0 0\n"
+        "newmtl ghost\nd 0.25\nKd 1 1 1\nKs 0 0 0\n")
+    (tmp_path / "t.obj").write_text(
+        "mtllib t.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n"
+        "g quad\nusemtl glass\nf 1/1/1 2/2/1 3/3/1 4/4/1\n"
+        "g two\nusemtl shiny\nf 1 2 3\nusemtl dull\nf -4 -3 -2\n"
+        "g nomtl\nusemtl missing\nf 1//1 3//1 4//1\n"
+        "g t\nusemtl ghost\nf 2 3 4\n")
+    hs = api.HostScene()
+    assert hs.load_obj(tmp_path / "t.obj") == 6
+    d = hs.build()
+    a = _desc_arrays(d)
+    assert d.n_meshes == 5 and d.n_triangles == 6
+    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 12)
+    fm = np.frombuffer(a["materials"], dtype=np.float32).reshape(-1, 12)
+    assert mats[:, 0].tolist() == [L.ARN_MAT_GLASS, L.ARN_MAT_PLASTIC, L.ARN_MAT_MATTE, L.ARN_MAT_TRANSLUCENT, L.ARN_MAT_MATTE]
+    assert fm[0, 10] == np.float32(1.5) and fm[3, 11] == np.float32(0.25) and fm[1, 8] == np.float32(0.8)      # eta, dissolve, roughness (1000-200)/1000
+    assert np.allclose(fm[4, 1:4], (0.5, 0.6, 0.7))                       # fallback material
+    meshes = np.frombuffer(a["meshes"], dtype=np.uint32).reshape(-1, 4)
+    assert meshes[:, 0].tolist() == [0, 1, 2, 4, 3] and meshes[:, 1].tolist() == [1, 0, 0, 1, 0] and meshes[:, 2].tolist() == [1, 0, 0, 0, 0]
+    assert a["indices"][:2].tolist() == [[0, 1, 2], [0, 2, 3]]              # quad fanned from its first vertex
+    with pytest.raises(api.ArnError):
+        api.HostScene().load_obj(tmp_path / "missing.obj")
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not present (GPU box)")
+def test_json_and_obj_loader_match_fixture():
+    """arencli parse_input on the reference's cb.json + OBJ/MTL == the scene assembled from the
+    committed fixture (which an independent Python parser produced)."""
+    hs = api.HostScene()
+    cam, film, smp, prm, out = hs.load_json(os.path.join(REF, "cb.json"), base_dir="/root/reference")
+    hs.build()
+    a = _desc_arrays(hs.desc())
+    fs, fcam, ffilm, fsmp, fprm = scenes.cornell_scene(1024, 768, 32, 32)
+    b = _desc_arrays(fs.desc())
+    for k in ("positions", "normals", "uvs", "indices", "tri_mesh", "prims"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert a["meshes"] == b["meshes"] and a["spheres"] == b["spheres"]
+    # material tables: same entries; the fixture scene appends the sphere material after the OBJ ones as well
+    ma, mb = np.frombuffer(a["materials"], np.uint32).reshape(-1, 12), np.frombuffer(b["materials"], np.uint32).reshape(-1, 12)
+    assert ma.shape == mb.shape
+    assert np.array_equal(ma[:, :10], mb[:, :10])                      # type, kd, ks, sigma, roughness, alpha
+    glass = ma[:, 0] == L.ARN_MAT_GLASS
+    assert np.array_equal(ma[glass, 10], mb[glass, 10])                # eta only matters for Glass
+    assert np.array_equal(hs.nodes(), fs.nodes()) and np.array_equal(hs.order(), fs.order())
+    assert bytes(cam) == bytes(fcam)
+    assert (film.res_x, film.res_y, film.crop_max_x, film.crop_max_y, film.filter_radius_x) == (1024, 768, 1024, 768, 4.0)
+    assert (smp.sampledx, smp.sampledy, smp.ndim) == (32, 32, 8) and prm.max_depth == 8
+    assert out.endswith("CornellBox-Glossy44.png")
+
+
+def test_json_errors(tmp_path):
+    p = tmp_path / "bad.json"
+    p.write_text("{ not json")
+    with pytest.raises(api.ArnError) as e:
+        api.HostScene().load_json(p)
+    assert e.value.code == L.ARN_E_IO
+    p.write_text('{"lights": [{"Point": {}}], "components": []}')
+    with pytest.raises(api.ArnError) as e:
+        api.HostScene().load_json(p)
+    assert e.value.code == L.ARN_E_UNSUPPORTED
