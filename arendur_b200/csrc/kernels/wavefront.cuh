@@ -387,7 +387,7 @@ __global__ void k_next_bounce(Queues q, int cur) { q.counts[cur] = 0; q.counts[2
 __global__ void k_begin_wave(Queues q, uint32_t n) { q.counts[0] = n; q.counts[1] = 0; q.counts[2] = 0; for (int c = 0; c < ARN_NCLS; c++) q.counts[3 + c] = 0; }
 
 // ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
-ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return sinf(xpi) / xpi; }
+ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return cr_sinf(xpi) / xpi; }
 ARN_DEV float lanczos1(float x) { return sinc1(x * (1.f / 3.f)) * sinc1(x); }        // tau = 3 (film.rs:47-51)
 
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
