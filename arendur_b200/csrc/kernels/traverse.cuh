@@ -187,6 +187,23 @@ static __device__ __noinline__ void sphere_slot(const DevScene& sc, uint32_t com
 // the reference's shadow rays run the closest-hit query and only look at is_some(),
 // component/mod.rs:35-38, so the boolean is identical).
 // COUNT: accumulate nodes/primitives tested into ctr[0..2] (for the algorithmic-bytes figure).
+// pop the next stack entry whose entry distance is still below tmax; false when the stack is empty
+ARN_DEV bool trav_pop(const DevScene& sc, const TravRay& r, const uint2* stack, int& sp,
+                      uint32_t& idx, uint32_t& offset, uint32_t& len_axis) {
+    for (;;) {
+        if (sp == 0) return false;
+        uint2 e = stack[--sp];
+        if (__uint_as_float(e.y) < r.tmax) {
+            idx = e.x;
+            float4 n1 = __ldg(&sc.nodes[2 * idx + 1]);
+            offset = __float_as_uint(n1.z); len_axis = __float_as_uint(n1.w);
+            return true;
+        }
+    }
+}
+
+// "while-while" form (Aila & Laine): all lanes of a warp first descend through interior nodes,
+// then test leaf primitives together, so the long triangle test runs with many lanes active.
 template <bool ANY, bool COUNT>
 ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
     h.prim = -1; h.t = ARN_INF; h.a = h.b = h.c = 0.f;
@@ -200,9 +217,9 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
     uint32_t idx = 0;
     uint32_t offset = __float_as_uint(q1.z), len_axis = __float_as_uint(q1.w);
     for (;;) {
-        uint32_t len = len_axis >> 2;
-        if (len == 0) {
-            // interior: expand both children (first child = idx+1, second = idx+offset)
+        // ---- interior nodes: expand both children (first child = idx+1, second = idx+offset)
+        bool alive = true;
+        while ((len_axis >> 2) == 0) {
             uint32_t ia = idx + 1, ib = idx + offset;
             float4 a0 = __ldg(&sc.nodes[2 * ia]), a1 = __ldg(&sc.nodes[2 * ia + 1]);
             float4 b0 = __ldg(&sc.nodes[2 * ib]), b1 = __ldg(&sc.nodes[2 * ib + 1]);
@@ -210,41 +227,35 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
             float ta, tb;
             bool ha = slab(a0, a1, r, ta) && ta < r.tmax;
             bool hb = slab(b0, b1, r, tb) && tb < r.tmax;
-            uint32_t axis = len_axis & 3u;
-            bool neg = axis_of(r.inv, (int)axis) < 0.f;       // dir_is_neg[split_axis]: second child first
+            bool neg = axis_of(r.inv, (int)(len_axis & 3u)) < 0.f;     // dir_is_neg[split_axis]: second child first
             if (ha && hb) {
-                if (neg) { stack[sp++] = make_uint2(ia, __float_as_uint(ta)); idx = ib; offset = __float_as_uint(b1.z); len_axis = __float_as_uint(b1.w); }
-                else     { stack[sp++] = make_uint2(ib, __float_as_uint(tb)); idx = ia; offset = __float_as_uint(a1.z); len_axis = __float_as_uint(a1.w); }
-                continue;
-            } else if (ha) { idx = ia; offset = __float_as_uint(a1.z); len_axis = __float_as_uint(a1.w); continue; }
-            else if (hb) { idx = ib; offset = __float_as_uint(b1.z); len_axis = __float_as_uint(b1.w); continue; }
-        } else {
-            for (uint32_t k = offset; k < offset + len; k++) {
-                float4 v0 = __ldg(&sc.tris[3 * k]);
-                uint32_t comp = __float_as_uint(v0.w);          // component id, sphere bit set for sphere slots
-                if (comp & ARN_PRIM_SPHERE) { if (COUNT) ctr[2]++; sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h); }
-                else {
-                    float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
-                    if (COUNT) ctr[1]++;
-                    float t, b0, b1, b2;
-                    if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
-                        r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
-                    }
+                bool first_b = neg;
+                stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(ta)) : make_uint2(ib, __float_as_uint(tb));
+                idx = first_b ? ib : ia;
+                offset = __float_as_uint(first_b ? b1.z : a1.z); len_axis = __float_as_uint(first_b ? b1.w : a1.w);
+            } else if (ha || hb) {
+                idx = ha ? ia : ib;
+                offset = __float_as_uint(ha ? a1.z : b1.z); len_axis = __float_as_uint(ha ? a1.w : b1.w);
+            } else if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) { alive = false; break; }
+        }
+        if (!alive) return;
+        // ---- leaf: primitives in slot order, strict `<` acceptance
+        const uint32_t end = offset + (len_axis >> 2);
+        for (uint32_t k = offset; k < end; k++) {
+            float4 v0 = __ldg(&sc.tris[3 * k]);
+            uint32_t comp = __float_as_uint(v0.w);          // component id, sphere bit set for sphere slots
+            if (comp & ARN_PRIM_SPHERE) { if (COUNT) ctr[2]++; sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h); }
+            else {
+                float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
+                if (COUNT) ctr[1]++;
+                float t, b0, b1, b2;
+                if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
+                    r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
                 }
-                if (ANY && h.prim >= 0) return;
             }
+            if (ANY && h.prim >= 0) return;
         }
-        // pop: skip entries whose entry distance is no longer below tmax
-        for (;;) {
-            if (sp == 0) return;
-            uint2 e = stack[--sp];
-            if (__uint_as_float(e.y) < r.tmax) {
-                idx = e.x;
-                float4 n1 = __ldg(&sc.nodes[2 * idx + 1]);
-                offset = __float_as_uint(n1.z); len_axis = __float_as_uint(n1.w);
-                break;
-            }
-        }
+        if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
     }
 }
 

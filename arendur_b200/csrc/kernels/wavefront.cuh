@@ -18,6 +18,9 @@
 namespace arn {
 
 #define ARN_BLOCK 256
+#ifndef ARN_SHADE_MINB
+#define ARN_SHADE_MINB 2
+#endif
 
 struct PathBuf {                 // SoA over path slots, capacity W
     float4* ray_o;               // origin xyz
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Q
 
 // ---- K3 shade ------------------------------------------------------------------------------------
 // launched once per shading class: every warp shades one kind of material
-__global__ void __launch_bounds__(ARN_BLOCK) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur, int cls) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur, int cls) {
     const uint32_t n = q.counts[3 + cls];
     const uint32_t* __restrict__ ids = q.cls[cls];
     uint32_t* next = q.active[cur ^ 1];
