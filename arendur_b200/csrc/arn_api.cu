@@ -447,11 +447,10 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             if (c->opt_count) k_extend<true><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
             else k_extend<false><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
-            for (int cls = 0; cls < ARN_NCLS; cls++)
-                if (s->class_mask & (1u << cls)) { k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur, cls); launches++; }
+            k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur);
             k_connect<<<c->g_connect, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q);
             k_next_bounce<<<1, 1, 0, c->stream>>>(c->q, cur);
-            launches += 3;
+            launches += 4;
             cur ^= 1;
         }
         k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);

@@ -204,17 +204,29 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Q
 }
 
 // ---- K3 shade ------------------------------------------------------------------------------------
-// launched once per shading class: every warp shades one kind of material
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur, int cls) {
-    const uint32_t n = q.counts[3 + cls];
-    const uint32_t* __restrict__ ids = q.cls[cls];
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
+    // One launch over the concatenation of the class queues, each padded to a multiple of 32 so that
+    // every warp shades ONE material class; heavy classes (glass, plastic) first, so that the tail of
+    // the launch is made of cheap Lambert work and near-empty classes cost no launch of their own.
+    const uint32_t ORDER = 0x01423u;                    // nibble k = class shaded k-th: 3, 2, 4, 1, 0
+    uint32_t seg_start[ARN_NCLS + 1];
+    seg_start[0] = 0;
+#pragma unroll
+    for (int k = 0; k < ARN_NCLS; k++) seg_start[k + 1] = seg_start[k] + ((q.counts[3 + ((ORDER >> (4 * k)) & 0xFu)] + 31u) & ~31u);
     uint32_t* next = q.active[cur ^ 1];
     __shared__ uint32_t stage_rows[2][ARN_BLOCK / 32][64];
     WarpStage st_next, st_conn;
     st_next.row = stage_rows[0][threadIdx.x >> 5]; st_next.fill = 0;
     st_conn.row = stage_rows[1][threadIdx.x >> 5]; st_conn.fill = 0;
-    const uint32_t n_round = (n + 31u) & ~31u;          // warp-uniform trip count
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const uint32_t n_round = seg_start[ARN_NCLS];       // multiple of 32: warp-uniform trip count
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_round; gi += gridDim.x * blockDim.x) {
+        uint32_t k = 0, base = 0;
+#pragma unroll
+        for (int j = 1; j < ARN_NCLS; j++) if (gi >= seg_start[j]) { k = (uint32_t)j; base = seg_start[j]; }
+        const uint32_t cls = (ORDER >> (4 * k)) & 0xFu;
+        const uint32_t i = gi - base;
+        const uint32_t n = q.counts[3 + cls];
+        const uint32_t* __restrict__ ids = q.cls[cls];
         bool alive = false, nee = false;
         uint32_t pid = 0;
         if (i < n) {
