@@ -18,6 +18,9 @@
 namespace arn {
 
 #define ARN_BLOCK 256
+#ifndef ARN_TRAV_MINB
+#define ARN_TRAV_MINB 3
+#endif
 #ifndef ARN_SHADE_MINB
 #define ARN_SHADE_MINB 2
 #endif
@@ -159,7 +162,7 @@ ARN_DEV int shading_class(const arn_material& m) {
     }
 }
 template <bool COUNT>
-__global__ void __launch_bounds__(ARN_BLOCK) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t n = q.counts[cur];
     const uint32_t* __restrict__ ids = q.active[cur];
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
 }
 
 // ---- K4 connect: shadow ray (any hit) + BSDF-sampled light ray (closest hit), then resolve -----
-__global__ void __launch_bounds__(ARN_BLOCK) k_connect(DevScene sc, PathBuf pb, Queues q) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_connect(DevScene sc, PathBuf pb, Queues q) {
     const uint32_t n = q.counts[2];
     unsigned long long n_sh = 0, n_mis = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_const
 
 // ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(ARN_BLOCK) k_closest_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
                                                              unsigned long long* ctr_out) {
     uint32_t ctr[3] = {0, 0, 0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_closest_batch(DevScene sc, const 
         if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr_out[0], a); atomicAdd(&ctr_out[1], b); atomicAdd(&ctr_out[2], c); }
     }
 }
-__global__ void __launch_bounds__(ARN_BLOCK) k_any_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);

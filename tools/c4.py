@@ -1,0 +1,31 @@
+"""C4: 20 000 172-triangle closed box, incoherent diffuse bounces, depth 8.
+usage: python tools/c4.py [cells] [res] [sppx]   (no GPU: build only)"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from arendur_b200 import api, scenes, _lib as L
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 1291
+res = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+sx = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+t = time.time()
+hs, cam, film, smp, prm = scenes.c4_box_scene(cells=cells, res=res, sampledx=sx, sampledy=sx)
+d = hs.desc()
+print(f"c4 cells={cells}: {d.n_triangles} triangles, {d.n_nodes} nodes, build+flatten {time.time()-t:.1f} s", flush=True)
+import torch
+if not torch.cuda.is_available():
+    sys.exit(0)
+ctx = api.Context(0)
+t = time.time(); sc = ctx.upload(d); print(f"upload {time.time()-t:.1f} s")
+for rep in range(2):
+    f, st = sc.render_pt(cam, film, smp, prm)
+rays = st.extend_rays + st.shadow_rays + st.mis_rays
+print(f"c4 render {res}^2 x {sx*sx} spp: {st.gpu_ms:.1f} ms, all rays {rays/st.gpu_ms/1e3:.1f} Mrays/s; extend {st.extend_rays} rays in {st.extend_ms:.1f} ms = {st.extend_rays/st.extend_ms/1e3:.1f} Mrays/s; "
+      f"incoherent (bounce>=1) {st.extend_bounce_rays} rays in {st.extend_bounce_ms:.1f} ms = {st.extend_bounce_rays/max(st.extend_bounce_ms,1e-9)/1e3:.1f} Mrays/s; invalid {st.invalid_samples}")
+ctx.set_option(L.ARN_OPT_COUNT_TRAVERSAL, 1)
+p1 = api.make_pt_params(max_depth=8, spp_begin=0, spp_end=1)
+f, stc = sc.render_pt(cam, film, smp, p1)
+bpr = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_spheres) / stc.extend_rays + 36
+print(f"Nn/ray {stc.extend_nodes/stc.extend_rays:.1f} Nt/ray {stc.extend_tris/stc.extend_rays:.2f} bytes/ray {bpr:.0f} -> extend algorithmic {bpr*st.extend_rays/st.extend_ms/1e6:.0f} GB/s of 6457 measured")
+g, _ = api.film_finalize(f)
+print("image mean", g.reshape(-1, 3).mean(0), "finite", np.isfinite(g).all())
