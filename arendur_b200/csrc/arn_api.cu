@@ -37,7 +37,7 @@ struct arn_ctx {
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> events;
     // launch geometry (blocks per kernel, persistent grid-stride)
-    int g_generate = 0, g_extend = 0, g_shade = 0, g_connect = 0, g_accum = 0, g_closest = 0, g_any = 0;
+    int g_generate = 0, g_trace = 0, g_shade = 0, g_resolve = 0, g_accum = 0, g_closest = 0, g_any = 0;
     // scratch for batched queries through host buffers
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
@@ -97,8 +97,8 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     size_t o_pfilm = carve(cap * 8), o_pix = carve(cap * 4), o_smp = carve(cap * 4), o_st = carve(cap * 4);
     size_t o_hp = carve(cap * 4), o_hit = carve(cap * 16);
     size_t o_sho = carve(cap * 16), o_shd = carve(cap * 16), o_mo = carve(cap * 16), o_md = carve(cap * 16);
-    size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16);
-    size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4);
+    size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16), o_occ = carve(cap * 4), o_mok = carve(cap * 4);
+    size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4), o_qs = carve(cap * 4), o_qm = carve(cap * 4);
     size_t o_cls[ARN_NCLS]; for (int k = 0; k < ARN_NCLS; k++) o_cls[k] = carve(cap * 4);
     size_t o_counts = carve(64), o_stats = carve(64);
     CUDA_TRY(c, cudaMalloc(&c->pool, off));
@@ -109,7 +109,8 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     c->pb.hit_prim = (int*)(b + o_hp); c->pb.hit = (float4*)(b + o_hit);
     c->pb.sh_o = (float4*)(b + o_sho); c->pb.sh_d = (float4*)(b + o_shd); c->pb.mis_o = (float4*)(b + o_mo); c->pb.mis_d = (float4*)(b + o_md);
     c->pb.a1 = (float4*)(b + o_a1); c->pb.a2 = (float4*)(b + o_a2); c->pb.beta_old = (float4*)(b + o_bo);
-    c->q.active[0] = (uint32_t*)(b + o_q0); c->q.active[1] = (uint32_t*)(b + o_q1); c->q.connect = (uint32_t*)(b + o_qc);
+    c->pb.occluded = (uint32_t*)(b + o_occ); c->pb.mis_ok = (uint32_t*)(b + o_mok);
+    c->q.active[0] = (uint32_t*)(b + o_q0); c->q.active[1] = (uint32_t*)(b + o_q1); c->q.connect = (uint32_t*)(b + o_qc); c->q.shadow = (uint32_t*)(b + o_qs); c->q.mis = (uint32_t*)(b + o_qm);
     for (int k = 0; k < ARN_NCLS; k++) c->q.cls[k] = (uint32_t*)(b + o_cls[k]);
     c->q.counts = (uint32_t*)(b + o_counts); c->q.stats = (unsigned long long*)(b + o_stats);
     c->wave_cap = cap;
@@ -149,9 +150,9 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->g_generate = grid_for(c, (const void*)k_generate);
-    c->g_extend = grid_for(c, (const void*)k_extend<false>);
+    c->g_trace = grid_for(c, (const void*)k_trace<false>);
     c->g_shade = grid_for(c, (const void*)k_shade);
-    c->g_connect = grid_for(c, (const void*)k_connect);
+    c->g_resolve = grid_for(c, (const void*)k_resolve);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
     c->g_closest = grid_for(c, (const void*)k_closest_batch<false>);
     c->g_any = grid_for(c, (const void*)k_any_batch);
@@ -442,16 +443,24 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, base, n);
         launches += 2;
         int cur = 0;
-        for (uint32_t b = 0; b < prm->max_depth; b++) {
-            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, (int)b}); }
-            if (c->opt_count) k_extend<true><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
-            else k_extend<false><<<c->g_extend, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, (int)b);
+        auto trace = [&](int first, int bounce) {
+            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, bounce}); }
+            if (c->opt_count) k_trace<true><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
+            else k_trace<false><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
+        };
+        trace(1, 0);                                               // camera rays
+        launches += 1;
+        const uint32_t CLS_MASK = 0xF8u, NEE_MASK = (1u << 2) | (1u << 10) | (1u << 11);
+        for (uint32_t b = 0; b < prm->max_depth; b++) {
+            // shade(b): consumes the class queues, fills active[cur^1] + connect / shadow / light-ray queues
             k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur);
-            k_connect<<<c->g_connect, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q);
-            k_next_bounce<<<1, 1, 0, c->stream>>>(c->q, cur);
-            launches += 4;
+            k_reset<<<1, 1, 0, c->stream>>>(c->q, CLS_MASK | (1u << cur));
             cur ^= 1;
+            trace(0, (int)b + 1);                                  // path rays of bounce b+1, shadow + light rays of bounce b
+            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, c->stream>>>(c->pb, c->q);
+            k_reset<<<1, 1, 0, c->stream>>>(c->q, NEE_MASK);
+            launches += 5;
         }
         k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
         launches += 1;

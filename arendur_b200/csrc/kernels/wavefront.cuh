@@ -1,7 +1,9 @@
 // Wavefront path-tracing kernels for sm_100a (K1..K7 of SURVEY.md §2.1).
 //
 // One "wave" = up to W camera samples processed bounce by bounce:
-//   k_generate -> [ k_extend -> k_shade -> k_connect ] x max_depth -> k_accumulate
+//   k_generate -> k_trace -> [ k_shade -> k_trace -> k_resolve ] x max_depth -> k_accumulate
+// k_trace handles, in ONE launch, the path rays of the next bounce plus the shadow rays and the
+// BSDF-sampled light rays of the current one (three warp-uniform segments of one ray queue).
 // Stages are separate kernels linked by compacted queues of path ids; the queues are built
 // in k_shade with warp ballots + shared-memory staging (one global atomic per block
 // iteration).  All launches are grid-stride over DEVICE-side counters, so a whole wave is
@@ -44,6 +46,8 @@ struct PathBuf {                 // SoA over path slots, capacity W
     float4* a1;                  // light-sampling term rgb, w = light choice pdf
     float4* a2;                  // BSDF-sampling term rgb, w = light component id (bits)
     float4* beta_old;            // throughput before this bounce's BSDF sample, w = flags (bits)
+    uint32_t* occluded;          // 1 = the shadow ray was blocked (written by k_trace)
+    uint32_t* mis_ok;            // 1 = the BSDF-sampled ray reached the chosen light and saw its emission
 };
 #define NEE_DONE 1u
 #define NEE_SHADOW 2u
@@ -53,8 +57,10 @@ struct PathBuf {                 // SoA over path slots, capacity W
 struct Queues {
     uint32_t* active[2];         // path ids for the current / next bounce
     uint32_t* connect;           // path ids with a pending direct-light term
+    uint32_t* shadow;            // path ids with a shadow ray to trace
+    uint32_t* mis;               // path ids with a BSDF-sampled light ray to trace
     uint32_t* cls[ARN_NCLS];     // hits of the current bounce, sorted by shading class (material sort)
-    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size, [3+c] = class c size
+    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size, [3+c] = class c size, [10] = shadow rays, [11] = mis rays
     unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1 [5..7] nodes/tris/spheres tested by extend (COUNT builds)
 };
 
@@ -161,43 +167,79 @@ ARN_DEV int shading_class(const arn_material& m) {
     default: return 4;
     }
 }
+// K2/K4 trace: one launch over [path rays of queue `cur`] ++ [shadow rays] ++ [BSDF-sampled light rays],
+// each segment padded to a multiple of 32 so that a warp runs one kind of query.
+//   path ray   : closest hit -> hit record; hits sorted into the per-material-class queues
+//   shadow ray : any hit (LightSample::occluded, lighting/mod.rs:125-133)      -> occluded[pid]
+//   light ray  : closest hit, `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155) -> mis_ok[pid]
 template <bool COUNT>
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_extend(DevScene sc, PathBuf pb, Queues q, int cur, int bounce) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc, PathBuf pb, Queues q, int cur, int first) {
     uint32_t ctr[3] = {0, 0, 0};
-    const uint32_t n = q.counts[cur];
+    const uint32_t n_ext = q.counts[cur], n_sh = q.counts[10], n_mis = q.counts[11];
+    const uint32_t s1 = (n_ext + 31u) & ~31u, s2 = s1 + ((n_sh + 31u) & ~31u), s3 = s2 + ((n_mis + 31u) & ~31u);
     const uint32_t* __restrict__ ids = q.active[cur];
     __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
     WarpStage st[ARN_NCLS];
 #pragma unroll
     for (int c = 0; c < ARN_NCLS; c++) { st[c].row = stage_rows[c][threadIdx.x >> 5]; st[c].fill = 0; }
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        uint32_t pid = 0; int cls = -1;
-        if (i < n) {
-            pid = ids[i];
-            float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
-            TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
-            HitRec h;
-            traverse<false, COUNT>(sc, r, h, ctr);
-            pb.hit_prim[pid] = h.prim;
-            pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
-            if (h.prim >= 0) {
-                uint32_t ref = sc.prims[h.prim], mat;
-                if (ref & ARN_PRIM_SPHERE) {
-                    mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
-                    pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
-                } else mat = sc.meshes[sc.tri_mesh[ref]].material;
-                cls = shading_class(sc.materials[mat]);
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {
+        if (gi < s1) {
+            uint32_t pid = 0; int cls = -1;
+            if (gi < n_ext) {
+                pid = ids[gi];
+                float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
+                TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
+                HitRec h;
+                traverse<false, COUNT>(sc, r, h, ctr);
+                pb.hit_prim[pid] = h.prim;
+                pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
+                if (h.prim >= 0) {
+                    uint32_t ref = sc.prims[h.prim], mat;
+                    if (ref & ARN_PRIM_SPHERE) {
+                        mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
+                        pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
+                    } else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                    cls = shading_class(sc.materials[mat]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < ARN_NCLS; c++) stage_push(st[c], cls == c, pid, q.cls[c], &q.counts[3 + c]);
+        } else if (gi < s2) {
+            uint32_t j = gi - s1;
+            if (j < n_sh) {
+                uint32_t pid = q.shadow[j];
+                float4 o = pb.sh_o[pid], d = pb.sh_d[pid];
+                TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
+                HitRec h; traverse<true, COUNT>(sc, r, h, ctr);
+                pb.occluded[pid] = h.prim >= 0 ? 1u : 0u;
+            }
+        } else {
+            uint32_t j = gi - s2;
+            if (j < n_mis) {
+                uint32_t pid = q.mis[j];
+                float4 o = pb.mis_o[pid], d = pb.mis_d[pid];
+                float3 wi = f3(d.x, d.y, d.z);
+                TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
+                HitRec h; traverse<false, COUNT>(sc, r, h, ctr);
+                uint32_t lcomp = __float_as_uint(pb.a2[pid].w);
+                uint32_t ok = 0;
+                if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
+                    const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
+                    float3 pos = f3(h.a, h.b, h.c);
+                    if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
+                    ok = is_black(light_le(sp, pos, -wi)) ? 0u : 1u;       // lsi.le(-wi)
+                }
+                pb.mis_ok[pid] = ok;
             }
         }
-#pragma unroll
-        for (int c = 0; c < ARN_NCLS; c++) stage_push(st[c], cls == c, pid, q.cls[c], &q.counts[3 + c]);
     }
 #pragma unroll
     for (int c = 0; c < ARN_NCLS; c++) stage_flush(st[c], q.cls[c], &q.counts[3 + c]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        atomicAdd(&q.stats[0], (unsigned long long)n);
-        if (bounce > 0) atomicAdd(&q.stats[4], (unsigned long long)n);
+        atomicAdd(&q.stats[0], (unsigned long long)n_ext);
+        atomicAdd(&q.stats[1], (unsigned long long)n_sh);
+        atomicAdd(&q.stats[2], (unsigned long long)n_mis);
+        if (!first) atomicAdd(&q.stats[4], (unsigned long long)(n_ext + n_sh + n_mis));
     }
     if (COUNT) {
         unsigned long long a = ctr[0], b = ctr[1], c = ctr[2];
@@ -217,10 +259,12 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
 #pragma unroll
     for (int k = 0; k < ARN_NCLS; k++) seg_start[k + 1] = seg_start[k] + ((q.counts[3 + ((ORDER >> (4 * k)) & 0xFu)] + 31u) & ~31u);
     uint32_t* next = q.active[cur ^ 1];
-    __shared__ uint32_t stage_rows[2][ARN_BLOCK / 32][64];
-    WarpStage st_next, st_conn;
+    __shared__ uint32_t stage_rows[4][ARN_BLOCK / 32][64];
+    WarpStage st_next, st_conn, st_sh, st_mis;
     st_next.row = stage_rows[0][threadIdx.x >> 5]; st_next.fill = 0;
     st_conn.row = stage_rows[1][threadIdx.x >> 5]; st_conn.fill = 0;
+    st_sh.row = stage_rows[2][threadIdx.x >> 5]; st_sh.fill = 0;
+    st_mis.row = stage_rows[3][threadIdx.x >> 5]; st_mis.fill = 0;
     const uint32_t n_round = seg_start[ARN_NCLS];       // multiple of 32: warp-uniform trip count
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_round; gi += gridDim.x * blockDim.x) {
         uint32_t k = 0, base = 0;
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
         const uint32_t i = gi - base;
         const uint32_t n = q.counts[3 + cls];
         const uint32_t* __restrict__ ids = q.cls[cls];
-        bool alive = false, nee = false;
+        bool alive = false, nee = false, has_sh = false, has_mis = false;
         uint32_t pid = 0;
         if (i < n) {
             pid = ids[i];
@@ -292,7 +336,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
                             float3 vd = v / len;
                             pb.sh_o[pid] = make_float4(a.x, a.y, a.z, len);
                             pb.sh_d[pid] = make_float4(vd.x, vd.y, vd.z, 0.f);
-                            flags |= NEE_SHADOW;
+                            flags |= NEE_SHADOW; has_sh = true;
                         }
                     }
                     // BSDF sampling half
@@ -310,7 +354,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
                             A2 = f2v * sphere_emission(light) * weight / bs.pdf;
                             pb.mis_o[pid] = make_float4(mo.x, mo.y, mo.z, 0.f);
                             pb.mis_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
-                            flags |= NEE_MIS;
+                            flags |= NEE_MIS; has_mis = true;
                         }
                     }
                     pb.a1[pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
@@ -353,56 +397,37 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
         }
         stage_push(st_next, alive, pid, next, &q.counts[cur ^ 1]);
         stage_push(st_conn, nee, pid, q.connect, &q.counts[2]);
+        stage_push(st_sh, has_sh, pid, q.shadow, &q.counts[10]);
+        stage_push(st_mis, has_mis, pid, q.mis, &q.counts[11]);
     }
     stage_flush(st_next, next, &q.counts[cur ^ 1]);
     stage_flush(st_conn, q.connect, &q.counts[2]);
+    stage_flush(st_sh, q.shadow, &q.counts[10]);
+    stage_flush(st_mis, q.mis, &q.counts[11]);
 }
 
-// ---- K4 connect: shadow ray (any hit) + BSDF-sampled light ray (closest hit), then resolve -----
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_connect(DevScene sc, PathBuf pb, Queues q) {
+// ---- resolve: L += beta * (light term + BSDF term) / p_light  (evaluate_direct's sum, pt.rs:89) -----
+__global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q) {
     const uint32_t n = q.counts[2];
-    unsigned long long n_sh = 0, n_mis = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pid = q.connect[i];
         float4 bo = pb.beta_old[pid];
         uint32_t flags = __float_as_uint(bo.w);
         float4 a1 = pb.a1[pid], a2 = pb.a2[pid];
         float3 ret = f3(a1.x, a1.y, a1.z);
-        if (flags & NEE_SHADOW) {
-            float4 o = pb.sh_o[pid], d = pb.sh_d[pid];
-            TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
-            HitRec h; traverse<true, false>(sc, r, h, nullptr);
-            if (h.prim >= 0) ret = grey(0.f);
-            n_sh++;
-        }
-        if (flags & NEE_MIS) {
-            float4 o = pb.mis_o[pid], d = pb.mis_d[pid];
-            float3 wi = f3(d.x, d.y, d.z);
-            TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
-            HitRec h; traverse<false, false>(sc, r, h, nullptr);
-            uint32_t lcomp = __float_as_uint(a2.w);
-            n_mis++;
-            if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
-                const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
-                float3 pos = f3(h.a, h.b, h.c);
-                if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
-                float3 li = light_le(sp, pos, -wi);                       // lsi.le(-wi)
-                if (!is_black(li)) ret = ret + f3(a2.x, a2.y, a2.z);
-            }
-        }
+        if ((flags & NEE_SHADOW) && pb.occluded[pid]) ret = grey(0.f);
+        if ((flags & NEE_MIS) && pb.mis_ok[pid]) ret = ret + f3(a2.x, a2.y, a2.z);
         float3 term = ret / a1.w;                                        // evaluate_direct(..) / lightpdf
         float4 l4 = pb.L[pid];
-        float3 L = f3(l4.x, l4.y, l4.z) + f3(bo.x, bo.y, bo.z) * term;   // ret += beta * term (pt.rs:89)
+        float3 L = f3(l4.x, l4.y, l4.z) + f3(bo.x, bo.y, bo.z) * term;   // ret += beta * term
         pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
     }
-    // warp-aggregated statistics
-    for (int off = 16; off > 0; off >>= 1) { n_sh += __shfl_down_sync(0xffffffffu, n_sh, off); n_mis += __shfl_down_sync(0xffffffffu, n_mis, off); }
-    if ((threadIdx.x & 31) == 0) { if (n_sh) atomicAdd(&q.stats[1], n_sh); if (n_mis) atomicAdd(&q.stats[2], n_mis); }
 }
 
 // resets the queue counters between bounces (single thread)
-__global__ void k_next_bounce(Queues q, int cur) { q.counts[cur] = 0; q.counts[2] = 0; for (int c = 0; c < ARN_NCLS; c++) q.counts[3 + c] = 0; }
-__global__ void k_begin_wave(Queues q, uint32_t n) { q.counts[0] = n; q.counts[1] = 0; q.counts[2] = 0; for (int c = 0; c < ARN_NCLS; c++) q.counts[3 + c] = 0; }
+// single-thread counter maintenance between stages (stream order makes these race free)
+__global__ void k_reset(Queues q, uint32_t mask) { for (int i = 0; i < 16; i++) if (mask & (1u << i)) q.counts[i] = 0; }
+__global__ void k_begin_wave(Queues q, uint32_t n) { for (int i = 0; i < 16; i++) q.counts[i] = 0; q.counts[0] = n; }
 
 // ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
 ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return cr_sinf(xpi) / xpi; }
