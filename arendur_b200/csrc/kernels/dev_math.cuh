@@ -75,6 +75,8 @@ ARN_DEV bool relative_eq(float a, float b) {     // approx::relative_eq!, eps = 
 // 2*eps).  B200's FP64 pipe runs at half the FP32 rate, so this costs a few % of shading time.
 ARN_NOINL float cr_sinf(float x) { return (float)sin((double)x); }
 ARN_NOINL float cr_cosf(float x) { return (float)cos((double)x); }
+// sin and cos of one argument share the range reduction (bit-identical to the separate calls)
+ARN_NOINL void cr_sincosf(float x, float& s, float& c) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
 ARN_NOINL float cr_acosf(float x) { return (float)acos((double)x); }
 ARN_NOINL float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 ARN_NOINL float cr_logf(float x) { return (float)log((double)x); }

@@ -152,7 +152,8 @@ ARN_DEV float2 sample_concentric_disk(float2 u) {
     float r, theta;
     if (fabsf(w.x) > fabsf(w.y)) { r = w.x; theta = ARN_PI_4 * (w.y / w.x); }
     else { r = w.y; theta = ARN_PI_2 - ARN_PI_4 * (w.x / w.y); }
-    return f2(r * cr_cosf(theta), r * cr_sinf(theta));
+    float st, ct; cr_sincosf(theta, st, ct);
+    return f2(r * ct, r * st);
 }
 ARN_DEV float3 sample_cosw_hemisphere(float2 u) {
     float2 d = sample_concentric_disk(u);
@@ -231,7 +232,8 @@ static __device__ __noinline__ float3 sample_wh_beckmann(float3 wo, float2 u, fl
     if (ct > 0.9999f) {
         float r = sqrtf(-cr_logf(u.x));
         float phi = 2.f * u.y * ARN_PI;
-        sx = r * cr_cosf(phi); sy = r * cr_sinf(phi);
+        float sphi, cphi; cr_sincosf(phi, sphi, cphi);
+        sx = r * cphi; sy = r * sphi;
     } else {
         float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
         float tant = st / ct, cott = ct / st;
@@ -270,7 +272,8 @@ static __device__ __noinline__ float3 sample_wh_trowbridge(float3 wo_in, float2 
     if (ct > 0.9999f) {
         float r = sqrtf(u.x / (1.f - u.x));
         float phi = 2.f * u.y * ARN_PI;
-        sx = r * cr_cosf(phi); sy = r * cr_sinf(phi);
+        float sphi, cphi; cr_sincosf(phi, sphi, cphi);
+        sx = r * cphi; sy = r * sphi;
     } else {
         float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
         float tant = st / ct, cott = ct / st;
@@ -590,7 +593,7 @@ ARN_NOINL LightSample light_sample(const DevSphere& sp, float3 pos, float2 u) {
     if (sp.has_transform) pos = xform_point(sp.parent_local, pos);
     float phi = u.x * sp.phimax;                                            // Sphere::sample (sphere.rs:304-311)
     float theta = u.y * (sp.thetamax - sp.thetamin) + sp.thetamin;
-    float st = cr_sinf(theta), ct = cr_cosf(theta), sph = cr_sinf(phi), cph = cr_cosf(phi);
+    float st, ct, sph, cph; cr_sincosf(theta, st, ct); cr_sincosf(phi, sph, cph);
     float3 dir = f3(st * cph, st * sph, ct);
     float3 lp = dir * sp.radius;
     float lpdf = 1.f / sphere_area(sp);

@@ -151,8 +151,15 @@ ARN_NOINL bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, 
     float3 p = o + d * t;
     p = p * sp.radius / length(p);
     if (p.x == 0.f && p.y == 0.f) p.x = 1e-5f * sp.radius;
-    float phi = cr_atan2f(p.y, p.x);
+    // phi > phimax clip: decided with the cheap f32 atan2f unless phi lies within 1e-4 of phimax or of the
+    // 0 / 2pi seam, where the reference's correctly-rounded value is computed (identical decisions:
+    // libdevice atan2f is accurate to ~1e-6, far inside the 1e-4 band).
+    float phi = atan2f(p.y, p.x);
     if (phi < 0.f) phi += 2.f * ARN_PI;
+    if (fabsf(phi - sp.phimax) < 1e-4f || phi < 1e-4f || phi > 2.f * ARN_PI - 1e-4f) {
+        phi = cr_atan2f(p.y, p.x);
+        if (phi < 0.f) phi += 2.f * ARN_PI;
+    }
     if (p.z < sp.zmin || p.z > sp.zmax || phi > sp.phimax) return false;
     t_out = t; p_out = p;
     return true;
