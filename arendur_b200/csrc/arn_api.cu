@@ -37,7 +37,7 @@ struct arn_ctx {
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> events;
     // launch geometry (blocks per kernel, persistent grid-stride)
-    int g_generate = 0, g_trace = 0, g_shade = 0, g_resolve = 0, g_accum = 0, g_closest = 0, g_any = 0;
+    int g_generate = 0, g_trace = 0, g_shade = 0, g_shade_d = 0, g_resolve = 0, g_accum = 0, g_closest = 0, g_any = 0;
     // scratch for batched queries through host buffers
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
@@ -151,7 +151,8 @@ int arn_ctx_create(int device, arn_ctx** out) {
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<false>);
-    c->g_shade = grid_for(c, (const void*)k_shade);
+    c->g_shade = grid_for(c, (const void*)k_shade<false>);
+    c->g_shade_d = grid_for(c, (const void*)k_shade<true>);
     c->g_resolve = grid_for(c, (const void*)k_resolve);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
     c->g_closest = grid_for(c, (const void*)k_closest_batch<false>);
@@ -454,13 +455,14 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         const uint32_t CLS_MASK = 0xF8u, NEE_MASK = (1u << 2) | (1u << 10) | (1u << 11);
         for (uint32_t b = 0; b < prm->max_depth; b++) {
             // shade(b): consumes the class queues, fills active[cur^1] + connect / shadow / light-ray queues
-            k_shade<<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur);
+            if (s->class_mask & 0x1Cu) { k_shade<false><<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
+            if (s->class_mask & 0x03u) { k_shade<true><<<c->g_shade_d, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
             k_reset<<<1, 1, 0, c->stream>>>(c->q, CLS_MASK | (1u << cur));
             cur ^= 1;
             trace(0, (int)b + 1);                                  // path rays of bounce b+1, shadow + light rays of bounce b
             k_resolve<<<c->g_resolve, ARN_BLOCK, 0, c->stream>>>(c->pb, c->q);
             k_reset<<<1, 1, 0, c->stream>>>(c->q, NEE_MASK);
-            launches += 5;
+            launches += 4;
         }
         k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
         launches += 1;

@@ -576,6 +576,54 @@ ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     return ret;
 }
 
+// ---------------------------------------------------------------- single diffuse lobe fast path
+// Matte materials build at most ONE lobe (Lambert or Oren–Nayar).  The diffuse shade kernel uses
+// these inlined forms of Bsdf::{evaluate, pdf, evaluate_sampled}; the arithmetic is the generic code's
+// (lobe_eval / lobe_pdf / lobe_sample cases LAMBERT_R / OREN_NAYAR), so results are bit-identical.
+ARN_DEV float3 diffuse_lobe_eval(const Lobe& x, float3 wo, float3 wi) {
+    if (x.kind == LOBE_LAMBERT_R) return x.a * ARN_INV_PI;
+    float sti = sin_theta(wi), sto = sin_theta(wo);
+    float max_cos = 0.f;
+    if (sti > 1e-4f || sto > 1e-4f) {
+        float spi = sin_phi(wi), spo = sin_phi(wo), cpi = cos_phi(wi), cpo = cos_phi(wo);
+        max_cos = fmaxf(max_cos, cpi * cpo + spi * spo);
+    }
+    float ci = fabsf(cos_theta(wi)), co = fabsf(cos_theta(wo));
+    float sin_a, tan_b;
+    if (ci > co) { sin_a = sto; tan_b = sti / ci; } else { sin_a = sti; tan_b = sto / co; }
+    return x.a * ARN_INV_PI * (x.c0 + x.c1 * max_cos * sin_a * tan_b);
+}
+ARN_DEV float diffuse_lobe_pdf(float3 wo, float3 wi) { return wo.z * wi.z > 0.f ? fabsf(cos_theta(wi)) * ARN_INV_PI : 0.f; }
+template <bool DIFFUSE> ARN_DEV float3 bsdf_eval_k(const Bsdf& b, float3 wow, float3 wiw) {
+    if (!DIFFUSE) return bsdf_eval(b, wow, wiw);
+    float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
+    bool is_reflection = dot(wow, b.ng) * dot(wiw, b.ng) > 0.f;
+    float3 ret = grey(0.f);
+    if (b.n > 0 && is_reflection) ret = ret + diffuse_lobe_eval(b.lobe[0], wo, wi);
+    return ret;
+}
+template <bool DIFFUSE> ARN_DEV float bsdf_pdf_k(const Bsdf& b, float3 wow, float3 wiw) {
+    if (!DIFFUSE) return bsdf_pdf(b, wow, wiw);
+    float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
+    if (wo.z == 0.f) return 0.f;
+    float pdfsum = 0.f;
+    if (b.n > 0) pdfsum += fmaxf(diffuse_lobe_pdf(wo, wi), 0.f);
+    return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
+}
+template <bool DIFFUSE> ARN_DEV Sampled bsdf_sample_k(const Bsdf& b, float3 wow, float2 u) {
+    if (!DIFFUSE) return bsdf_sample(b, wow, u);
+    Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
+    if (b.n == 0) return ret;
+    float3 wo = normalize(to_local(b, wow));
+    float3 wi = sample_cosw_hemisphere(u);
+    if (wo.z < 0.f) wi.z = -wi.z;
+    float pdf = diffuse_lobe_pdf(wo, wi);
+    if (pdf == 0.f) return ret;
+    ret.f = diffuse_lobe_eval(b.lobe[0], wo, wi); ret.pdf = pdf; ret.type = BXDF_REFLECTION | BXDF_DIFFUSE;
+    ret.wi = to_parent(b, wi);
+    return ret;
+}
+
 // ---------------------------------------------------------------- sphere area light
 ARN_DEV float3 sphere_emission(const DevSphere& sp) { return f3(sp.emission[0], sp.emission[1], sp.emission[2]); }
 ARN_DEV float sphere_area(const DevSphere& sp) { return sp.phimax * sp.radius * (sp.zmax - sp.zmin); }

@@ -26,6 +26,9 @@ namespace arn {
 #ifndef ARN_SHADE_MINB
 #define ARN_SHADE_MINB 2
 #endif
+#ifndef ARN_SHADE_MINB_DIFFUSE
+#define ARN_SHADE_MINB_DIFFUSE 3
+#endif
 
 struct PathBuf {                 // SoA over path slots, capacity W
     float4* ray_o;               // origin xyz
@@ -249,15 +252,18 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
 }
 
 // ---- K3 shade ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
+// DIFFUSE = true: classes 1, 0 (matte: one Lambert / Oren–Nayar lobe, inlined fast path, fewer registers);
+// DIFFUSE = false: classes 3, 2, 4 (glass, plastic, translucent: generic lobe code).
+template <bool DIFFUSE>
+__global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
     // One launch over the concatenation of the class queues, each padded to a multiple of 32 so that
     // every warp shades ONE material class; heavy classes (glass, plastic) first, so that the tail of
     // the launch is made of cheap Lambert work and near-empty classes cost no launch of their own.
-    const uint32_t ORDER = 0x01423u;                    // nibble k = class shaded k-th: 3, 2, 4, 1, 0
+    const uint32_t ORDER = DIFFUSE ? 0x55501u : 0x55423u;    // nibble k = class shaded k-th (5 = none): 1, 0 | 3, 2, 4
     uint32_t seg_start[ARN_NCLS + 1];
     seg_start[0] = 0;
 #pragma unroll
-    for (int k = 0; k < ARN_NCLS; k++) seg_start[k + 1] = seg_start[k] + ((q.counts[3 + ((ORDER >> (4 * k)) & 0xFu)] + 31u) & ~31u);
+    for (int k = 0; k < ARN_NCLS; k++) { uint32_t c = (ORDER >> (4 * k)) & 0xFu; seg_start[k + 1] = seg_start[k] + (c < ARN_NCLS ? ((q.counts[3 + c] + 31u) & ~31u) : 0u); }
     uint32_t* next = q.active[cur ^ 1];
     __shared__ uint32_t stage_rows[4][ARN_BLOCK / 32][64];
     WarpStage st_next, st_conn, st_sh, st_mis;
@@ -320,8 +326,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
                     float3 wi = normalize(ls.pfrom - ls.pto);
                     float3 A1 = grey(0.f);
                     if (!(ls.pdf == 0.f || is_black(ls.radiance))) {
-                        float3 f = bsdf_eval(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns));
-                        float spdf = bsdf_pdf(bsdf, s.wo, wi);
+                        float3 f = bsdf_eval_k<DIFFUSE>(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns));
+                        float spdf = bsdf_pdf_k<DIFFUSE>(bsdf, s.wo, wi);
                         if (spdf == 0.f) f = grey(0.f);
                         float weight = power_heuristic(ls.pdf, spdf);
                         A1 = ls.radiance * f * weight / ls.pdf;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
                     }
                     // BSDF sampling half
                     float3 A2 = grey(0.f);
-                    Sampled bs = bsdf_sample(bsdf, s.wo, uscatter);
+                    Sampled bs = bsdf_sample_k<DIFFUSE>(bsdf, s.wo, uscatter);
                     float3 f2v = bs.f * fabsf(dot(bs.wi, s.ns));
                     if (!is_black(f2v) && bs.pdf > 0.f) {
                         float weight = 1.f; bool skip = false;
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_SHADE_MINB) k_shade(DevScene sc
                 }
                 // sample the BSDF for the next direction (pt.rs:92-107)
                 float3 wo = -raydir;
-                Sampled bs = bsdf_sample(bsdf, wo, sm.next_2d());
+                Sampled bs = bsdf_sample_k<DIFFUSE>(bsdf, wo, sm.next_2d());
                 spec = (bs.type & BXDF_SPECULAR) != 0;
                 alive = !(is_black(bs.f) || bs.pdf == 0.f);
                 if (alive) {
