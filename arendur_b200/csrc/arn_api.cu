@@ -37,7 +37,7 @@ struct arn_ctx {
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> events;
     // launch geometry (blocks per kernel, persistent grid-stride)
-    int g_generate = 0, g_trace = 0, g_shade = 0, g_shade_d = 0, g_resolve = 0, g_accum = 0, g_closest = 0, g_any = 0;
+    int g_generate = 0, g_trace = 0, g_shade = 0, g_shade_d = 0, g_resolve = 0, g_accum = 0, g_accum_px = 0, g_closest = 0, g_any = 0;
     // scratch for batched queries through host buffers
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
@@ -155,6 +155,7 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_shade_d = grid_for(c, (const void*)k_shade<true>);
     c->g_resolve = grid_for(c, (const void*)k_resolve);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
+    c->g_accum_px = grid_for(c, (const void*)k_accumulate_px);
     c->g_closest = grid_for(c, (const void*)k_closest_batch<false>);
     c->g_any = grid_for(c, (const void*)k_any_batch);
     CUDA_TRY(nullptr, cudaMalloc(&c->d_ctr, 64));
@@ -464,6 +465,11 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             k_reset<<<1, 1, 0, c->stream>>>(c->q, NEE_MASK);
             launches += 4;
         }
+        if (film->filter_radius_x <= 4.f && film->filter_radius_y <= 4.f && film->filter_radius_x >= 0.5f && film->filter_radius_y >= 0.5f) {
+            unsigned long long npix = (base + n - 1) / wp.spp_count - base / wp.spp_count + 1;
+            int blocks = (int)std::min<unsigned long long>((unsigned long long)c->g_accum_px, (npix * 32 + ARN_BLOCK - 1) / ARN_BLOCK);
+            k_accumulate_px<<<std::max(blocks, 1), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, base, n);
+        } else
         k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
         launches += 1;
         if (radiance_dev) { k_store_radiance<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, radiance_dev, n); launches += 1; }

@@ -436,7 +436,9 @@ __global__ void k_reset(Queues q, uint32_t mask) { for (int i = 0; i < 16; i++) 
 __global__ void k_begin_wave(Queues q, uint32_t n) { for (int i = 0; i < 16; i++) q.counts[i] = 0; q.counts[0] = n; }
 
 // ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
-ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return cr_sinf(xpi) / xpi; }
+// film filter weights feed sums only (no discrete decision): libdevice f32 sinf (<= 2 ulp) instead of the
+// correctly-rounded f64 route; covered by the film-sum tolerance of tests/test_gpu_parity.py
+ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return sinf(xpi) / xpi; }
 ARN_DEV float lanczos1(float x) { return sinc1(x * (1.f / 3.f)) * sinc1(x); }        // tau = 3 (film.rs:47-51)
 
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
@@ -467,6 +469,66 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant_
     }
     for (int off = 16; off > 0; off >>= 1) invalid += __shfl_down_sync(0xffffffffu, invalid, off);
     if ((threadIdx.x & 31) == 0 && invalid) atomicAdd(&q.stats[3], invalid);
+}
+
+// ---- K6 accumulate, warp-per-pixel form (filter radius <= 4): a warp walks the samples of ONE
+// pixel of the wave (they are consecutive path slots), keeps the 9x9 window of affected film pixels in
+// registers (3 targets per lane), and issues one vector atomic per target per pixel instead of 64 per
+// sample.  Every (L*w, w) term is the scatter kernel's; only the order of the additions differs.
+__global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film,
+                                                              unsigned long long wave_base, uint32_t n) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long first_pl = wave_base / p.spp_count, last_pl = (wave_base + n - 1) / p.spp_count;
+    unsigned long long invalid = 0;
+    for (unsigned long long pl = first_pl + warp; pl <= last_pl; pl += nwarps) {
+        unsigned long long g0 = pl * p.spp_count, g1 = g0 + p.spp_count;
+        uint32_t s_begin = (uint32_t)((g0 > wave_base ? g0 : wave_base) - wave_base);
+        uint32_t s_end = (uint32_t)((g1 < wave_base + n ? g1 : wave_base + n) - wave_base);
+        uint32_t pix = pb.pix[s_begin];
+        int px = (int)(pix & 0xffffu), py = (int)(pix >> 16);
+        float4 acc[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t s = s_begin; s < s_end; s++) {
+            float4 l4 = pb.L[s];
+            float3 L = f3(l4.x, l4.y, l4.z);
+            bool valid = !(isnan(L.x) || isnan(L.y) || isnan(L.z)) && !(isinf(L.x) || isinf(L.y) || isinf(L.z)) && L.x >= 0.f && L.y >= 0.f && L.z >= 0.f;
+            if (!valid) { L = grey(0.f); if (lane == 0) invalid++; }     // pt.rs:152-156
+            float2 pos = pb.pfilm[s];
+            float cx = pos.x - p.fr_x + 0.5f, cy = pos.y - p.fr_y + 0.5f;
+            float fx = pos.x + p.fr_x - 0.5f, fy = pos.y + p.fr_y - 0.5f;
+            int x0 = (int)cx, y0 = (int)cy, x1 = (int)fx + 1, y1 = (int)fy + 1;   // truncation toward zero
+            if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
+            if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
+            float wv = 0.f;
+            if (lane < 9) wv = lanczos1(((float)(px - 4 + (int)lane) + 0.5f) - pos.x);
+            else if (lane < 18) wv = lanczos1(((float)(py - 4 + (int)lane - 9) + 0.5f) - pos.y);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                int t = (int)lane + 32 * j;
+                int tx = t % 9, ty = t / 9;
+                float wx = __shfl_sync(0xffffffffu, wv, tx);
+                float wy = __shfl_sync(0xffffffffu, wv, 9 + (ty < 9 ? ty : 8));
+                int X = px - 4 + tx, Y = py - 4 + ty;
+                if (t < 81 && X >= x0 && X < x1 && Y >= y0 && Y < y1) {
+                    float w = wx * wy;
+                    float3 c = L * w;
+                    acc[j].x += c.x; acc[j].y += c.y; acc[j].z += c.z; acc[j].w += w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            int t = (int)lane + 32 * j;
+            int X = px - 4 + t % 9, Y = py - 4 + t / 9;
+            if (t < 81 && X >= p.crop_x0 && X < p.crop_x0 + p.crop_w && Y >= p.crop_y0 && Y < p.crop_y0 + p.crop_h
+                && (acc[j].x != 0.f || acc[j].y != 0.f || acc[j].z != 0.f || acc[j].w != 0.f))
+                atomicAdd(&film[(size_t)(Y - p.crop_y0) * (size_t)p.crop_w + (size_t)(X - p.crop_x0)], acc[j]);
+        }
+    }
+    if (lane == 0 && invalid) atomicAdd(&q.stats[3], invalid);
 }
 
 // diagnostic: per-sample radiance, indexed ((y*crop_w + x)*spp_count + (s - spp_begin)) (parity tests)
