@@ -370,10 +370,11 @@ int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t
     if (grid < 1) grid = 1;
     k_closest_batch<true><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, c->d_ctr);
     CUDA_TRY(c, cudaGetLastError());
-    unsigned long long h[3];
-    CUDA_TRY(c, cudaMemcpyAsync(h, c->d_ctr, 24, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long h[4];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->d_ctr, 32, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     counters_out[0] = h[0]; counters_out[1] = h[1]; counters_out[2] = h[2];
+    if (std::getenv("ARN_PROBE")) std::fprintf(stderr, "[arn probe] nodes %llu, sum of per-warp max %llu -> lane utilisation %.3f\n", h[0], h[3], (double)h[0] / (32.0 * (double)h[3]));
     return ARN_OK;
 }
 

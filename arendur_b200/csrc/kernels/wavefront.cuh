@@ -548,9 +548,15 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevS
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        uint32_t before = ctr[0];
         HitRec h; traverse<false, COUNT>(sc, r, h, ctr);
         arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? h.t : ARN_INF;
         hits[i] = o;
+        if (COUNT) {   // lane-utilisation probe: sum over warps of the longest ray's node count
+            uint32_t steps = ctr[0] - before, mx = steps;
+            for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(__activemask(), mx, off));
+            if ((threadIdx.x & 31) == 0) atomicAdd(&ctr_out[3], (unsigned long long)mx);
+        }
     }
     if (COUNT) {
         unsigned long long a = ctr[0], b = ctr[1], c = ctr[2];

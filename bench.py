@@ -12,7 +12,7 @@ tile-partitioned (16x16 tiles, t % N) and every step renders 64*N spp, i.e. per-
 
   value  = Mrays/s, rays = every BVH traversal (path + shadow + MIS), film resident in HBM
   e2e    = same metric through the host-buffer C-ABI: scene upload (H2D) + arn_render_pt + film D2H
-  roofline: k_extend (closest hit), algorithmic bytes = 32*Nn + 36*Nt + 152*Ns + 36 per ray
+  roofline: k_trace (all BVH traversals), algorithmic bytes = 32*Nn + 36*Nt + 152*Ns + 36 per ray
   cpu_baseline / --impl reference: the oracle (CPU restatement of arendur; the Rust original
   cannot be built here) on the host cores, bounded sample of the same workload.
 """
@@ -208,7 +208,7 @@ def main():
     # ---- timed: device-resident film
     clocks = ClockSampler(local)
     clocks.start()
-    step_ms, ext_ms, ext_rays, rays, samples, launches = [], 0.0, 0, 0, 0, 0
+    step_ms, ext_ms, ext_rays, rays, samples, launches, inc_ms, inc_rays = [], 0.0, 0, 0, 0, 0, 0.0, 0
     with torch.cuda.stream(ext):
         for k in range(args.steps):
             flush.fill_(k & 0xFF)                      # L2 flush between timed iterations (untimed)
@@ -219,7 +219,8 @@ def main():
             e1.record(ext)
             barrier()
             step_ms.append(e0.elapsed_time(e1))
-            ext_ms += st.extend_ms; ext_rays += st.extend_rays
+            ext_ms += st.extend_ms; ext_rays += st.extend_rays + st.shadow_rays + st.mis_rays
+            inc_ms += st.extend_bounce_ms; inc_rays += st.extend_bounce_rays
             rays += st.extend_rays + st.shadow_rays + st.mis_rays
             samples += st.camera_rays
             launches += st.kernel_launches
@@ -234,7 +235,8 @@ def main():
         stc = scene.render_pt_dev(cam, film, smp, api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=0, spp_end=min(8, spp_step)), scratch.data_ptr())
     ctx.set_option(L.ARN_OPT_COUNT_TRAVERSAL, 0)
     torch.cuda.synchronize()
-    bytes_per_ray = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_spheres) / max(1, stc.extend_rays) + 28 + 8
+    rays_counted = stc.extend_rays + stc.shadow_rays + stc.mis_rays
+    bytes_per_ray = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_spheres) / max(1, rays_counted) + 28 + 8
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region
     scene_bytes = int(desc.n_nodes * 32 + desc.n_prims * 48 + desc.n_spheres * 176 + desc.n_triangles * 16 + desc.n_vertices * 32
@@ -269,13 +271,13 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        n_ext_launch = args.steps * prm0.max_depth * max(1, (RES * RES * spp_step // world + (1 << 20) - 1) // (1 << 20))
+        n_ext_launch = args.steps * (prm0.max_depth + 1) * max(1, (RES * RES * spp_step // world + (1 << 20) - 1) // (1 << 20))
         achieved = bytes_per_ray * ext_rays / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("k_trace_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
@@ -289,9 +291,10 @@ def main():
             "e2e": {"value": e2e_rays_all / (e2e_ms_max * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_bytes,
                     "d2h_bytes_per_step": RES * RES * 16, "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps},
             "gpu_launches": int(launches_all),
-            "roofline": {"kernel": "k_extend (closest hit)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"kernel": "k_trace (closest hit of path rays + any hit of shadow rays + closest hit of light rays, one launch)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": ext_rays / max(1, n_ext_launch),
-                         "extend_mrays_s": ext_rays / (ext_ms * 1e-3) / 1e6 if ext_ms > 0 else 0.0, "extend_share_of_step": ext_ms / total_ms,
+                         "trace_mrays_s": ext_rays / (ext_ms * 1e-3) / 1e6 if ext_ms > 0 else 0.0, "trace_share_of_step": ext_ms / total_ms,
+                         "incoherent_mrays_s": inc_rays / (inc_ms * 1e-3) / 1e6 if inc_ms > 0 else 0.0,
                          "note": "Cornell scene (0.2 MB) is cache resident: the HBM roofline is the contract's denominator, not the binding limit (DESIGN.md)"},
             "clocks": clk,
         }

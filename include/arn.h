@@ -187,11 +187,11 @@ typedef struct arn_stats {
     uint64_t invalid_samples;    /* radiance replaced by black (pt.rs:152-156)              */
     uint64_t kernel_launches;    /* kernels of this library launched by the call            */
     double   gpu_ms;             /* device time of the call, CUDA events                    */
-    double   extend_ms;          /* device time spent in closest-hit kernels (path rays)    */
-    double   extend_bounce_ms;   /* ... of which for bounces >= 1 (incoherent)              */
-    uint64_t extend_bounce_rays; /* path rays of bounces >= 1                               */
+    double   extend_ms;          /* device time of the k_trace launches (path + shadow + light rays)   */
+    double   extend_bounce_ms;   /* ... without each wave's first launch (camera rays): incoherent rays */
+    uint64_t extend_bounce_rays; /* rays traced by those launches (path rays of bounces >= 1, shadow, light) */
     /* filled only when ARN_OPT_COUNT_TRAVERSAL is on (instrumented kernels, not for timing):
-     * BVH nodes / triangles / spheres tested by the path-ray (extend) traversals — the Nn, Nt
+     * BVH nodes / triangles / spheres tested by ALL traversals of k_trace — the Nn, Nt
      * of the algorithmic-bytes figure, SURVEY.md §8(d) */
     uint64_t extend_nodes, extend_tris, extend_spheres;
 } arn_stats;
