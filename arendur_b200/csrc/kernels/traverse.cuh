@@ -72,6 +72,9 @@ ARN_DEV void trav_init(TravRay& r, float3 o, float3 d, float tmax) {
 }
 
 // Slab test without the tmax comparison: returns false on a definite miss, else t0.
+// Branch-free form of BBox3f::intersect_ray_cached (bbox.rs:549-580): the reference's two early
+// `return None` become predicates (the updates they skip cannot change a `false` result), the
+// comparisons and selects are the reference's own (NaNs propagate identically; no fmin/fmax).
 ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_out) {
     const float k = 1.f + 2.f * gamma_n(3.f);
     const bool nx = r.inv.x < 0.f, ny = r.inv.y < 0.f, nz = r.inv.z < 0.f;
@@ -80,18 +83,17 @@ ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_
     float t1 = ((nx ? bminx : bmaxx) - r.co.x) * r.inv.x;
     float ty0 = ((ny ? bmaxy : bminy) - r.co.y) * r.inv.y;
     float ty1 = ((ny ? bminy : bmaxy) - r.co.y) * r.inv.y;
-    t1 *= k; ty1 *= k;
-    if (t0 > ty1 || ty0 > t1) return false;
-    if (ty0 > t0) t0 = ty0;
-    if (ty1 < t1) t1 = ty1;
     float tz0 = ((nz ? bmaxz : bminz) - r.co.z) * r.inv.z;
     float tz1 = ((nz ? bminz : bmaxz) - r.co.z) * r.inv.z;
-    tz1 *= k;
-    if (t0 > tz1 || tz0 > t1) return false;
-    if (tz0 > t0) t0 = tz0;
-    if (tz1 < t1) t1 = tz1;
+    t1 *= k; ty1 *= k; tz1 *= k;
+    const bool miss_xy = (t0 > ty1) | (ty0 > t1);
+    t0 = ty0 > t0 ? ty0 : t0;
+    t1 = ty1 < t1 ? ty1 : t1;
+    const bool miss_z = (t0 > tz1) | (tz0 > t1);
+    t0 = tz0 > t0 ? tz0 : t0;
+    t1 = tz1 < t1 ? tz1 : t1;
     t0_out = t0;
-    return t1 > 0.f;           // caller adds `t0 < tmax` (NaN t0 fails it, as in the reference)
+    return !miss_xy & !miss_z & (t1 > 0.f);     // caller adds `t0 < tmax` (NaN t0 fails it, as in the reference)
 }
 
 ARN_DEV float3 perm_point(float3 p, int kz) {
