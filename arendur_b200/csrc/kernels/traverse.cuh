@@ -177,7 +177,7 @@ struct HitRec {               // what shading needs from the final hit
 // element.intersect_ray(&mut iray); if ray.tmax > iray.tmax { *ray = iray }` (bvh.rs:108-113)
 // through TransformedComposable (transformed.rs:73-83): on an accepted hit the traversal ray
 // becomes the round-tripped one.
-static __device__ __noinline__ void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& h) {
+ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& h) {
     const DevSphere& sp = sc.spheres[sc.prims[comp] & ~ARN_PRIM_SPHERE];
     float3 lo = r.o, ld = r.d;
     if (sp.has_transform) { lo = xform_point(sp.parent_local, r.o); ld = xform_vector(sp.parent_local, r.d); }
