@@ -42,6 +42,8 @@ struct arn_ctx {
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
     bool opt_count = false;
+    int opt_width = 0;           // ARN_OPT_BVH_WIDTH: 0 auto, 2 binary, 4 wide
+    int g_trace_w = 0, g_closest_w = 0, g_any_w = 0;
     size_t opt_wave = 0;
 };
 
@@ -150,14 +152,17 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->g_generate = grid_for(c, (const void*)k_generate);
-    c->g_trace = grid_for(c, (const void*)k_trace<false>);
+    c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
+    c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
     c->g_shade = grid_for(c, (const void*)k_shade<false>);
     c->g_shade_d = grid_for(c, (const void*)k_shade<true>);
     c->g_resolve = grid_for(c, (const void*)k_resolve);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
     c->g_accum_px = grid_for(c, (const void*)k_accumulate_px);
-    c->g_closest = grid_for(c, (const void*)k_closest_batch<false>);
-    c->g_any = grid_for(c, (const void*)k_any_batch);
+    c->g_closest = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_BINARY>);
+    c->g_closest_w = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_WIDE>);
+    c->g_any = grid_for(c, (const void*)k_any_batch<ARN_TRAV_BINARY>);
+    c->g_any_w = grid_for(c, (const void*)k_any_batch<ARN_TRAV_WIDE>);
     CUDA_TRY(nullptr, cudaMalloc(&c->d_ctr, 64));
     *out = c;
     return ARN_OK;
@@ -182,6 +187,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     if (!c) return ARN_E_INVALID;
     switch (option) {
     case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
+    case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2 or 4"); c->opt_width = (int)value; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -196,6 +202,44 @@ void arn_scene_destroy(arn_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);
     for (void* p : s->allocs) cudaFree(p);
     delete s;
+}
+
+// Order-preserving 4-wide collapse of the pre-order binary nodes: wide node of interior node n =
+// records (n.first's children | n.first itself if it is a leaf, n.second's likewise); a record keeps
+// the child's bounds and its reference words (traverse.cuh).  Wide nodes are emitted in pre-order.
+static void collapse_wide(const arn_node* nodes, std::vector<arn_node>& wide, arn_node& root) {
+    auto is_leaf = [&](uint32_t i) { return (nodes[i].len_axis >> 2) != 0; };
+    auto axes_of = [&](uint32_t i) {
+        uint32_t a = i + 1, b = i + nodes[i].offset;
+        return (nodes[i].len_axis & 3u) | ((is_leaf(a) ? 0u : (nodes[a].len_axis & 3u)) << 2) | ((is_leaf(b) ? 0u : (nodes[b].len_axis & 3u)) << 4);
+    };
+    struct Todo { uint32_t node, rec; };              // binary interior node -> the record that refers to it
+    std::vector<Todo> todo;
+    auto make_rec = [&](uint32_t i, arn_node& r, size_t rec_index) {
+        r = nodes[i];
+        if (is_leaf(i)) { r.offset = nodes[i].offset; r.len_axis = ((nodes[i].len_axis >> 2) << 8) | ARN_W_LEAF; }
+        else { r.offset = 0; r.len_axis = (axes_of(i) << 2) | ARN_W_INNER; if (rec_index != (size_t)-1) todo.push_back({i, (uint32_t)rec_index}); }
+    };
+    make_rec(0, root, (size_t)-1);
+    if (is_leaf(0)) return;
+    arn_node empty; std::memset(&empty, 0, sizeof empty);
+    // explicit stack, children pushed so that wide nodes come out in pre-order
+    std::vector<Todo> st; st.push_back({0u, 0xffffffffu});
+    while (!st.empty()) {
+        Todo t = st.back(); st.pop_back();
+        uint32_t w = (uint32_t)(wide.size() / 4);
+        if (t.rec != 0xffffffffu) wide[t.rec].offset = w;
+        wide.resize(wide.size() + 4, empty);
+        uint32_t pair[2] = {t.node + 1, t.node + nodes[t.node].offset};
+        todo.clear();
+        for (int g = 0; g < 2; g++) {
+            uint32_t ch = pair[g];
+            size_t base = (size_t)w * 4 + 2 * g;
+            if (is_leaf(ch)) make_rec(ch, wide[base], base);
+            else { make_rec(ch + 1, wide[base], base); make_rec(ch + nodes[ch].offset, wide[base + 1], base + 1); }
+        }
+        for (size_t k = todo.size(); k-- > 0;) st.push_back(todo[k]);
+    }
 }
 
 int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
@@ -248,6 +292,15 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     const arn_node* dn = nullptr;
     if ((rc = dev_upload(s, d->nodes, d->n_nodes, &dn)) != ARN_OK) return fail(rc);
     s->dev.nodes = (const float4*)dn;
+    {   // 4-wide collapse (kernels/traverse.cuh, traverse4)
+        std::vector<arn_node> wide;
+        arn_node root;
+        collapse_wide(d->nodes, wide, root);
+        const arn_node* dw = nullptr;
+        if ((rc = dev_upload(s, wide.data(), wide.size(), &dw)) != ARN_OK) return fail(rc);
+        s->dev.wide = (const float4*)dw;
+        std::memcpy(&s->dev.root0, &root, 16); std::memcpy(&s->dev.root1, (const char*)&root + 16, 16);
+    }
     // ordered 48-byte primitive slots
     std::vector<float4> slots((size_t)d->n_prims * 3);
     for (uint32_t k = 0; k < d->n_prims; k++) {
@@ -289,15 +342,26 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     return ARN_OK;
 }
 
+// Which tree the product kernels walk.  Both give the same bits (traverse.cuh); the 4-wide walk halves
+// the chain of dependent node fetches and wins once the tree no longer sits in L1 (C4: +10 %), the
+// binary walk issues fewer instructions per node and wins on cache-resident trees (Cornell: +15 %).
+#define ARN_WIDE_MIN_NODES (1u << 16)
+static bool use_wide(const arn_scene* s) {
+    int w = s->ctx->opt_width;
+    return w == 4 || (w == 0 && s->dev.n_nodes >= ARN_WIDE_MIN_NODES);
+}
+
 // ---------------------------------------------------------------- batched queries
 int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void* hits_dev, arn_stats* stats) {
     if (!s || (n && (!rays_dev || !hits_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_dev: NULL argument");
     arn_ctx* c = s->ctx; cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
-    int grid = (int)std::min<size_t>((size_t)c->g_closest, (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    const bool wide = use_wide(s);
+    int grid = (int)std::min<size_t>((size_t)(wide ? c->g_closest_w : c->g_closest), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    k_closest_batch<false><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    if (wide) k_closest_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    else k_closest_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     CUDA_TRY(c, cudaGetLastError());
     if (stats) {
         cudaEventRecord(e1, c->stream);
@@ -312,10 +376,12 @@ int arn_intersect_any_dev(arn_scene* s, const void* rays_dev, size_t n, void* ou
     if (!s || (n && (!rays_dev || !out_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any_dev: NULL argument");
     arn_ctx* c = s->ctx; cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
-    int grid = (int)std::min<size_t>((size_t)c->g_any, (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    const bool wide = use_wide(s);
+    int grid = (int)std::min<size_t>((size_t)(wide ? c->g_any_w : c->g_any), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    k_any_batch<<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    if (wide) k_any_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    else k_any_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     CUDA_TRY(c, cudaGetLastError());
     if (stats) {
         cudaEventRecord(e1, c->stream);
@@ -368,7 +434,7 @@ int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t
     CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 64, c->stream));
     int grid = (int)std::min<size_t>((size_t)c->g_closest, (n + ARN_BLOCK - 1) / ARN_BLOCK);
     if (grid < 1) grid = 1;
-    k_closest_batch<true><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, c->d_ctr);
+    k_closest_batch<ARN_TRAV_COUNTED><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, c->d_ctr);
     CUDA_TRY(c, cudaGetLastError());
     unsigned long long h[4];
     CUDA_TRY(c, cudaMemcpyAsync(h, c->d_ctr, 32, cudaMemcpyDeviceToHost, c->stream));
@@ -446,10 +512,12 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, base, n);
         launches += 2;
         int cur = 0;
+        const bool wide = use_wide(s);
         auto trace = [&](int first, int bounce) {
             if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, bounce}); }
-            if (c->opt_count) k_trace<true><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
-            else k_trace<false><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
+            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
+            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
+            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
         };
         trace(1, 0);                                               // camera rays

@@ -42,9 +42,19 @@ struct DevScene {
     const float* __restrict__ light_cdf;
     float light_integral;
     uint32_t n_lights, n_nodes, n_prims, n_spheres;
+    // 4-wide collapse of `nodes` (built at upload, see traverse4): 4 records of 32 B per wide node
+    const float4* __restrict__ wide;
+    float4 root0, root1;                     // record of the root (bounds of nodes[0] + its reference words)
 };
 
 #define ARN_STACK 64           /* upload rejects trees deeper than this */
+#define ARN_STACK4 96          /* wide traversal: <= 3 pushes per wide level, ARN_STACK/2 wide levels */
+// reference words of a wide record: w0 = q1.z, w1 = q1.w
+//   w1 & 3 : 0 empty slot, 1 interior (w0 = wide node index, (w1 >> 2) & 63 = split axes of that node:
+//            its own | first child's << 2 | second child's << 4), 2 leaf (w0 = first slot, w1 >> 8 = count)
+#define ARN_W_EMPTY 0u
+#define ARN_W_INNER 1u
+#define ARN_W_LEAF 2u
 
 // Ray state used by traversal: the slab cache keeps the ORIGINAL origin / 1/dir
 // (bvh.rs:101,112 refreshes only tmax), the shear cache follows the CURRENT ray
@@ -266,6 +276,93 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
         }
         if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
     }
+}
+
+// ---- 4-wide traversal ------------------------------------------------------------------------
+// The wide tree is the binary tree with every second level removed: wide node = (children of the
+// first child, children of the second child), a leaf child occupying one slot of its pair.  The four
+// records are visited in the order the binary depth-first walk would reach them (pair order from the
+// node's split axis, order inside a pair from the child's split axis — signs of the ray direction, not
+// distances), entry distances travel on the stack and are re-checked against the shrinking tmax at pop
+// time.  Result: the same leaves are visited in the same order as in BVH::intersect_ray
+// (bvh.rs:97-128), so hits, ids and ties are bit-identical to the binary walk:
+//   * a grandchild's slab interval is contained in its parent's (same monotone f32 operations on
+//     nested bounds), so skipping the parent's test never admits a leaf the binary walk would reject
+//     — the leaf's own test, made with the same tmax as in the binary walk, decides;
+//   * only the `t0 < tmax` part of a slab test depends on when it is evaluated, and that part is
+//     re-evaluated when the record is popped.
+// tests/test_gpu_parity.py::test_wide_equals_binary checks it ray by ray against the binary kernel.
+ARN_DEV bool trav_pop4(const TravRay& r, const uint4* stack, int& sp, uint32_t& w0, uint32_t& w1) {
+    for (;;) {
+        if (sp == 0) return false;
+        uint4 e = stack[--sp];
+        if (__uint_as_float(e.z) < r.tmax) { w0 = e.x; w1 = e.y; return true; }
+    }
+}
+template <bool ANY>
+ARN_DEV void traverse4(const DevScene& sc, TravRay& r, HitRec& h) {
+    h.prim = -1; h.t = ARN_INF; h.a = h.b = h.c = 0.f;
+    uint4 stack[ARN_STACK4];
+    int sp = 0;
+    float t0;
+    if (!slab(sc.root0, sc.root1, r, t0) || !(t0 < r.tmax)) return;
+    uint32_t w0 = __float_as_uint(sc.root1.z), w1 = __float_as_uint(sc.root1.w);
+    const uint32_t negbits = (r.inv.x < 0.f ? 1u : 0u) | (r.inv.y < 0.f ? 2u : 0u) | (r.inv.z < 0.f ? 4u : 0u);
+    for (;;) {
+        bool alive = true;
+        while ((w1 & 3u) == ARN_W_INNER) {
+            const uint32_t ax = w1 >> 2;
+            const uint32_t sN = (negbits >> (ax & 3u)) & 1u, sA = (negbits >> ((ax >> 2) & 3u)) & 1u, sB = (negbits >> ((ax >> 4) & 3u)) & 1u;
+            const uint32_t g1 = sN << 1, g2 = 2u - g1;                 // pair visited first / second
+            const uint32_t s1 = sN ? sB : sA, s2 = sN ? sA : sB;
+            const float4* __restrict__ rec = sc.wide + (size_t)w0 * 8u;
+            const uint32_t o0 = (g1 + s1) * 2u, o1 = (g1 + (s1 ^ 1u)) * 2u, o2 = (g2 + s2) * 2u, o3 = (g2 + (s2 ^ 1u)) * 2u;
+            const float4 a0 = __ldg(rec + o0), a1 = __ldg(rec + o0 + 1);
+            const float4 b0 = __ldg(rec + o1), b1 = __ldg(rec + o1 + 1);
+            const float4 c0 = __ldg(rec + o2), c1 = __ldg(rec + o2 + 1);
+            const float4 d0 = __ldg(rec + o3), d1 = __ldg(rec + o3 + 1);
+            float ta, tb, tc, td;
+            const bool ha = slab(a0, a1, r, ta) && ta < r.tmax && (__float_as_uint(a1.w) & 3u);
+            const bool hb = slab(b0, b1, r, tb) && tb < r.tmax && (__float_as_uint(b1.w) & 3u);
+            const bool hc = slab(c0, c1, r, tc) && tc < r.tmax && (__float_as_uint(c1.w) & 3u);
+            const bool hd = slab(d0, d1, r, td) && td < r.tmax && (__float_as_uint(d1.w) & 3u);
+            // walk the visiting order backwards: every hit record but the first goes on the stack
+            bool have = hd;
+            uint32_t n0 = __float_as_uint(d1.z), n1 = __float_as_uint(d1.w); float nt = td;
+            if (hc) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(c1.z); n1 = __float_as_uint(c1.w); nt = tc; have = true; }
+            if (hb) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(b1.z); n1 = __float_as_uint(b1.w); nt = tb; have = true; }
+            if (ha) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(a1.z); n1 = __float_as_uint(a1.w); nt = ta; have = true; }
+            if (have) { w0 = n0; w1 = n1; }
+            else if (!trav_pop4(r, stack, sp, w0, w1)) { alive = false; break; }
+        }
+        if (!alive) return;
+        const uint32_t end = w0 + (w1 >> 8);
+        for (uint32_t k = w0; k < end; k++) {
+            float4 v0 = __ldg(&sc.tris[3 * k]);
+            uint32_t comp = __float_as_uint(v0.w);
+            if (comp & ARN_PRIM_SPHERE) sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h);
+            else {
+                float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
+                float t, b0, b1, b2;
+                if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
+                    r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
+                }
+            }
+            if (ANY && h.prim >= 0) return;
+        }
+        if (!trav_pop4(r, stack, sp, w0, w1)) return;
+    }
+}
+
+// What the kernels call.  The counted mode always walks the binary nodes: its counters report the
+// reference algorithm's node / primitive tests.
+#define ARN_TRAV_BINARY 0
+#define ARN_TRAV_COUNTED 1
+#define ARN_TRAV_WIDE 2
+template <bool ANY, int MODE>
+ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
+    if (MODE == ARN_TRAV_WIDE) traverse4<ANY>(sc, r, h);
+    else traverse<ANY, MODE == ARN_TRAV_COUNTED>(sc, r, h, ctr);
 }
 
 }  // namespace arn

@@ -175,8 +175,9 @@ ARN_DEV int shading_class(const arn_material& m) {
 //   path ray   : closest hit -> hit record; hits sorted into the per-material-class queues
 //   shadow ray : any hit (LightSample::occluded, lighting/mod.rs:125-133)      -> occluded[pid]
 //   light ray  : closest hit, `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155) -> mis_ok[pid]
-template <bool COUNT>
+template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc, PathBuf pb, Queues q, int cur, int first) {
+    constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t n_ext = q.counts[cur], n_sh = q.counts[10], n_mis = q.counts[11];
     const uint32_t s1 = (n_ext + 31u) & ~31u, s2 = s1 + ((n_sh + 31u) & ~31u), s3 = s2 + ((n_mis + 31u) & ~31u);
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
                 float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
                 HitRec h;
-                traverse<false, COUNT>(sc, r, h, ctr);
+                trace_ray<false, MODE>(sc, r, h, ctr);
                 pb.hit_prim[pid] = h.prim;
                 pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
                 if (h.prim >= 0) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
                 uint32_t pid = q.shadow[j];
                 float4 o = pb.sh_o[pid], d = pb.sh_d[pid];
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
-                HitRec h; traverse<true, COUNT>(sc, r, h, ctr);
+                HitRec h; trace_ray<true, MODE>(sc, r, h, ctr);
                 pb.occluded[pid] = h.prim >= 0 ? 1u : 0u;
             }
         } else {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
                 float4 o = pb.mis_o[pid], d = pb.mis_d[pid];
                 float3 wi = f3(d.x, d.y, d.z);
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
-                HitRec h; traverse<false, COUNT>(sc, r, h, ctr);
+                HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
                 uint32_t lcomp = __float_as_uint(pb.a2[pid].w);
                 uint32_t ok = 0;
                 if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
@@ -541,15 +542,16 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_const
 }
 
 // ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------
-template <bool COUNT>
+template <int MODE>
 __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
                                                              unsigned long long* ctr_out) {
+    constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
         uint32_t before = ctr[0];
-        HitRec h; traverse<false, COUNT>(sc, r, h, ctr);
+        HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
         arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? h.t : ARN_INF;
         hits[i] = o;
         if (COUNT) {   // lane-utilisation probe: sum over warps of the longest ray's node count
@@ -564,11 +566,12 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevS
         if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr_out[0], a); atomicAdd(&ctr_out[1], b); atomicAdd(&ctr_out[2], c); }
     }
 }
+template <int MODE>
 __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
-        HitRec h; traverse<true, false>(sc, r, h, nullptr);
+        HitRec h; trace_ray<true, MODE>(sc, r, h, nullptr);
         out[i] = h.prim >= 0 ? 1 : 0;
     }
 }

@@ -177,3 +177,47 @@ def test_render_tile_partition_sums_to_full_frame(ctx, cornell_small):
     rf, _, _ = osc.render_pt(cam, film, smp, p1)
     assert np.allclose(parts[1][..., 3], rf[..., 3], rtol=2e-5, atol=1e-6)
     sc.close(); osc.close()
+
+
+def test_wide_equals_binary(ctx, cornell_small):
+    """The product kernels walk the 4-wide collapse of the BVH; the counted kernels walk the reference's binary
+    nodes (bvh.rs:97-128).  Same leaves in the same order => identical hit records, bit for bit, on rays
+    that exercise ties, spheres and deep subtrees; and an identical film through the whole bounce loop."""
+    import torch
+    hs, cam, film, smp, prm = cornell_small
+    sc = ctx.upload(hs.desc())
+    rng = np.random.default_rng(11)
+    n = 200_000
+    rays = np.zeros(n, api.RAY_DTYPE)
+    rays["o"] = rng.uniform([-1.8, -1.3, 2.2], [1.8, 2.2, 5.8], (n, 3)).astype(np.float32)
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v[: n // 8, rng.integers(0, 3)] = 0.0                       # axis-parallel components: inv = +-inf
+    rays["d"] = v.astype(np.float32)
+    rays["tmax"] = np.where(rng.random(n) < 0.3, rng.uniform(0.1, 4.0, n), np.inf).astype(np.float32)
+    dr = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    h_wide = torch.empty(n * api.HIT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    h_bin = torch.empty_like(h_wide)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, 4)                      # auto would pick the binary walk for a tree this small
+    sc.intersect_closest_dev(dr.data_ptr(), n, h_wide.data_ptr())
+    ctr = sc.intersect_closest_counted_dev(dr.data_ptr(), n, h_bin.data_ptr())
+    ctx.synchronize()
+    assert ctr[0] > n
+    assert torch.equal(h_wide, h_bin)
+    assert (h_bin.cpu().numpy().view(api.HIT_DTYPE)["prim_id"] >= 0).sum() > n // 4
+    # whole bounce loop: the counted render walks the binary nodes
+    f_wide, rad_wide, st = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_COUNT_TRAVERSAL, 1)
+    f_bin, rad_bin, stc = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_COUNT_TRAVERSAL, 0)
+    assert stc.extend_nodes > 0 and st.extend_nodes == 0
+    assert np.array_equal(rad_wide, rad_bin)                    # every camera sample, bit for bit
+    assert np.allclose(f_wide, f_bin, rtol=1e-5, atol=1e-6)     # film: float atomics, order differs run to run
+    # forced binary (uncounted) == forced wide, any-hit included
+    a4 = sc.intersect_any(rays)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, 2)
+    a2 = sc.intersect_any(rays)
+    h2 = sc.intersect_closest(rays)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
+    assert np.array_equal(a2, a4)
+    assert h2.tobytes() == h_bin.cpu().numpy().tobytes()
+    sc.close()
