@@ -14,6 +14,8 @@ ARN_OK, ARN_E_INVALID, ARN_E_CUDA, ARN_E_OOM, ARN_E_IO, ARN_E_UNSUPPORTED = 0, -
 ARN_PRIM_SPHERE = 0x80000000
 ARN_BVH_SAH, ARN_BVH_MIDDLECOUNT, ARN_BVH_MIDPOINT = 0, 1, 2
 ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY, ARN_OPT_BVH_WIDTH = 1, 2, 3
+ARN_LIGHT_POINT, ARN_LIGHT_SPOT, ARN_LIGHT_DISTANT = 0, 1, 2
+ARN_LIGHT_ANALYTIC = 0x80000000
 ARN_MAT_MATTE, ARN_MAT_PLASTIC, ARN_MAT_GLASS, ARN_MAT_TRANSLUCENT = 0, 1, 2, 3
 
 c_float_p = C.POINTER(C.c_float)
@@ -40,6 +42,12 @@ class Sphere(C.Structure):
                 ("local_parent", C.c_float * 16), ("parent_local", C.c_float * 16)]
 
 
+class AnalyticLight(C.Structure):
+    """arn_analytic_light: PointLight / SpotLight / DistantLight (include/arn.h)."""
+    _fields_ = [("type", C.c_uint32), ("pos", C.c_float * 3), ("intensity", C.c_float * 3), ("cost", C.c_float), ("cosf", C.c_float),
+                ("parent_local", C.c_float * 16), ("dir", C.c_float * 3), ("world_radius", C.c_float)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("n_vertices", C.c_uint32), ("positions", c_float_p), ("normals", c_float_p), ("uvs", c_float_p),
                 ("n_triangles", C.c_uint32), ("indices", c_u32_p), ("tri_mesh", c_u32_p),
@@ -49,7 +57,8 @@ class SceneDesc(C.Structure):
                 ("n_prims", C.c_uint32), ("prims", c_u32_p),
                 ("n_nodes", C.c_uint32), ("nodes", C.POINTER(Node)), ("order", c_u32_p),
                 ("n_lights", C.c_uint32), ("light_prims", c_u32_p), ("light_func", c_float_p), ("light_cdf", c_float_p),
-                ("light_func_integral", C.c_float)]
+                ("light_func_integral", C.c_float),
+                ("n_analytic_lights", C.c_uint32), ("analytic_lights", C.POINTER(AnalyticLight))]
 
 
 class Camera(C.Structure):
@@ -97,7 +106,8 @@ ARN_H_SYMBOLS = [
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
-    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_load_obj", "arn_hscene_load_json",
+    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_spot_light_make", "arn_point_light_make",
+    "arn_distant_light_make", "arn_hscene_load_obj", "arn_hscene_load_json",
     "arn_hscene_build", "arn_hscene_desc", "arn_camera_make", "arn_save_png",
 ]
 
@@ -142,6 +152,10 @@ def load():
         "arn_hscene_add_material": (C.c_int, [vp, C.POINTER(Material)]),
         "arn_hscene_add_mesh": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32]),
         "arn_hscene_add_sphere": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, vp, vp]),
+        "arn_hscene_add_light": (C.c_int, [vp, C.POINTER(AnalyticLight)]),
+        "arn_spot_light_make": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.POINTER(AnalyticLight)]),
+        "arn_point_light_make": (C.c_int, [vp, vp, C.POINTER(AnalyticLight)]),
+        "arn_distant_light_make": (C.c_int, [vp, vp, C.c_float, C.POINTER(AnalyticLight)]),
         "arn_hscene_load_obj": (C.c_int, [vp, C.c_char_p, vp]),
         "arn_hscene_load_json": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), C.c_char_p, C.c_size_t]),
         "arn_hscene_build": (C.c_int, [vp, C.c_int]),

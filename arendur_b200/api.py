@@ -118,6 +118,10 @@ class HostScene:
         tr = _f32(transform).reshape(16) if transform is not None else None
         return self._check(self.lib.arn_hscene_add_sphere(self.h, radius, zmin, zmax, phimax, material_id, _ptr(em), _ptr(tr)))
 
+    def add_light(self, light):
+        """`lights.push(light.to_arc())` for a Point / Spot / Distant light (examples/arencli.rs:95-98)."""
+        return self._check(self.lib.arn_hscene_add_light(self.h, C.byref(light)))
+
     def load_obj(self, path, transform=None):
         tr = _f32(transform).reshape(16) if transform is not None else _f32(IDENTITY).reshape(16)
         return self._check(self.lib.arn_hscene_load_obj(self.h, str(path).encode(), _ptr(tr)))
@@ -221,6 +225,36 @@ class Context:
         if rc != 0:
             raise ArnError(rc, self.error())
         return Scene(self, s)
+
+
+def point_light(pos, intensity):
+    """PointLight::new (lighting/pointlights.rs:25-27)."""
+    out = L.AnalyticLight()
+    p, i = _f32(pos).reshape(3), _f32(intensity).reshape(3)
+    rc = L.load().arn_point_light_make(_ptr(p), _ptr(i), C.byref(out))
+    if rc != 0:
+        raise ArnError(rc, "arn_point_light_make")
+    return out
+
+
+def spot_light(pos, towards, intensity, total_angle, start_falloff_angle):
+    """SpotLight::new (lighting/pointlights.rs:103-122)."""
+    out = L.AnalyticLight()
+    p, t, i = _f32(pos).reshape(3), _f32(towards).reshape(3), _f32(intensity).reshape(3)
+    rc = L.load().arn_spot_light_make(_ptr(p), _ptr(t), _ptr(i), total_angle, start_falloff_angle, C.byref(out))
+    if rc != 0:
+        raise ArnError(rc, L.load().arn_hscene_last_error(None).decode())
+    return out
+
+
+def distant_light(intensity, direction, world_radius):
+    """DistantLight::new + the radius set_world_bounds would store (lighting/distantlight.rs:26-50)."""
+    out = L.AnalyticLight()
+    i, d = _f32(intensity).reshape(3), _f32(direction).reshape(3)
+    rc = L.load().arn_distant_light_make(_ptr(i), _ptr(d), world_radius, C.byref(out))
+    if rc != 0:
+        raise ArnError(rc, "arn_distant_light_make")
+    return out
 
 
 class Scene:

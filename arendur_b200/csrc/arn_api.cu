@@ -263,6 +263,11 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     }
     for (uint32_t i = 0; i < d->n_spheres; i++) if (d->spheres[i].material >= d->n_materials) return set_err(c, ARN_E_INVALID, "sphere material out of range");
     for (uint32_t i = 0; i < d->n_lights; i++) {
+        if (d->light_prims[i] & ARN_LIGHT_ANALYTIC) {
+            uint32_t k = d->light_prims[i] & ~ARN_LIGHT_ANALYTIC;
+            if (k >= d->n_analytic_lights || !d->analytic_lights || d->analytic_lights[k].type > ARN_LIGHT_DISTANT) return set_err(c, ARN_E_INVALID, "light references a missing Point/Spot/Distant light");
+            continue;
+        }
         if (d->light_prims[i] >= d->n_prims || !(d->prims[d->light_prims[i]] & ARN_PRIM_SPHERE))
             return set_err(c, ARN_E_UNSUPPORTED, "lights must be emissive sphere primitives (triangle emitters do not work in arendur: surface_area() == 0, SURVEY.md Appendix A-2)");
     }
@@ -327,6 +332,7 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if ((rc = dev_upload(s, d->materials, d->n_materials, &s->dev.materials)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->prims, d->n_prims, &s->dev.prims)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_prims, d->n_lights, &s->dev.light_prims)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->analytic_lights, d->n_analytic_lights, &s->dev.analytic)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_func, d->n_lights, &s->dev.light_func)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_cdf, d->n_lights ? d->n_lights + 1 : 0, &s->dev.light_cdf)) != ARN_OK) return fail(rc);
     for (uint32_t i = 0; i < d->n_materials; i++) {

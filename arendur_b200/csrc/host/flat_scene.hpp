@@ -28,7 +28,9 @@ public:
     std::vector<uint32_t> prims;
     std::vector<arn_node> nodes;
     std::vector<uint32_t> order;
-    std::vector<uint32_t> light_prims;
+    std::vector<uint32_t> light_prims;            // emissive primitives, in component order
+    std::vector<arn_analytic_light> analytic;     // Point / Spot / Distant lights (come first in Scene.lights)
+    std::vector<uint32_t> light_list;             // Scene.lights: analytic lights, then light_prims
     std::vector<float> light_func, light_cdf;
     float light_integral = 0.f;
     bool any_normals = false, any_uvs = false, built = false;
@@ -123,6 +125,13 @@ public:
         return (int)comp;
     }
 
+    int add_light(const arn_analytic_light& l) {
+        if (l.type > ARN_LIGHT_DISTANT) return fail(ARN_E_INVALID, "unknown light type");
+        analytic.push_back(l);
+        built = false;
+        return (int)analytic.size() - 1;
+    }
+
     // Composable::bbox_parent + intersection_cost of component `i` (ComponentInfo::new, bvh.rs:24-35)
     void component_bounds(uint32_t i, float* b6, float* cost) const {
         uint32_t ref = prims[i];
@@ -161,13 +170,28 @@ public:
         if (rc != ARN_OK) return fail(rc, "arn_bvh_build failed");
         nodes.resize(nn);
         // Scene::new: power().to_xyz().y per light (renderer/scene.rs:36-41, component/shape.rs:160-167)
-        light_func.clear();
+        light_func.clear(); light_list.clear();
+        const float pi = 3.14159265358979323846f;
+        for (size_t k = 0; k < analytic.size(); k++) {
+            const arn_analytic_light& l = analytic[k];
+            // Light::power: pointlights.rs:79-81 (I * (pi * 4)), :222-226 (I * (pi * 2) * (1 - 0.5 * (cosf - cost))),
+            // distantlight.rs:108-110 (I * (r * r * pi))
+            float scale = l.type == ARN_LIGHT_POINT ? pi * 4.0f
+                        : l.type == ARN_LIGHT_SPOT ? 0.f : l.world_radius * l.world_radius * pi;
+            float r = l.intensity[0] * scale, g = l.intensity[1] * scale, b = l.intensity[2] * scale;
+            if (l.type == ARN_LIGHT_SPOT) {
+                float c = 1.0f - 0.5f * (l.cosf - l.cost);
+                r = l.intensity[0] * (pi * 2.0f) * c; g = l.intensity[1] * (pi * 2.0f) * c; b = l.intensity[2] * (pi * 2.0f) * c;
+            }
+            light_func.push_back(0.212671f * r + 0.715160f * g + 0.072169f * b);
+            light_list.push_back(ARN_LIGHT_ANALYTIC | (uint32_t)k);
+        }
         for (uint32_t lp : light_prims) {
             const arn_sphere& s = spheres[prims[lp] & ~ARN_PRIM_SPHERE];
             float area = s.phimax * s.radius * (s.zmax - s.zmin);                 // Sphere::surface_area
-            const float pi = 3.14159265358979323846f;
             float r = s.emission[0] * area * pi, g = s.emission[1] * area * pi, b = s.emission[2] * area * pi;
             light_func.push_back(0.212671f * r + 0.715160f * g + 0.072169f * b);
+            light_list.push_back(lp);
         }
         light_cdf.assign(light_func.size() + 1, 0.f);
         rc = arn_light_distribution((uint32_t)light_func.size(), light_func.data(), light_cdf.data(), &light_integral);
@@ -190,7 +214,8 @@ public:
         desc.n_materials = (uint32_t)materials.size(); desc.materials = materials.data();
         desc.n_prims = (uint32_t)prims.size(); desc.prims = prims.data();
         desc.n_nodes = (uint32_t)nodes.size(); desc.nodes = nodes.data(); desc.order = order.data();
-        desc.n_lights = (uint32_t)light_prims.size(); desc.light_prims = light_prims.data();
+        desc.n_lights = (uint32_t)light_list.size(); desc.light_prims = light_list.data();
+        desc.n_analytic_lights = (uint32_t)analytic.size(); desc.analytic_lights = analytic.data();
         desc.light_func = light_func.data(); desc.light_cdf = light_cdf.data(); desc.light_func_integral = light_integral;
     }
 };

@@ -152,6 +152,75 @@ int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, f
     if (!h) return ARN_E_INVALID;
     return h->fs.add_sphere(radius, zmin, zmax, phimax, material, emission3, transform16);
 }
+int arn_hscene_add_light(arn_hscene* h, const arn_analytic_light* light) { if (!h || !light) return ARN_E_INVALID; return h->fs.add_light(*light); }
+
+int arn_point_light_make(const float* pos3, const float* intensity3, arn_analytic_light* out) {
+    if (!pos3 || !intensity3 || !out) return ARN_E_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->type = ARN_LIGHT_POINT;
+    for (int k = 0; k < 3; k++) { out->pos[k] = pos3[k]; out->intensity[k] = intensity3[k]; }
+    return ARN_OK;
+}
+int arn_distant_light_make(const float* intensity3, const float* dir3, float world_radius, arn_analytic_light* out) {
+    if (!intensity3 || !dir3 || !out) return ARN_E_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->type = ARN_LIGHT_DISTANT;
+    Vec3 d = normalize(Vec3{dir3[0], dir3[1], dir3[2]});                    // DistantLight::new (distantlight.rs:27)
+    out->dir[0] = d.x; out->dir[1] = d.y; out->dir[2] = d.z;
+    for (int k = 0; k < 3; k++) out->intensity[k] = intensity3[k];
+    out->world_radius = world_radius;
+    return ARN_OK;
+}
+int arn_spot_light_make(const float* pos3, const float* towards3, const float* intensity3, float total_angle,
+                        float start_falloff_angle, arn_analytic_light* out) {
+    if (!pos3 || !towards3 || !intensity3 || !out) return ARN_E_INVALID;
+    const float pi = 3.14159265358979323846f;
+    // assert!s of SpotLight::new (pointlights.rs:105-107)
+    if (!(total_angle > start_falloff_angle) || !(start_falloff_angle > 0.f) || !(total_angle < pi * 2.0f)) { g_host_error = "spot light: need 0 < start_falloff_angle < total_angle < 2 pi"; return ARN_E_INVALID; }
+    std::memset(out, 0, sizeof *out);
+    out->type = ARN_LIGHT_SPOT;
+    Vec3 src = normalize(Vec3{towards3[0], towards3[1], towards3[2]}), dst{0.f, 0.f, 1.f};
+    // cgmath 0.14 Quaternion::from_arc(src, dst, None)
+    auto ulps_eq = [](float a, float b) {
+        if (std::fabs(a - b) <= 1.1920929e-7f) return true;
+        if ((a < 0.f) != (b < 0.f)) return false;
+        int32_t ia, ib; std::memcpy(&ia, &a, 4); std::memcpy(&ib, &b, 4);
+        int64_t diff = (int64_t)ia - (int64_t)ib; if (diff < 0) diff = -diff;
+        return diff <= 4;
+    };
+    float mag_avg = std::sqrt((src.x * src.x + src.y * src.y + src.z * src.z) * (dst.x * dst.x + dst.y * dst.y + dst.z * dst.z));
+    float dt = src.x * dst.x + src.y * dst.y + src.z * dst.z;
+    float qs, qx, qy, qz;
+    if (ulps_eq(dt, mag_avg)) { qs = 1.f; qx = qy = qz = 0.f; }
+    else if (ulps_eq(dt, -mag_avg)) {
+        // fallback axis: unit_x x src, or unit_y x src when that vanishes; rotation by half a turn
+        Vec3 v{0.f * src.z - 0.f * src.y, 0.f * src.x - 1.f * src.z, 1.f * src.y - 0.f * src.x};
+        if (ulps_eq(v.x, 0.f) && ulps_eq(v.y, 0.f) && ulps_eq(v.z, 0.f)) v = Vec3{1.f * src.z - 0.f * src.y, 0.f * src.x - 0.f * src.z, 0.f * src.y - 1.f * src.x};
+        v = normalize(v);
+        float half = pi * 0.5f, sn = (float)std::sin((double)half), cs = (float)std::cos((double)half);
+        qs = cs; qx = v.x * sn; qy = v.y * sn; qz = v.z * sn;
+    } else {
+        qs = mag_avg + dt;
+        qx = src.y * dst.z - src.z * dst.y; qy = src.z * dst.x - src.x * dst.z; qz = src.x * dst.y - src.y * dst.x;
+        float inv = 1.f / std::sqrt(qs * qs + qx * qx + qy * qy + qz * qz);
+        qs *= inv; qx *= inv; qy *= inv; qz *= inv;
+    }
+    // Matrix4::from(Quaternion)
+    float x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    float xx2 = x2 * qx, xy2 = x2 * qy, xz2 = x2 * qz, yy2 = y2 * qy, yz2 = y2 * qz, zz2 = z2 * qz;
+    float sy2 = y2 * qs, sz2 = z2 * qs, sx2 = x2 * qs;
+    Mat4 rot = Mat4::identity();
+    rot.c[0][0] = 1.f - yy2 - zz2; rot.c[0][1] = xy2 + sz2; rot.c[0][2] = xz2 - sy2;
+    rot.c[1][0] = xy2 - sz2; rot.c[1][1] = 1.f - xx2 - zz2; rot.c[1][2] = yz2 + sx2;
+    rot.c[2][0] = xz2 + sy2; rot.c[2][1] = yz2 - sx2; rot.c[2][2] = 1.f - xx2 - yy2;
+    Mat4 parent_local = rot * Mat4::translation(pos3[0] - 0.f, pos3[1] - 0.f, pos3[2] - 0.f), local_parent;
+    if (!invert(parent_local, &local_parent)) { g_host_error = "spot light: invalid inversion"; return ARN_E_INVALID; }   // .expect("invalid inversion")
+    parent_local.to_array(out->parent_local);
+    for (int k = 0; k < 3; k++) { out->pos[k] = pos3[k]; out->intensity[k] = intensity3[k]; }
+    out->cost = (float)std::cos((double)total_angle); out->cosf = (float)std::cos((double)start_falloff_angle);
+    return ARN_OK;
+}
+
 int arn_hscene_load_obj(arn_hscene* h, const char* path, const float* transform16) {
     if (!h || !path) return ARN_E_INVALID;
     std::string err; int rc = load_obj_into(h->fs, path, transform16, &err);
@@ -195,9 +264,31 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
     std::stringstream ss; ss << f.rdbuf(); std::string text = ss.str();
     Json root; std::string perr;
     if (!JsonParser(text).parse(&root, &perr)) return fs.fail(ARN_E_IO, "JSON decode error: " + perr);
+    // `for light in scenedesc.lights.iter() { lights.push(light.to_arc()) }` (arencli.rs:95-98): serde's
+    // externally tagged LightDesc::{Point, Spot, Distant} carrying the light structs field by field
     const Json* lights = root.get("lights");
-    if (lights && lights->kind == Json::Arr && !lights->arr.empty())
-        return fs.fail(ARN_E_UNSUPPORTED, "Point/Spot/Distant lights are outside the hot path (SURVEY.md §8(f) N3)");
+    if (lights && lights->kind == Json::Arr) for (const Json& l : lights->arr) {
+        arn_analytic_light al; std::memset(&al, 0, sizeof al);
+        const Json* b;
+        auto rgb = [&](const Json* j, float* o) { return j && json_vec(j->get("inner"), XYZ, 3, o); };
+        if ((b = l.get("Point"))) {
+            al.type = ARN_LIGHT_POINT;
+            if (!json_vec(b->get("posw"), XYZ, 3, al.pos) || !rgb(b->get("intensity"), al.intensity)) return fs.fail(ARN_E_INVALID, "malformed Point light");
+        } else if ((b = l.get("Spot"))) {
+            al.type = ARN_LIGHT_SPOT;
+            const Json* pl = b->get("parent_local"); const Json* lp = b->get("local_parent"); float unused[16];
+            if (!json_vec(b->get("posw"), XYZ, 3, al.pos) || !rgb(b->get("intensity"), al.intensity) || !json_num(b->get("cost"), &al.cost)
+                || !json_num(b->get("cosf"), &al.cosf) || !pl || !json_matrix(*pl, al.parent_local) || !lp || !json_matrix(*lp, unused))
+                return fs.fail(ARN_E_INVALID, "malformed Spot light");
+        } else if ((b = l.get("Distant"))) {
+            al.type = ARN_LIGHT_DISTANT;
+            float centre[3];
+            if (!rgb(b->get("intensity"), al.intensity) || !json_vec(b->get("dir"), XYZ, 3, al.dir) || !json_vec(b->get("world_center"), XYZ, 3, centre)
+                || !json_num(b->get("world_radius"), &al.world_radius)) return fs.fail(ARN_E_INVALID, "malformed Distant light");
+        } else return fs.fail(ARN_E_INVALID, "unknown light description");
+        int rc = fs.add_light(al);
+        if (rc < 0) return rc;
+    }
     const Json* comps = root.get("components");
     if (!comps || comps->kind != Json::Arr) return fs.fail(ARN_E_INVALID, "scene has no components array");
     std::string base = base_dir ? std::string(base_dir) : std::string();

@@ -664,6 +664,35 @@ ARN_NOINL LightSample light_sample(const DevSphere& sp, float3 pos, float2 u) {
     if (sp.has_transform) { ls.pfrom = xform_point(sp.local_parent, ls.pfrom); ls.pto = xform_point(sp.local_parent, ls.pto); }
     return ls;
 }
+// PointLight / SpotLight / DistantLight::evaluate_sampled (lighting/pointlights.rs:50-61,181-194 with
+// falloff :147-158; lighting/distantlight.rs:68-80).  pdf is 1 for all three.
+ARN_NOINL LightSample analytic_sample(const arn_analytic_light& l, float3 pos) {
+    LightSample ls; ls.pdf = 1.f; ls.pto = pos;
+    float3 intensity = f3(l.intensity[0], l.intensity[1], l.intensity[2]);
+    if (l.type == ARN_LIGHT_POINT) {
+        ls.pfrom = f3(l.pos[0], l.pos[1], l.pos[2]);
+        ls.radiance = intensity / length2(ls.pto - ls.pfrom);
+    } else if (l.type == ARN_LIGHT_SPOT) {
+        ls.pfrom = f3(l.pos[0], l.pos[1], l.pos[2]);
+        float3 dir = ls.pto - ls.pfrom;
+        float mag2 = length2(dir);
+        float cos_theta = xform_vector(l.parent_local, dir / sqrtf(mag2)).z;
+        float falloff;
+        if (cos_theta < l.cost) falloff = 0.f;
+        else if (cos_theta > l.cosf) falloff = 1.f;
+        else {
+            float delta = (cos_theta - l.cost) / (l.cosf - l.cost);
+            float delta2 = delta * delta;
+            falloff = delta2 * delta2;
+        }
+        ls.radiance = intensity * falloff / mag2;
+    } else {
+        ls.radiance = intensity;
+        ls.pfrom = pos + f3(l.dir[0], l.dir[1], l.dir[2]) * (-2.0f * l.world_radius);
+    }
+    return ls;
+}
+
 // Light::pdf = Shape::pdf_wrt (shape/mod.rs:67-75): needs the local hit normal
 ARN_NOINL float light_pdf(const DevSphere& sp, float3 pos, float3 wi) {
     if (sp.has_transform) { pos = xform_point(sp.parent_local, pos); wi = xform_vector(sp.parent_local, wi); }

@@ -38,6 +38,7 @@ struct DevScene {
     const arn_material* __restrict__ materials;
     const uint32_t* __restrict__ prims;      // component -> triangle id | sphere bit
     const uint32_t* __restrict__ light_prims;
+    const arn_analytic_light* __restrict__ analytic;   // Point / Spot / Distant lights
     const float* __restrict__ light_func;
     const float* __restrict__ light_cdf;
     float light_integral;

@@ -320,17 +320,20 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                     uint32_t lidx = lo - 1;
                     float lightpdf = sc.light_integral > 0.f ? sc.light_func[lidx] / sc.light_integral : 0.f;
                     uint32_t lcomp = sc.light_prims[lidx];
-                    const DevSphere& light = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
+                    // a Point / Spot / Distant light (pointlights.rs, distantlight.rs) or an emissive sphere
+                    const bool analytic = (lcomp & ARN_LIGHT_ANALYTIC) != 0;
+                    const bool delta = analytic && sc.analytic[lcomp & ~ARN_LIGHT_ANALYTIC].type != ARN_LIGHT_DISTANT;
+                    const DevSphere& light = sc.spheres[analytic ? 0u : (sc.prims[lcomp] & ~ARN_PRIM_SPHERE)];   // not read when analytic
                     flags = NEE_DONE;
                     // Scene::evaluate_direct (scene.rs:83-167): light sampling half
-                    LightSample ls = light_sample(light, s.pos, ulight);
+                    LightSample ls = analytic ? analytic_sample(sc.analytic[lcomp & ~ARN_LIGHT_ANALYTIC], s.pos) : light_sample(light, s.pos, ulight);
                     float3 wi = normalize(ls.pfrom - ls.pto);
                     float3 A1 = grey(0.f);
                     if (!(ls.pdf == 0.f || is_black(ls.radiance))) {
                         float3 f = bsdf_eval_k<DIFFUSE>(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns));
                         float spdf = bsdf_pdf_k<DIFFUSE>(bsdf, s.wo, wi);
                         if (spdf == 0.f) f = grey(0.f);
-                        float weight = power_heuristic(ls.pdf, spdf);
+                        float weight = delta ? 1.f : power_heuristic(ls.pdf, spdf);    // is_delta: no MIS weight (scene.rs:107-115); x * 1 is exact
                         A1 = ls.radiance * f * weight / ls.pdf;
                         if (!is_black(f)) {
                             // LightSample::occluded (lighting/mod.rs:125-133) + RawRay::spawn (ray.rs:93-98)
@@ -346,19 +349,22 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                             flags |= NEE_SHADOW; has_sh = true;
                         }
                     }
-                    // BSDF sampling half
+                    // BSDF sampling half (scene.rs:128-165), skipped for delta lights.  A Distant light has no
+                    // Light::pdf (default 0, lighting/mod.rs:64-66) and is nobody's `as_light()`: non-specular
+                    // samples stop at lpdf == 0, specular ones trace a ray that can only add black.
                     float3 A2 = grey(0.f);
-                    Sampled bs = bsdf_sample_k<DIFFUSE>(bsdf, s.wo, uscatter);
+                    Sampled bs; bs.f = grey(0.f); bs.wi = f3(0.f, 1.f, 0.f); bs.pdf = 0.f; bs.type = 0;
+                    if (!delta) bs = bsdf_sample_k<DIFFUSE>(bsdf, s.wo, uscatter);
                     float3 f2v = bs.f * fabsf(dot(bs.wi, s.ns));
                     if (!is_black(f2v) && bs.pdf > 0.f) {
                         float weight = 1.f; bool skip = false;
                         if (!(bs.type & BXDF_SPECULAR)) {
-                            float lpdf = light_pdf(light, s.pos, bs.wi);
+                            float lpdf = analytic ? 0.f : light_pdf(light, s.pos, bs.wi);
                             if (lpdf == 0.f) skip = true; else weight = power_heuristic(bs.pdf, lpdf);
                         }
                         if (!skip) {
                             float3 mo = offset_towards(s, bs.wi);
-                            A2 = f2v * sphere_emission(light) * weight / bs.pdf;
+                            if (!analytic) A2 = f2v * sphere_emission(light) * weight / bs.pdf;
                             pb.mis_o[pid] = make_float4(mo.x, mo.y, mo.z, 0.f);
                             pb.mis_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
                             flags |= NEE_MIS; has_mis = true;

@@ -115,11 +115,14 @@ def pixel_center_rays(cam, w, h):
 
 
 # ---------------------------------------------------------------- Cornell (C1 / C3 / C5)
-def cornell_scene(res_x=256, res_y=256, sampledx=4, sampledy=4, seed=0, fixture=CORNELL_FIXTURE):
+def cornell_scene(res_x=256, res_y=256, sampledx=4, sampledy=4, seed=0, fixture=CORNELL_FIXTURE, lights=()):
     """The cb.json scene with the film / sampler of the requested config.
-    Returns (HostScene built, camera, film, sampler, pt_params)."""
+    `lights`: extra Point / Spot / Distant lights (api.point_light(...) etc.), placed first in Scene.lights as
+    arencli does.  Returns (HostScene built, camera, film, sampler, pt_params)."""
     z = np.load(fixture, allow_pickle=False)
     hs = api.HostScene()
+    for l in lights:
+        hs.add_light(l)
     mats = z["materials"]          # rows: type, kd3, ks3, sigma, roughness, eta, dissolve
     mat_ids = []
     for r in mats:

@@ -96,6 +96,24 @@ typedef struct arn_sphere {
     float    parent_local[16];
 } arn_sphere;
 
+/* `PointLight`, `SpotLight` (lighting/pointlights.rs:16-22,88-101) and `DistantLight`
+ * (lighting/distantlight.rs:16-21): the lights arencli reads from the scene file's `lights` array
+ * (examples/arencli.rs:95-98,487-509).  Fields are the reference's own (its serde form), so a
+ * deserialised light is passed through unchanged. */
+#define ARN_LIGHT_POINT   0u
+#define ARN_LIGHT_SPOT    1u
+#define ARN_LIGHT_DISTANT 2u
+#define ARN_LIGHT_ANALYTIC 0x80000000u   /* light_prims[i] = ARN_LIGHT_ANALYTIC | k: entry k of analytic_lights */
+typedef struct arn_analytic_light {
+    uint32_t type;               /* ARN_LIGHT_*                                                    */
+    float    pos[3];             /* Point / Spot: posw                                             */
+    float    intensity[3];
+    float    cost, cosf;         /* Spot: cos(total angle), cos(falloff start)                     */
+    float    parent_local[16];   /* Spot: column-major; falloff reads its z row only               */
+    float    dir[3];             /* Distant: direction the light travels in (normalised by ::new)  */
+    float    world_radius;       /* Distant: bounding-sphere radius; power and pfrom scale with it */
+} arn_analytic_light;
+
 /* Everything `Scene::new(lights, BVH::new(components, SAH))` holds
  * (renderer/scene.rs:23-51, component/bvh.rs:49-79), flattened. */
 typedef struct arn_scene_desc {
@@ -121,13 +139,17 @@ typedef struct arn_scene_desc {
     uint32_t        n_nodes;
     const arn_node* nodes;
     const uint32_t* order;         /* n_prims: ordered slot -> index into prims   */
-    /* lights = emissive primitives, in `Scene.lights` order, with the power
-     * distribution of Scene::new (renderer/scene.rs:31-51, sample/distribution.rs:25-63) */
+    /* lights in `Scene.lights` order (arencli: the file's `lights` array, then the emissive
+     * primitives), with the power distribution of Scene::new (renderer/scene.rs:31-51,
+     * sample/distribution.rs:25-63) */
     uint32_t        n_lights;
-    const uint32_t* light_prims;   /* n_lights: index into prims                  */
+    const uint32_t* light_prims;   /* n_lights: index into prims (an emissive sphere), or
+                                      ARN_LIGHT_ANALYTIC | index into analytic_lights        */
     const float*    light_func;    /* n_lights: power().to_xyz().y                */
     const float*    light_cdf;     /* n_lights + 1                                */
     float           light_func_integral;
+    uint32_t        n_analytic_lights;
+    const arn_analytic_light* analytic_lights;
 } arn_scene_desc;
 
 /* `PerspecCam` (filming/perspective.rs:25-38) reduced to what ray generation reads

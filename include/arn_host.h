@@ -43,6 +43,23 @@ int arn_hscene_add_mesh(arn_hscene* h, const float* positions, uint32_t n_vertic
 int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, float phimax,
                           uint32_t material, const float* emission3, const float* transform16);
 
+/* `lights.push(light.to_arc())` for the scene file's Point / Spot / Distant lights
+ * (examples/arencli.rs:95-98).  These come first in `Scene.lights`, before the emissive
+ * primitives.  Returns the index into analytic_lights or an error. */
+int arn_hscene_add_light(arn_hscene* h, const arn_analytic_light* light);
+
+/* SpotLight::new(pos, towards, intensity, total_angle, start_falloff_angle)
+ * (lighting/pointlights.rs:103-122): builds parent_local = rotation(towards -> +z) * translation(pos)
+ * with cgmath's Quaternion::from_arc.  cgmath is a crates.io dependency that is not vendored in the
+ * reference tree; its published from_arc / Matrix4::from(Quaternion) are restated (parity unpinned —
+ * scene files carry the matrices themselves and do not go through this helper). */
+int arn_spot_light_make(const float* pos3, const float* towards3, const float* intensity3,
+                        float total_angle, float start_falloff_angle, arn_analytic_light* out);
+/* PointLight::new (pointlights.rs:25-27) / DistantLight::new + set_world_bounds given the radius
+ * (distantlight.rs:26-50). */
+int arn_point_light_make(const float* pos3, const float* intensity3, arn_analytic_light* out);
+int arn_distant_light_make(const float* intensity3, const float* dir3, float world_radius, arn_analytic_light* out);
+
 /* component::load_obj (component/mod.rs:65-185): tobj-compatible OBJ + MTL ingest, material
  * choice per MTL, one mesh per model. Returns the number of triangles added or an error. */
 int arn_hscene_load_obj(arn_hscene* h, const char* path, const float* transform16);

@@ -48,6 +48,14 @@ int arn_oracle_light_distribution(uint32_t n, const float* func, float* cdf_out,
 }
 // Light::power().to_xyz().y for a sphere primitive (component/shape.rs:160-167, renderer/scene.rs:38-40)
 float arn_oracle_light_power_y(const arn_sphere* sp) { return rgb_y(light_power(*sp)); }
+// the same for Point / Spot / Distant lights (pointlights.rs:79-81,222-226, distantlight.rs:108-110)
+float arn_oracle_analytic_power_y(const arn_analytic_light* l) { return rgb_y(analytic_power(*l)); }
+// Light::evaluate_sampled of an analytic light: out7 = radiance rgb, pdf, pfrom xyz
+void arn_oracle_analytic_sample(const arn_analytic_light* l, const float* pos3, float* out7) {
+    LightSample ls = analytic_evaluate_sampled(*l, v3(pos3[0], pos3[1], pos3[2]));
+    out7[0] = ls.radiance.x; out7[1] = ls.radiance.y; out7[2] = ls.radiance.z; out7[3] = ls.pdf;
+    out7[4] = ls.pfrom.x; out7[5] = ls.pfrom.y; out7[6] = ls.pfrom.z;
+}
 
 int arn_oracle_scene_create(const arn_scene_desc* d, arn_oracle_scene** out) {
     if (!d || !out) return ARN_E_INVALID;

@@ -98,6 +98,47 @@ inline Float light_pdf(const arn_sphere& sp, V3 pos, V3 wi) {
     if (sp.has_transform) { M4 pl = m4_from_cols(sp.parent_local); pos = transform_point(pl, pos); wi = transform_vector(pl, wi); }
     return sphere_pdf_wrt(sp, pos, wi);
 }
+// ---- PointLight / SpotLight / DistantLight (lighting/pointlights.rs, lighting/distantlight.rs)
+// SpotLight::falloff (pointlights.rs:147-158): cos_theta = parent_local.transform_vector(dir).z
+inline Float spot_falloff(const arn_analytic_light& l, V3 dir) {
+    M4 pl = m4_from_cols(l.parent_local);
+    Float cos_theta = transform_vector(pl, dir).z;
+    if (cos_theta < l.cost) return 0.f;
+    else if (cos_theta > l.cosf) return 1.f;
+    else {
+        Float delta = (cos_theta - l.cost) / (l.cosf - l.cost);
+        Float delta2 = delta * delta;
+        return delta2 * delta2;
+    }
+}
+// Light::evaluate_sampled: pointlights.rs:50-61 (Point), :181-194 (Spot), distantlight.rs:68-80 (Distant)
+inline LightSample analytic_evaluate_sampled(const arn_analytic_light& l, V3 pos) {
+    LightSample ret; ret.pdf = 1.0f; ret.pto = pos;
+    RGB intensity = rgb(l.intensity[0], l.intensity[1], l.intensity[2]);
+    if (l.type == ARN_LIGHT_POINT) {
+        ret.pfrom = v3(l.pos[0], l.pos[1], l.pos[2]);
+        ret.radiance = intensity / magnitude2(ret.pto - ret.pfrom);
+    } else if (l.type == ARN_LIGHT_SPOT) {
+        ret.pfrom = v3(l.pos[0], l.pos[1], l.pos[2]);
+        V3 dir = ret.pto - ret.pfrom;
+        Float mag2 = magnitude2(dir);
+        ret.radiance = intensity * spot_falloff(l, dir / std::sqrt(mag2)) / mag2;
+    } else {
+        V3 d = v3(l.dir[0], l.dir[1], l.dir[2]);
+        ret.radiance = intensity;
+        ret.pfrom = pos + d * (-2.0f * l.world_radius);
+    }
+    return ret;
+}
+inline bool analytic_is_delta(const arn_analytic_light& l) { return l.type != ARN_LIGHT_DISTANT; }   // LIGHT_DPOS vs LIGHT_INFINITE
+// Light::power: pointlights.rs:79-81, :222-226, distantlight.rs:108-110
+inline RGB analytic_power(const arn_analytic_light& l) {
+    RGB intensity = rgb(l.intensity[0], l.intensity[1], l.intensity[2]);
+    if (l.type == ARN_LIGHT_POINT) return intensity * (pi() * 4.0f);
+    if (l.type == ARN_LIGHT_SPOT) return intensity * (pi() * 2.0f) * (1.0f - 0.5f * (l.cosf - l.cost));
+    return intensity * (l.world_radius * l.world_radius * pi());
+}
+
 // Light::power (component/shape.rs:160-167): mean * area * pi
 inline RGB light_power(const arn_sphere& sp) {
     if (!sp.emissive) return grey(0.f);
@@ -128,6 +169,35 @@ inline bool ls_occluded(const Scene& s, const LightSample& ls, RayStats* st) {
 // Scene::evaluate_direct (renderer/scene.rs:83-167)
 inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 uscattering,
                            const SurfaceInteraction& si, const Bsdf& bsdf, RayStats* st) {
+    if (light_comp & ARN_LIGHT_ANALYTIC) {
+        const arn_analytic_light& al = s.analytic_lights[light_comp & ~ARN_LIGHT_ANALYTIC];
+        RGB ret = grey(0.f);
+        LightSample ls = analytic_evaluate_sampled(al, si.basic.pos);
+        V3 wi = normalize(ls.pfrom - ls.pto);
+        bool no_effect = ls.pdf == 0.f || is_black(ls.radiance);
+        if (!no_effect) {
+            RGB f = bsdf_evaluate(bsdf, si.basic.wo, wi, BXDF_ALL) * std::fabs(dot(wi, si.shading_norm));
+            Float spdf = bsdf_pdf(bsdf, si.basic.wo, wi, BXDF_ALL);
+            if (spdf == 0.f) f = grey(0.f);
+            if (!is_black(f) && ls_occluded(s, ls, st)) f = grey(0.f);
+            if (analytic_is_delta(al)) ret = ret + ls.radiance * f / ls.pdf;                       // scene.rs:107-115
+            else ret = ret + ls.radiance * f * power_heuristic(ls.pdf, spdf) / ls.pdf;            // :116-124
+        }
+        // scene.rs:128-165 for a non-delta light without Light::pdf / as_light: the BSDF-sampled ray can only
+        // add `li = black` — non-specular lobes stop at `lpdf == 0` (lighting/mod.rs:64-66), specular ones
+        // trace a ray whose hit is never `ptr::eq` to this light.  The ray is still traced (and counted).
+        if (!analytic_is_delta(al)) {
+            Sampled bs = bsdf_evaluate_sampled(bsdf, si.basic.wo, uscattering, BXDF_ALL);
+            RGB f = bs.f * std::fabs(dot(bs.wi, si.shading_norm));
+            if (!is_black(f) && bs.pdf > 0.f && (bs.type & BXDF_SPECULAR)) {
+                RawRay ray = si_spawn_ray(si, bs.wi);
+                SurfaceInteraction lsi; int lprim;
+                if (st) st->mis++;
+                bvh_intersect(s, ray, &lsi, &lprim, st ? &st->trav : nullptr, true);
+            }
+        }
+        return ret;
+    }
     const arn_sphere& light = s.spheres[s.prim_index(light_comp)];
     RGB ret = grey(0.f);
     LightSample ls = light_evaluate_sampled(light, si.basic.pos, ulight);

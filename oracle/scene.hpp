@@ -20,7 +20,8 @@ struct Scene {
     std::vector<uint32_t> prims;          // component list handed to BVH::new
     std::vector<arn_node> nodes;
     std::vector<uint32_t> order;          // ordered slot -> component index
-    std::vector<uint32_t> light_prims;
+    std::vector<uint32_t> light_prims;    // Scene.lights: component index, or ARN_LIGHT_ANALYTIC | index below
+    std::vector<arn_analytic_light> analytic_lights;
     std::vector<Float> light_func, light_cdf;
     Float light_func_integral = 0.f;
 
@@ -44,6 +45,7 @@ struct Scene {
             light_cdf.assign(d.light_cdf, d.light_cdf + d.n_lights + 1);
         }
         light_func_integral = d.light_func_integral;
+        if (d.n_analytic_lights) analytic_lights.assign(d.analytic_lights, d.analytic_lights + d.n_analytic_lights);
     }
     bool prim_is_sphere(uint32_t comp) const { return (prims[comp] & ARN_PRIM_SPHERE) != 0; }
     uint32_t prim_index(uint32_t comp) const { return prims[comp] & ~ARN_PRIM_SPHERE; }

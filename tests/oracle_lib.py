@@ -37,6 +37,10 @@ def load():
     lib.arn_oracle_light_distribution.argtypes = [C.c_uint32, vp, vp, vp]
     lib.arn_oracle_light_power_y.restype = C.c_float
     lib.arn_oracle_light_power_y.argtypes = [C.POINTER(L.Sphere)]
+    lib.arn_oracle_analytic_power_y.restype = C.c_float
+    lib.arn_oracle_analytic_power_y.argtypes = [C.POINTER(L.AnalyticLight)]
+    lib.arn_oracle_analytic_sample.restype = None
+    lib.arn_oracle_analytic_sample.argtypes = [C.POINTER(L.AnalyticLight), vp, vp]
     lib.arn_oracle_scene_create.restype = C.c_int
     lib.arn_oracle_scene_create.argtypes = [C.POINTER(L.SceneDesc), C.POINTER(vp)]
     lib.arn_oracle_scene_destroy.argtypes = [vp]

@@ -221,3 +221,59 @@ def test_wide_equals_binary(ctx, cornell_small):
     assert np.array_equal(a2, a4)
     assert h2.tobytes() == h_bin.cpu().numpy().tobytes()
     sc.close()
+
+
+def _light_rig():
+    # inside the Cornell room: a point light near the ceiling, a spot aimed at the glass box, a distant "sun"
+    return [api.point_light((0.3, 1.6, 3.0), (2.0, 1.5, 1.0)),
+            api.spot_light((-0.8, 1.9, 4.5), (0.4, -1.0, -0.6), (9.0, 9.0, 7.0), 0.7, 0.35),
+            api.distant_light((0.8, 0.8, 1.0), (0.2, -1.0, -0.4), 6.0)]
+
+
+def test_analytic_lights_bit_exact(ctx):
+    """Point / Spot / Distant lights (lighting/pointlights.rs, distantlight.rs) next to the two emissive
+    spheres: delta lights skip MIS, the distant light keeps the weight and traces its (fruitless) specular
+    light rays.  Every camera sample bit-identical to the oracle; the same rays are traced."""
+    hs, cam, film, smp, prm = scenes.cornell_scene(96, 72, 2, 2, lights=_light_rig())
+    d = hs.desc()
+    assert d.n_lights == 5
+    sc = ctx.upload(d)
+    osc = O.OracleScene(d)
+    gf, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    rf, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.mean() >= 1.0 - 1e-4, f"{(~same).sum()} of {same.size} samples differ"
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays)
+    # the rig changes the picture: compare with the sphere-lit render
+    hs0, *_ = scenes.cornell_scene(96, 72, 2, 2)
+    sc0 = ctx.upload(hs0.desc())
+    _, grad0, _ = sc0.render_pt_samples(cam, film, smp, prm)
+    assert np.abs(grad[..., :3] - grad0[..., :3]).mean() > 1e-3
+    sc.close(); sc0.close(); osc.close()
+
+
+def test_analytic_lights_only(ctx):
+    """A scene without any emissive primitive (and without spheres at all): only a spot and a point light."""
+    hs = api.HostScene()
+    hs.add_light(api.spot_light((0, 3, 0), (0.1, -1, 0.05), (20, 18, 15), 0.6, 0.3))
+    hs.add_light(api.point_light((2, 1, -1), (3, 3, 4)))
+    matte = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.6, 0.7)))
+    plastic = hs.add_material(api.material(L.ARN_MAT_PLASTIC, kd=(0.4, 0.3, 0.2), ks=(0.5, 0.5, 0.5), roughness=0.2))
+    hs.add_mesh(np.float32([[-10, 0, -10], [10, 0, -10], [10, 0, 10], [-10, 0, 10]]), np.uint32([0, 2, 1, 0, 3, 2]), matte)
+    hs.add_mesh(np.float32([[-1, 0.5, -1], [1, 0.5, -1], [1, 1.2, 1], [-1, 1.2, 1]]), np.uint32([0, 2, 1, 0, 3, 2]), plastic)
+    hs.build()
+    view_parent = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, -1, 0, 0], [0, 5, 0, 1]], np.float32)
+    parent_view = np.linalg.inv(view_parent.T).T.astype(np.float32)
+    cam = api.make_camera(parent_view.reshape(-1), (-1, -1, 1, 1), 0.1, 100.0, 1.0, 64, 64)
+    film, smp, prm = api.make_film(64, 64), api.make_sampler(2, 2, 8, 3), api.make_pt_params(max_depth=4)
+    d = hs.desc()
+    assert d.n_spheres == 0 and d.n_lights == 2
+    sc = ctx.upload(d)
+    osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.mean() >= 1.0 - 1e-4, f"{(~same).sum()} of {same.size} samples differ"
+    assert st.mis_rays == 0 and st.shadow_rays > 0 and (orad[..., :3].max(-1) > 0).mean() > 0.3
+    sc.close(); osc.close()

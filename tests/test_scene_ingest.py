@@ -164,4 +164,4 @@ def test_json_errors(tmp_path):
     p.write_text('{"lights": [{"Point": {}}], "components": []}')
     with pytest.raises(api.ArnError) as e:
         api.HostScene().load_json(p)
-    assert e.value.code == L.ARN_E_UNSUPPORTED
+    assert e.value.code == L.ARN_E_INVALID          # malformed Point light
