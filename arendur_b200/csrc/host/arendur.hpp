@@ -63,6 +63,27 @@ struct RawRay {                                            // geometry/ray.rs:64
 };
 struct Hit { int prim_id; Float t; bool is_some() const { return prim_id >= 0; } };
 
+// lighting::pointlights::{PointLight, SpotLight}, lighting::distantlight::DistantLight — same constructors
+struct Light {
+    arn_analytic_light l;
+    static Light point(const Float pos[3], const RGBSpectrumf& intensity) {                       // PointLight::new
+        Light x{}; Float i[3] = {intensity.r, intensity.g, intensity.b};
+        int rc = arn_point_light_make(pos, i, &x.l); if (rc != ARN_OK) throw Panic(rc, "PointLight::new"); return x;
+    }
+    static Light spot(const Float pos[3], const Float towards[3], const RGBSpectrumf& intensity, Float total_angle, Float start_falloff_angle) {   // SpotLight::new
+        Light x{}; Float i[3] = {intensity.r, intensity.g, intensity.b};
+        int rc = arn_spot_light_make(pos, towards, i, total_angle, start_falloff_angle, &x.l);
+        if (rc != ARN_OK) throw Panic(rc, arn_hscene_last_error(nullptr));                         // the assert!s of SpotLight::new
+        return x;
+    }
+    // DistantLight::new(intensity, dir) followed by set_world_bounds(): pass the bounding-sphere radius (the reference
+    // leaves it infinite until set_world_bounds is called, which makes the light sample NaN)
+    static Light distant(const RGBSpectrumf& intensity, const Float dir[3], Float world_radius) {
+        Light x{}; Float i[3] = {intensity.r, intensity.g, intensity.b};
+        int rc = arn_distant_light_make(i, dir, world_radius, &x.l); if (rc != ARN_OK) throw Panic(rc, "DistantLight::new"); return x;
+    }
+};
+
 // The `Vec<ComponentPointer>` + `lights` that arencli assembles (examples/arencli.rs:88-194).
 class Components {
 public:
@@ -81,6 +102,8 @@ public:
         Float e[3]; if (emission) { e[0] = emission->r; e[1] = emission->g; e[2] = emission->b; }
         return check(arn_hscene_add_sphere(h_, s.radius, s.zmin, s.zmax, s.phimax, (uint32_t)material, emission ? e : nullptr, transform ? transform->data() : nullptr));
     }
+    // `lights.push(light.to_arc())` (examples/arencli.rs:95-98): ahead of the emissive primitives in Scene.lights
+    int push_light(const Light& light) { return check(arn_hscene_add_light(h_, &light.l)); }
     arn_hscene* raw() { return h_; }
     int check(int rc) const { if (rc < 0) throw Panic(rc, arn_hscene_last_error(h_)); return rc; }
 private:

@@ -51,11 +51,35 @@ static void test_render_small(Device& dev) {
     assert(lum > 0.0);                                      // the wall is lit by the sphere behind the camera
 }
 
+// a wall lit only by scene-file style lights: SpotLight::new + PointLight::new, no emissive primitive
+static void test_render_analytic_lights(Device& dev) {
+    Components comps;
+    int wall = comps.add_material(Material::matte({0.7f, 0.7f, 0.7f}, 0.f));
+    comps.push_mesh({-2, -2, 4, 2, -2, 4, 2, 2, 4, -2, 2, 4}, {0, 1, 2, 0, 2, 3}, wall);
+    const Float pos[3] = {0.f, 0.f, 1.f}, towards[3] = {0.f, 0.f, 1.f}, ppos[3] = {1.f, 1.f, 2.f};
+    comps.push_light(Light::spot(pos, towards, {8.f, 8.f, 8.f}, 0.6f, 0.3f));
+    comps.push_light(Light::point(ppos, {1.f, 2.f, 3.f}));
+    bool threw = false;
+    try { Light::spot(pos, towards, {1, 1, 1}, 0.2f, 0.3f); } catch (const Panic&) { threw = true; }     // assert!(total_angle > start_falloff_angle)
+    assert(threw);
+    BVH::build(comps);
+    Scene scene(dev, comps);
+    const Float screen[4] = {-1.f, -1.f, 1.f, 1.f};
+    PerspecCam cam = PerspecCam::make(identity(), screen, 0.1f, 1000.f, 1.2707964f, nullptr, Film::make(32, 32));
+    PTRenderer r(StrataSampler::make(2, 2, 8), cam, "", 3, true);
+    arn_stats st;
+    const std::vector<Float>& film = r.render(scene, &st);
+    assert(st.shadow_rays > 0 && st.mis_rays == 0 && st.invalid_samples == 0);
+    double lum = 0; for (size_t i = 0; i < film.size(); i += 4) if (film[i + 3] != 0.f) lum += film[i] / film[i + 3];
+    assert(lum > 0.0);
+}
+
 int main() {
     test_panics();
     Device dev(0);
     test_sy_intersect(dev);
     test_render_small(dev);
+    test_render_analytic_lights(dev);
     std::printf("mirror API tests: OK\n");
     return 0;
 }
