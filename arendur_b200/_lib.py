@@ -16,6 +16,7 @@ ARN_BVH_SAH, ARN_BVH_MIDDLECOUNT, ARN_BVH_MIDPOINT = 0, 1, 2
 ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY, ARN_OPT_BVH_WIDTH = 1, 2, 3
 ARN_LIGHT_POINT, ARN_LIGHT_SPOT, ARN_LIGHT_DISTANT = 0, 1, 2
 ARN_LIGHT_ANALYTIC = 0x80000000
+ARN_FILTER_LANCZOS, ARN_FILTER_BOX, ARN_FILTER_TRIANGLE, ARN_FILTER_GAUSSIAN, ARN_FILTER_MITCHELL = 0, 1, 2, 3, 4
 ARN_MAT_MATTE, ARN_MAT_PLASTIC, ARN_MAT_GLASS, ARN_MAT_TRANSLUCENT = 0, 1, 2, 3
 
 c_float_p = C.POINTER(C.c_float)
@@ -63,12 +64,13 @@ class SceneDesc(C.Structure):
 
 class Camera(C.Structure):
     _fields_ = [("raster_view", C.c_float * 16), ("view_parent", C.c_float * 16), ("has_lens", C.c_uint32),
-                ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
+                ("lens_radius", C.c_float), ("focal_distance", C.c_float), ("ortho", C.c_uint32)]
 
 
 class Film(C.Structure):
     _fields_ = [("res_x", C.c_uint32), ("res_y", C.c_uint32), ("crop_min_x", C.c_int32), ("crop_min_y", C.c_int32),
-                ("crop_max_x", C.c_int32), ("crop_max_y", C.c_int32), ("filter_radius_x", C.c_float), ("filter_radius_y", C.c_float)]
+                ("crop_max_x", C.c_int32), ("crop_max_y", C.c_int32), ("filter_radius_x", C.c_float), ("filter_radius_y", C.c_float),
+                ("filter_kind", C.c_uint32), ("filter_a", C.c_float), ("filter_b", C.c_float)]
 
 
 class Sampler(C.Structure):
@@ -108,7 +110,7 @@ ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
     "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_spot_light_make", "arn_point_light_make",
     "arn_distant_light_make", "arn_hscene_load_obj", "arn_hscene_load_json",
-    "arn_hscene_build", "arn_hscene_desc", "arn_camera_make", "arn_save_png",
+    "arn_hscene_build", "arn_hscene_desc", "arn_camera_make", "arn_ortho_camera_make", "arn_save_png",
 ]
 
 _lib = None
@@ -161,6 +163,7 @@ def load():
         "arn_hscene_build": (C.c_int, [vp, C.c_int]),
         "arn_hscene_desc": (C.POINTER(SceneDesc), [vp]),
         "arn_camera_make": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]),
+        "arn_ortho_camera_make": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]),
         "arn_save_png": (C.c_int, [C.c_char_p, vp, C.c_uint32, C.c_uint32]),
     }
     for name, (res, args) in sig.items():

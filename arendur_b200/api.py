@@ -41,13 +41,29 @@ def make_camera(parent_view, screen, znear, zfar, fov, res_x, res_y, lens=None):
     return cam
 
 
-def make_film(res_x, res_y, crop=None, filter_radius=(4.0, 4.0)):
+def make_film(res_x, res_y, crop=None, filter_radius=(4.0, 4.0), filter_kind=0, filter_a=0.0, filter_b=0.0):
+    """Film (filming/film.rs:38-45).  filter_kind 0 = the deserialised default Lanczos(tau 3); Film::new's other
+    filters (sample/filters.rs): L.ARN_FILTER_BOX / _TRIANGLE / _GAUSSIAN (filter_a = alpha) / _MITCHELL (b, c)."""
     f = L.Film()
     f.res_x, f.res_y = res_x, res_y
     c = crop or (0, 0, res_x, res_y)
     f.crop_min_x, f.crop_min_y, f.crop_max_x, f.crop_max_y = c
     f.filter_radius_x, f.filter_radius_y = filter_radius
+    f.filter_kind, f.filter_a, f.filter_b = filter_kind, filter_a, filter_b
     return f
+
+
+def make_ortho_camera(view_parent, screen, znear, zfar, res_x, res_y, lens=None):
+    """OrthoCam::new (filming/ortho.rs:30-55). `view_parent`: 4 COLUMNS; note the reference takes view_parent here."""
+    lib = L.load()
+    cam = L.Camera()
+    vpm = _f32(view_parent).reshape(16)
+    sc = _f32(screen).reshape(4)
+    rc = lib.arn_ortho_camera_make(_ptr(vpm), _ptr(sc), znear, zfar, 1 if lens else 0,
+                                   lens[0] if lens else 0.0, lens[1] if lens else 0.0, float(res_x), float(res_y), C.byref(cam))
+    if rc != 0:
+        raise ArnError(rc, lib.arn_hscene_last_error(None).decode())
+    return cam
 
 
 def make_sampler(sampledx, sampledy, ndim=8, seed=0):

@@ -498,7 +498,13 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
 
     WaveParams wp;
     std::memcpy(wp.raster_view, cam->raster_view, 64); std::memcpy(wp.view_parent, cam->view_parent, 64);
-    wp.has_lens = cam->has_lens; wp.lens_radius = cam->lens_radius; wp.focal_distance = cam->focal_distance;
+    wp.has_lens = cam->has_lens; wp.lens_radius = cam->lens_radius; wp.focal_distance = cam->focal_distance; wp.ortho = cam->ortho;
+    // the film's filter (sample/filters.rs): constructor asserts, then the per-axis parameters filter1 reads
+    if (film->filter_kind > ARN_FILTER_MITCHELL) return set_err(c, ARN_E_INVALID, "arn_render_pt: unknown film filter");
+    if (!(film->filter_radius_x > 0.f) || !(film->filter_radius_y > 0.f)) return set_err(c, ARN_E_INVALID, "arn_render_pt: filter radius must be positive (assert! in every Filter::new)");
+    wp.filt_kind = film->filter_kind; wp.filt_a = film->filter_a; wp.filt_b = film->filter_b;
+    if (film->filter_kind == ARN_FILTER_LANCZOS) wp.filt_a = 1.0f / (film->filter_a > 0.f ? film->filter_a : 3.0f);    // inv_tau (filters.rs:203-206)
+    if (film->filter_kind == ARN_FILTER_GAUSSIAN) wp.filt_a = -film->filter_a;                                           // neg_alpha (:104)
     wp.crop_x0 = film->crop_min_x; wp.crop_y0 = film->crop_min_y; wp.crop_w = cw; wp.crop_h = chh;
     wp.fr_x = film->filter_radius_x; wp.fr_y = film->filter_radius_y;
     wp.seed = smp->seed; wp.max_depth = prm->max_depth; wp.min_depth = prm->min_depth; wp.rr_threshold = prm->rr_threshold;

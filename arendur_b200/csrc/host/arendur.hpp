@@ -115,11 +115,29 @@ inline int load_obj(Components& out, const std::string& path, const Matrix4f& tr
     return out.check(arn_hscene_load_obj(out.raw(), path.c_str(), transform.data()));
 }
 
+// sample::filters::{BoxFilter, TriangleFilter, GaussianFilter, MitchellFilter, LanczosSincFilter}::new
+struct Filter {
+    uint32_t kind; Float rx, ry, a, b;
+    static Filter box(Float rx, Float ry) { return check({ARN_FILTER_BOX, rx, ry, 0.f, 0.f}); }
+    static Filter triangle(Float rx, Float ry) { return check({ARN_FILTER_TRIANGLE, rx, ry, 0.f, 0.f}); }
+    static Filter gaussian(Float alpha, Float rx, Float ry) { return check({ARN_FILTER_GAUSSIAN, rx, ry, alpha, 0.f}); }
+    static Filter mitchell(Float rx, Float ry, Float b, Float c) { return check({ARN_FILTER_MITCHELL, rx, ry, b, c}); }
+    static Filter lanczos(Float rx, Float ry, Float tau) { if (!(tau > 0.f)) throw Panic(ARN_E_INVALID, "assertion failed: tau > 0.0"); return check({ARN_FILTER_LANCZOS, rx, ry, tau, 0.f}); }
+private:
+    static Filter check(Filter f) { if (!(f.rx > 0.f) || !(f.ry > 0.f)) throw Panic(ARN_E_INVALID, "assertion failed: radius > 0.0"); return f; }
+};
+
 struct Film {                                              // filming/film.rs:38-45
     arn_film f;
+    // a deserialised film: Lanczos(tau 3) whatever the radius (film.rs:42,47-51)
     static Film make(uint32_t res_x, uint32_t res_y, Float filter_radius = 4.f) {
         Film x{}; x.f.res_x = res_x; x.f.res_y = res_y; x.f.crop_max_x = (int32_t)res_x; x.f.crop_max_y = (int32_t)res_y;
         x.f.filter_radius_x = x.f.filter_radius_y = filter_radius; return x;
+    }
+    // Film::new(resolution, crop_window = whole frame, filter) (film.rs:55-80)
+    static Film make(uint32_t res_x, uint32_t res_y, const Filter& filter) {
+        Film x = make(res_x, res_y); x.f.filter_radius_x = filter.rx; x.f.filter_radius_y = filter.ry;
+        x.f.filter_kind = filter.kind; x.f.filter_a = filter.a; x.f.filter_b = filter.b; return x;
     }
 };
 
@@ -130,6 +148,16 @@ struct PerspecCam {                                        // filming/perspectiv
         PerspecCam c{}; c.film = film;
         int rc = arn_camera_make(parent_view.data(), screen, znear, zfar, fov, lens ? 1 : 0, lens ? lens[0] : 0.f, lens ? lens[1] : 0.f, (Float)film.f.res_x, (Float)film.f.res_y, &c.cam);
         if (rc != ARN_OK) throw Panic(rc, arn_hscene_last_error(nullptr));     // "matrix inversion failure" / assert!(znear < zfar)
+        return c;
+    }
+};
+
+struct OrthoCam {                                          // filming/ortho.rs:19-28; the record PTRenderer takes is shared
+    // OrthoCam::new(view_parent, screen, znear, zfar, lens, film) — view_parent, unlike PerspecCam::new
+    static PerspecCam make(const Matrix4f& view_parent, const Float screen[4], Float znear, Float zfar, const Float* lens, const Film& film) {
+        PerspecCam c{}; c.film = film;
+        int rc = arn_ortho_camera_make(view_parent.data(), screen, znear, zfar, lens ? 1 : 0, lens ? lens[0] : 0.f, lens ? lens[1] : 0.f, (Float)film.f.res_x, (Float)film.f.res_y, &c.cam);
+        if (rc != ARN_OK) throw Panic(rc, arn_hscene_last_error(nullptr));
         return c;
     }
 };

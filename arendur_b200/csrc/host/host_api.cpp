@@ -250,7 +250,26 @@ int arn_camera_make(const float* parent_view16, const float* screen4, float znea
     if (!invert(view_screen, &inv_vs)) { g_host_error = "camera: matrix inversion failure"; return ARN_E_INVALID; }
     Mat4 raster_view = inv_vs * raster_screen;
     raster_view.to_array(out->raster_view); view_parent.to_array(out->view_parent);
-    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_radius; out->focal_distance = focal_distance;
+    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_radius; out->focal_distance = focal_distance; out->ortho = 0u;
+    return ARN_OK;
+}
+
+int arn_ortho_camera_make(const float* view_parent16, const float* screen4, float znear, float zfar, int has_lens,
+                          float lens_radius, float focal_distance, float res_x, float res_y, arn_camera* out) {
+    if (!view_parent16 || !screen4 || !out) return ARN_E_INVALID;
+    Mat4 view_parent = Mat4::from_array(view_parent16), parent_view;
+    if (!invert(view_parent, &parent_view)) { g_host_error = "camera transform: matrix inversion failure"; return ARN_E_INVALID; }   // ortho.rs:39
+    // OrthoCam::ortho_transform (ortho.rs:57-66): scale(1, 1, 1 / (zfar - znear)) * translation(0, 0, -znear)
+    Mat4 view_screen = Mat4::scale(1.f, 1.f, 1.f / (zfar - znear)) * Mat4::translation(0.f, 0.f, -znear);
+    // ProjCameraInfo::new (filming/projective.rs:24-45)
+    Mat4 raster_screen = Mat4::translation(screen4[0], screen4[3], 0.f)
+                       * Mat4::scale((screen4[2] - screen4[0]) / res_x, (screen4[1] - screen4[3]) / res_y, 1.f);
+    Mat4 tmp, inv_vs;
+    if (!invert(raster_screen, &tmp)) { g_host_error = "camera: raster_screen is singular"; return ARN_E_INVALID; }
+    if (!invert(view_screen, &inv_vs)) { g_host_error = "camera: matrix inversion failure"; return ARN_E_INVALID; }
+    Mat4 raster_view = inv_vs * raster_screen;
+    raster_view.to_array(out->raster_view); view_parent.to_array(out->view_parent);
+    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_radius; out->focal_distance = focal_distance; out->ortho = 1u;
     return ARN_OK;
 }
 
@@ -360,6 +379,7 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
     film->res_x = (uint32_t)res[0]; film->res_y = (uint32_t)res[1];
     film->crop_min_x = (int32_t)cmin[0]; film->crop_min_y = (int32_t)cmin[1]; film->crop_max_x = (int32_t)cmax[0]; film->crop_max_y = (int32_t)cmax[1];
     film->filter_radius_x = fr[0]; film->filter_radius_y = fr[1];
+    film->filter_kind = ARN_FILTER_LANCZOS; film->filter_a = 0.f; film->filter_b = 0.f;   // `filter` is skip_deserializing (film.rs:42,47-51)
     float screen4[4] = {smin[0], smin[1], smax[0], smax[1]};
     int rc = arn_camera_make(pv, screen4, znear, zfar, fov, has_lens, lens[0], lens[1], (float)film->res_x, (float)film->res_y, cam);
     if (rc != ARN_OK) return fs.fail(rc, g_host_error);

@@ -70,6 +70,8 @@ struct Queues {
 struct WaveParams {
     float raster_view[16], view_parent[16];
     uint32_t has_lens; float lens_radius, focal_distance;
+    uint32_t ortho;                      // OrthoCam (filming/ortho.rs)
+    uint32_t filt_kind; float filt_a, filt_b;   // film filter (see filter1)
     int crop_x0, crop_y0, crop_w, crop_h;
     float fr_x, fr_y;
     uint32_t seed;
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ 
         float2 plens = sm.next_2d();
         // PerspecCam::generate_path_differential, main ray
         float3 pview = xform_point(p.raster_view, f3(pfilm.x, pfilm.y, 0.f));
-        float3 o = f3(0.f, 0.f, 0.f), d = normalize(pview);
+        float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
+        if (p.ortho) o = pview; else d = normalize(pview);       // OrthoCam::generate_path (ortho.rs:180-198)
         if (p.has_lens) {
             float2 dl = sample_concentric_disk(plens);
             float2 pln = f2(p.lens_radius * dl.x, p.lens_radius * dl.y);
@@ -446,7 +449,22 @@ __global__ void k_begin_wave(Queues q, uint32_t n) { for (int i = 0; i < 16; i++
 // film filter weights feed sums only (no discrete decision): libdevice f32 sinf (<= 2 ulp) instead of the
 // correctly-rounded f64 route; covered by the film-sum tolerance of tests/test_gpu_parity.py
 ARN_DEV float sinc1(float x) { if (x < 1.0e-5f) return 1.f; float xpi = x * ARN_PI; return sinf(xpi) / xpi; }
-ARN_DEV float lanczos1(float x) { return sinc1(x * (1.f / 3.f)) * sinc1(x); }        // tau = 3 (film.rs:47-51)
+ARN_DEV float mitchell1(float x, float b, float c) {                                 // MitchellFilter::mitchell_1d (filters.rs:154-169)
+    const float INV_SIX = 1.0f / 6.0f;
+    if (x > 1.0f) return (-b - 6.0f * c) * x * x * x + (6.0f * b + 30.0f * c) * x * x - (12.0f * b + 48.0f * c) * x + (8.0f * b + 24.0f * c) * INV_SIX;
+    return (12.0f - 9.0f * b - 6.0f * c) * x * x * x + (-18.0f - 12.0f * b + 6.0f * c) * x * x + (6.0f - 2.0f * b) * INV_SIX;
+}
+// One axis of the film filter at signed offset x (every filter of sample/filters.rs is a product of two such
+// factors); r = that axis' radius.  Lanczos: p.filt_a = 1 / tau (film.rs:47-51: tau = 3 after deserialisation).
+ARN_DEV float filter1(const WaveParams& p, float x, float r) {
+    switch (p.filt_kind) {
+    case ARN_FILTER_BOX: return 1.f;
+    case ARN_FILTER_TRIANGLE: return r - fabsf(x);
+    case ARN_FILTER_GAUSSIAN: return expf(p.filt_a * x * x) - p.filt_a * r * r;       // filt_a = -alpha; sic (filters.rs:104-107,121-125)
+    case ARN_FILTER_MITCHELL: return mitchell1(fabsf(2.0f * ((1.0f / r) * x)), p.filt_a, p.filt_b);
+    default: return sinc1(x * p.filt_a) * sinc1(x);
+    }
+}
 
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
     unsigned long long invalid = 0;
@@ -465,9 +483,9 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant_
         // than the crop window does for samples inside the tile (DESIGN.md "Film")
         x0 = max(x0, p.crop_x0); y0 = max(y0, p.crop_y0); x1 = min(x1, p.crop_x0 + p.crop_w); y1 = min(y1, p.crop_y0 + p.crop_h);
         for (int y = y0; y < y1; y++) {
-            float wy = lanczos1(((float)y + 0.5f) - pos.y);
+            float wy = filter1(p, ((float)y + 0.5f) - pos.y, p.fr_y);
             for (int x = x0; x < x1; x++) {
-                float wx = lanczos1(((float)x + 0.5f) - pos.x);
+                float wx = filter1(p, ((float)x + 0.5f) - pos.x, p.fr_x);
                 float w = wx * wy;
                 float3 c = L * w;
                 atomicAdd(&film[(size_t)(y - p.crop_y0) * (size_t)p.crop_w + (size_t)(x - p.crop_x0)], make_float4(c.x, c.y, c.z, w));
@@ -510,8 +528,8 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
             if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
             if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
             float wv = 0.f;
-            if (lane < 9) wv = lanczos1(((float)(px - 4 + (int)lane) + 0.5f) - pos.x);
-            else if (lane < 18) wv = lanczos1(((float)(py - 4 + (int)lane - 9) + 0.5f) - pos.y);
+            if (lane < 9) wv = filter1(p, ((float)(px - 4 + (int)lane) + 0.5f) - pos.x, p.fr_x);
+            else if (lane < 18) wv = filter1(p, ((float)(py - 4 + (int)lane - 9) + 0.5f) - pos.y, p.fr_y);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 int t = (int)lane + 32 * j;

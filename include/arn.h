@@ -152,23 +152,33 @@ typedef struct arn_scene_desc {
     const arn_analytic_light* analytic_lights;
 } arn_scene_desc;
 
-/* `PerspecCam` (filming/perspective.rs:25-38) reduced to what ray generation reads
- * (perspective.rs:292-320): raster_view = inverse(view_screen) * raster_screen
- * (filming/projective.rs:29-37) and view_parent. */
+/* `PerspecCam` (filming/perspective.rs:25-38) or `OrthoCam` (filming/ortho.rs:19-28) reduced to
+ * what ray generation reads (perspective.rs:292-320, ortho.rs:180-198): raster_view =
+ * inverse(view_screen) * raster_screen (filming/projective.rs:29-37) and view_parent. */
 typedef struct arn_camera {
     float    raster_view[16];
     float    view_parent[16];
     uint32_t has_lens;
     float    lens_radius;
     float    focal_distance;
+    uint32_t ortho;              /* 0 PerspecCam, 1 OrthoCam (rays leave the raster point along +z) */
 } arn_camera;
 
-/* `Film` (filming/film.rs:38-45); the filter is always Lanczos(radius (4,4), tau 3)
- * after deserialisation (film.rs:42,47-51); filter_radius only sizes the splat box. */
+/* `Film` (filming/film.rs:38-45).  A deserialised film always filters with Lanczos(radius (4,4),
+ * tau 3) whatever the file says (film.rs:42,47-51) and `filter_radius` only sizes the splat box;
+ * `Film::new(resolution, crop, filter)` accepts any `Filter` of sample/filters.rs, selected here by
+ * filter_kind (0 = that default Lanczos, so a zero-initialised tail keeps the arencli behaviour). */
+#define ARN_FILTER_LANCZOS  0u   /* LanczosSincFilter (filters.rs:189-240): filter_a = tau, 0 = 3             */
+#define ARN_FILTER_BOX      1u   /* BoxFilter (:35-59)                                                        */
+#define ARN_FILTER_TRIANGLE 2u   /* TriangleFilter (:61-85): (rx - |x|) (ry - |y|)                            */
+#define ARN_FILTER_GAUSSIAN 3u   /* GaussianFilter (:87-127): filter_a = alpha; sic: subtracts -alpha r^2     */
+#define ARN_FILTER_MITCHELL 4u   /* MitchellFilter (:129-187): filter_a = b, filter_b = c                     */
 typedef struct arn_film {
     uint32_t res_x, res_y;
     int32_t  crop_min_x, crop_min_y, crop_max_x, crop_max_y;  /* pixels, max exclusive */
-    float    filter_radius_x, filter_radius_y;
+    float    filter_radius_x, filter_radius_y;   /* Film.filter_radius: the splat box AND the filter's own radius */
+    uint32_t filter_kind;
+    float    filter_a, filter_b;
 } arn_film;
 
 /* Sampler: `StrataSampler{sampledx, sampledy, ndim}` (sample/strata.rs:25-31) gives the

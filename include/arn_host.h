@@ -85,6 +85,12 @@ int arn_camera_make(const float* parent_view16, const float* screen4, float znea
                     float fov, int has_lens, float lens_radius, float focal_distance,
                     float res_x, float res_y, arn_camera* out);
 
+/* OrthoCam::new(view_parent, screen, znear, zfar, lens, film) (filming/ortho.rs:30-67).  Note the
+ * reference's argument is view_parent here (PerspecCam::new takes parent_view). */
+int arn_ortho_camera_make(const float* view_parent16, const float* screen4, float znear, float zfar,
+                          int has_lens, float lens_radius, float focal_distance,
+                          float res_x, float res_y, arn_camera* out);
+
 /* Image::save (filming/film.rs:380-391): finalize + 8-bit RGB PNG, no gamma. */
 int arn_save_png(const char* path, const float* film, uint32_t width, uint32_t height);
 

@@ -96,6 +96,10 @@ int arn_oracle_camera_make(const float* parent_view16, const float* screen4, flo
                            int has_lens, float lens_radius, float focal_distance, float res_x, float res_y, arn_camera* out) {
     return camera_make(parent_view16, screen4, znear, zfar, fov, has_lens, lens_radius, focal_distance, res_x, res_y, out) ? ARN_OK : ARN_E_INVALID;
 }
+int arn_oracle_ortho_camera_make(const float* view_parent16, const float* screen4, float znear, float zfar,
+                                 int has_lens, float lens_radius, float focal_distance, float res_x, float res_y, arn_camera* out) {
+    return ortho_camera_make(view_parent16, screen4, znear, zfar, has_lens, lens_radius, focal_distance, res_x, res_y, out) ? ARN_OK : ARN_E_INVALID;
+}
 // Camera rays for a list of film positions (pfilm.xy, plens.xy per ray): PerspecCam::generate_path
 int arn_oracle_camera_rays(const arn_camera* cam, const float* pfilm_plens4, size_t n, arn_ray* out) {
     for (size_t i = 0; i < n; i++) {
@@ -208,6 +212,8 @@ int arn_oracle_sampler_draws(uint32_t seed, uint32_t px, uint32_t py, uint32_t s
     return ARN_OK;
 }
 float arn_oracle_lanczos(float dx, float dy) { return lanczos_evaluate(v2(dx, dy), 1.f / 3.f); }
+// Filter::evaluate_unsafe of the film's filter at a signed offset (sample/filters.rs)
+float arn_oracle_filter(const arn_film* film, float dx, float dy) { return filter_evaluate(*film, v2(dx, dy)); }
 float arn_oracle_roughness_to_alpha(float r) { return roughness_to_alpha(r); }
 
 // BSDF probe for kernel-level parity: evaluate_sampled / evaluate / pdf of a material at a fixed

@@ -35,15 +35,32 @@ inline bool camera_make(const Float* parent_view16, const Float screen[4] /*pmin
     M4 raster_view = m4_mul(inv_vs, raster_screen);
     std::memcpy(out->raster_view, raster_view.m, 64);
     std::memcpy(out->view_parent, view_parent.m, 64);
-    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_r; out->focal_distance = lens_d;
+    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_r; out->focal_distance = lens_d; out->ortho = 0u;
+    return true;
+}
+// OrthoCam::new (filming/ortho.rs:30-55) with ortho_transform (:57-66)
+inline bool ortho_camera_make(const Float* view_parent16, const Float screen[4], Float znear, Float zfar,
+                              int has_lens, Float lens_r, Float lens_d, Float res_x, Float res_y, arn_camera* out) {
+    M4 view_parent = m4_from_cols(view_parent16);
+    M4 parent_view; if (!m4_invert(view_parent, &parent_view)) return false;
+    M4 view_screen = m4_mul(m4_from_nonuniform_scale(1.f, 1.f, 1.f / (zfar - znear)), m4_from_translation(v3(0.f, 0.f, -znear)));
+    M4 raster_screen = m4_mul(m4_from_translation(v3(screen[0], screen[3], 0.f)),
+                              m4_from_nonuniform_scale((screen[2] - screen[0]) / res_x, (screen[1] - screen[3]) / res_y, 1.f));
+    M4 inv_vs; if (!m4_invert(view_screen, &inv_vs)) return false;
+    M4 screen_raster; if (!m4_invert(raster_screen, &screen_raster)) return false;
+    M4 raster_view = m4_mul(inv_vs, raster_screen);
+    std::memcpy(out->raster_view, raster_view.m, 64);
+    std::memcpy(out->view_parent, view_parent.m, 64);
+    out->has_lens = has_lens ? 1u : 0u; out->lens_radius = lens_r; out->focal_distance = lens_d; out->ortho = 1u;
     return true;
 }
 // PerspecCam::generate_path_differential (perspective.rs:292-320), main ray only
 inline RawRay camera_generate(const arn_camera& cam, V2 pfilm, V2 plens) {
     M4 rv = m4_from_cols(cam.raster_view), vp = m4_from_cols(cam.view_parent);
     V3 pview = transform_point(rv, v3(pfilm.x, pfilm.y, 0.f));
-    RawRay ray = ray_from_od(v3(0.f, 0.f, 0.f), normalize(pview));
-    if (cam.has_lens) {
+    RawRay ray = cam.ortho ? ray_from_od(pview, v3(0.f, 0.f, 1.f))                 // OrthoCam::generate_path (ortho.rs:180-198)
+                           : ray_from_od(v3(0.f, 0.f, 0.f), normalize(pview));
+    if (cam.has_lens) {                                                            // same lines in both cameras (sic for ortho: the origin forgets pview)
         V2 pl = cam.lens_radius * sample_concentric_disk(plens);
         Float ft = cam.focal_distance / ray.dir.z;
         V3 pfocus = ray_evaluate(ray, ft);
@@ -328,7 +345,7 @@ inline void tile_add_sample(FilmTile& t, const arn_film& film, V2 pos, RGB spect
     for (long y = rb.y0; y < rb.y1; y++) for (long x = rb.x0; x < rb.x1; x++) {     // row-major iteration, bbox.rs:603-620
         V2 pixel_pos = v2((Float)x + 0.5f, (Float)y + 0.5f);                         // pidx_to_pcenter :23-28
         V2 offset = pixel_pos - pos;
-        Float weight = lanczos_evaluate(offset, 1.f / 3.f);
+        Float weight = filter_evaluate(film, offset);
         Float* p = &t.px[((size_t)(x - t.sink.x0) + (size_t)(y - t.sink.y0) * (size_t)sw) * 4];
         RGB c = spectrum * weight;
         p[0] += c.x; p[1] += c.y; p[2] += c.z; p[3] += weight;

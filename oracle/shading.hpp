@@ -88,6 +88,39 @@ inline void distribution_new(const Float* func, uint32_t n, Float* cdf, Float* i
 inline Float lanczos_sinc1(Float x) { if (x < 1.0e-5f) return 1.f; Float xpi = x * pi(); return fsin(xpi) / xpi; }
 inline Float lanczos_sinc(Float x, Float inv_tau) { return lanczos_sinc1(x * inv_tau) * lanczos_sinc1(x); }
 inline Float lanczos_evaluate(V2 p, Float inv_tau) { return lanczos_sinc(p.x, inv_tau) * lanczos_sinc(p.y, inv_tau); }
+// MitchellFilter::mitchell_1d (filters.rs:154-169)
+inline Float mitchell_1d(Float x, Float b, Float c) {
+    const Float INV_SIX = 1.0f / 6.0f;
+    if (x > 1.0f) {
+        return (-b - 6.0f * c) * x * x * x + (6.0f * b + 30.0f * c) * x * x - (12.0f * b + 48.0f * c) * x + (8.0f * b + 24.0f * c) * INV_SIX;
+    } else {
+        return (12.0f - 9.0f * b - 6.0f * c) * x * x * x + (-18.0f - 12.0f * b + 6.0f * c) * x * x + (6.0f - 2.0f * b) * INV_SIX;
+    }
+}
+// Filter::evaluate_unsafe of the film's filter (sample/filters.rs), `p` = pixel centre - sample position (signed)
+inline Float filter_evaluate(const arn_film& film, V2 p) {
+    Float rx = film.filter_radius_x, ry = film.filter_radius_y;
+    switch (film.filter_kind) {
+    case ARN_FILTER_BOX: return 1.0f;                                                              // :55-57
+    case ARN_FILTER_TRIANGLE: return (rx - std::fabs(p.x)) * (ry - std::fabs(p.y));                // :81-83
+    case ARN_FILTER_GAUSSIAN: {                                                                    // :101-126
+        Float neg_alpha = -film.filter_a;
+        Float ex = neg_alpha * rx * rx, ey = neg_alpha * ry * ry;                                  // sic: the exponent, not its exponential
+        Float gx = fexp(neg_alpha * p.x * p.x) - ex;
+        Float gy = fexp(neg_alpha * p.y * p.y) - ey;
+        return gx * gy;
+    }
+    case ARN_FILTER_MITCHELL: {                                                                    // :140-186
+        Float ix = 1.0f / rx, iy = 1.0f / ry;
+        Float mx = 2.0f * (ix * p.x), my = 2.0f * (iy * p.y);
+        return mitchell_1d(std::fabs(mx), film.filter_a, film.filter_b) * mitchell_1d(std::fabs(my), film.filter_a, film.filter_b);
+    }
+    default: {                                                                                     // :189-240
+        Float tau = film.filter_a > 0.f ? film.filter_a : 3.0f;
+        return lanczos_evaluate(p, 1.0f / tau);
+    }
+    }
+}
 
 // ------------------------------------------------------------------ BxDFs
 enum { BXDF_REFLECTION = 0x01, BXDF_TRANSMISSION = 0x02, BXDF_DIFFUSE = 0x04, BXDF_GLOSSY = 0x08,

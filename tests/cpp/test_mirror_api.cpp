@@ -70,6 +70,14 @@ static void test_render_analytic_lights(Device& dev) {
     arn_stats st;
     const std::vector<Float>& film = r.render(scene, &st);
     assert(st.shadow_rays > 0 && st.mis_rays == 0 && st.invalid_samples == 0);
+    // OrthoCam + Film::new with a Mitchell filter
+    PerspecCam ocam = OrthoCam::make(identity(), screen, 0.1f, 1000.f, nullptr, Film::make(32, 32, Filter::mitchell(2.f, 2.f, 1.f / 3.f, 1.f / 3.f)));
+    PTRenderer r2(StrataSampler::make(1, 1, 8), ocam, "", 2, true);
+    const std::vector<Float>& film2 = r2.render(scene, &st);
+    assert(st.camera_rays == 32 * 32 && film2.size() == 32 * 32 * 4);
+    threw = false;
+    try { Filter::box(0.f, 1.f); } catch (const Panic&) { threw = true; }                                   // assert!(radius.x > 0.0)
+    assert(threw);
     double lum = 0; for (size_t i = 0; i < film.size(); i += 4) if (film[i + 3] != 0.f) lum += film[i] / film[i + 3];
     assert(lum > 0.0);
 }

@@ -165,6 +165,26 @@ def camera_make(parent_view, screen, znear, zfar, fov, res_x, res_y, lens=None):
     return cam
 
 
+def ortho_camera_make(view_parent, screen, znear, zfar, res_x, res_y, lens=None):
+    lib = load()
+    cam = L.Camera()
+    vpm = np.ascontiguousarray(view_parent, np.float32).reshape(16)
+    sc = np.ascontiguousarray(screen, np.float32).reshape(4)
+    lib.arn_oracle_ortho_camera_make.restype = C.c_int
+    lib.arn_oracle_ortho_camera_make.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(L.Camera)]
+    rc = lib.arn_oracle_ortho_camera_make(_p(vpm), _p(sc), znear, zfar, 1 if lens else 0, lens[0] if lens else 0.0,
+                                          lens[1] if lens else 0.0, float(res_x), float(res_y), C.byref(cam))
+    assert rc == 0
+    return cam
+
+
+def filter_eval(film, dx, dy):
+    lib = load()
+    lib.arn_oracle_filter.restype = C.c_float
+    lib.arn_oracle_filter.argtypes = [C.POINTER(L.Film), C.c_float, C.c_float]
+    return lib.arn_oracle_filter(C.byref(film), dx, dy)
+
+
 def camera_rays(cam, pfilm_plens):
     from arendur_b200.api import RAY_DTYPE
     lib = load()
