@@ -334,3 +334,33 @@ def test_material_zoo_bit_exact(ctx, lens):
     assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
     assert (orad[..., :3].max(-1) > 0).mean() > 0.2
     sc.close(); osc.close()
+
+
+def test_c2_full_size_bit_exact(ctx):
+    """BASELINE C2 at its full size: 1 002 528-triangle height field (1 537 561 BVH nodes), 1920x1080 pixel-centre
+    rays.  Every (prim id, t) equals the oracle's bit for bit, through the 4-wide walk (what `auto` picks for a tree
+    this size) and through the binary walk; any-hit == closest-hit existence; clipping tmax just below the hit
+    distance turns every hit into a miss (size-independent properties)."""
+    import torch
+    hs, cam, film = scenes.c2_heightfield_scene()
+    d = hs.desc()
+    assert d.n_triangles == 1_002_528
+    w, h = film.res_x, film.res_y
+    xs, ys = np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5, indexing="xy")
+    pf = np.zeros((w * h, 4), np.float32); pf[:, 0], pf[:, 1] = xs.reshape(-1), ys.reshape(-1)
+    rays = O.camera_rays(cam, pf)
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    oh = osc.intersect_closest(rays)
+    assert (oh["prim_id"] >= 0).sum() > 250_000          # the field covers 14 % of the 90-degree frame (SURVEY §8(d) C2)
+    for width in (0, 4, 2):
+        ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)
+        _assert_hits_equal(sc.intersect_closest(rays), oh)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
+    assert np.array_equal(sc.intersect_any(rays) != 0, oh["prim_id"] >= 0)
+    hit = oh["prim_id"] >= 0
+    clipped = rays[hit].copy(); clipped["tmax"] = np.nextafter(oh["t"][hit], np.float32(0))
+    # the accepted t must be < tmax (strict), so a ray that ends just before its hit sees nothing nearer
+    gh = sc.intersect_closest(clipped)
+    assert np.all((gh["prim_id"] < 0) | (gh["t"] < clipped["tmax"]))
+    assert (gh["prim_id"] < 0).mean() > 0.99
+    sc.close(); osc.close()
