@@ -104,13 +104,13 @@ ARN_H_SYMBOLS = [
     "arn_bvh_build", "arn_light_distribution", "arn_film_finalize", "arn_ctx_create", "arn_ctx_destroy",
     "arn_last_error", "arn_scene_upload", "arn_scene_destroy", "arn_intersect_closest", "arn_intersect_any",
     "arn_intersect_closest_dev", "arn_intersect_any_dev", "arn_intersect_closest_counted_dev",
-    "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_set_option", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
+    "arn_bvh_build_gpu", "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_set_option", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
     "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_spot_light_make", "arn_point_light_make",
     "arn_distant_light_make", "arn_hscene_load_obj", "arn_hscene_load_json",
-    "arn_hscene_build", "arn_hscene_desc", "arn_camera_make", "arn_ortho_camera_make", "arn_save_png",
+    "arn_hscene_build", "arn_hscene_build_gpu", "arn_hscene_desc", "arn_camera_make", "arn_ortho_camera_make", "arn_save_png",
 ]
 
 _lib = None
@@ -161,6 +161,8 @@ def load():
         "arn_hscene_load_obj": (C.c_int, [vp, C.c_char_p, vp]),
         "arn_hscene_load_json": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Camera), C.POINTER(Film), C.POINTER(Sampler), C.POINTER(PTParams), C.c_char_p, C.c_size_t]),
         "arn_hscene_build": (C.c_int, [vp, C.c_int]),
+        "arn_hscene_build_gpu": (C.c_int, [vp, vp, C.POINTER(C.c_float)]),
+        "arn_bvh_build_gpu": (C.c_int, [vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),
         "arn_hscene_desc": (C.POINTER(SceneDesc), [vp]),
         "arn_camera_make": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]),
         "arn_ortho_camera_make": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]),

@@ -154,6 +154,12 @@ class HostScene:
         self._check(self.lib.arn_hscene_build(self.h, strategy))
         return self.desc()
 
+    def build_gpu(self, ctx):
+        """BVH built on the device (arn_bvh_build_gpu: LBVH, not the reference's topology). Returns (desc, build ms)."""
+        ms = C.c_float(0.0)
+        self._check(self.lib.arn_hscene_build_gpu(self.h, ctx.c, C.byref(ms)))
+        return self.desc(), ms.value
+
     def desc(self):
         d = self.lib.arn_hscene_desc(self.h)
         if not d:

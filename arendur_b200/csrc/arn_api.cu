@@ -12,6 +12,8 @@
 #include <vector>
 #include "../../include/arn.h"
 #include "kernels/wavefront.cuh"
+#include "kernels/lbvh.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace arn;
 
@@ -447,6 +449,60 @@ int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     counters_out[0] = h[0]; counters_out[1] = h[1]; counters_out[2] = h[2];
     if (std::getenv("ARN_PROBE")) std::fprintf(stderr, "[arn probe] nodes %llu, sum of per-warp max %llu -> lane utilisation %.3f\n", h[0], h[3], (double)h[0] / (32.0 * (double)h[3]));
+    return ARN_OK;
+}
+
+// ---------------------------------------------------------------- device BVH build (kernels/lbvh.cuh)
+int arn_bvh_build_gpu(arn_ctx* c, uint32_t n, const float* bounds6, arn_node* nodes_out, uint32_t* order_out, uint32_t* n_nodes_out, float* build_ms_out) {
+    if (!c || !bounds6 || !nodes_out || !order_out || !n_nodes_out) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: NULL argument");
+    if (n == 0) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: no components (recursive_build asserts len != 0)");
+    if (n >= 0x40000000u) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: too many components");
+    std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    const size_t total = 2 * (size_t)n - 1;
+    std::vector<void*> allocs;
+    auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+    auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+    float* d_bounds = (float*)dalloc((size_t)n * 24);
+    unsigned long long* d_keys = (unsigned long long*)dalloc((size_t)n * 8); unsigned long long* d_keys2 = (unsigned long long*)dalloc((size_t)n * 8);
+    uint32_t* d_vals = (uint32_t*)dalloc((size_t)n * 4); uint32_t* d_vals2 = (uint32_t*)dalloc((size_t)n * 4);
+    int* d_cb = (int*)dalloc(32);
+    uint32_t* d_left = (uint32_t*)dalloc((size_t)n * 4); uint32_t* d_right = (uint32_t*)dalloc((size_t)n * 4);
+    uint32_t* d_axis = (uint32_t*)dalloc((size_t)n * 4); uint32_t* d_flag = (uint32_t*)dalloc((size_t)n * 4);
+    uint32_t* d_parent = (uint32_t*)dalloc(total * 4); uint32_t* d_size = (uint32_t*)dalloc(total * 4);
+    float* d_bb = (float*)dalloc(total * 24);
+    arn_node* d_nodes = (arn_node*)dalloc(total * sizeof(arn_node));
+    uint32_t* d_order = (uint32_t*)dalloc((size_t)n * 4);
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, c->stream);
+    void* d_temp = dalloc(temp_bytes);
+    if (!d_bounds || !d_keys || !d_keys2 || !d_vals || !d_vals2 || !d_cb || !d_left || !d_right || !d_axis || !d_flag || !d_parent || !d_size || !d_bb || !d_nodes || !d_order || !d_temp) {
+        cleanup(); cudaGetLastError(); return set_err(c, ARN_E_CUDA, "arn_bvh_build_gpu: out of device memory");
+    }
+    auto fail = [&](cudaError_t e, const char* what) { cleanup(); return set_err(c, ARN_E_CUDA, std::string("arn_bvh_build_gpu: ") + what + ": " + cudaGetErrorString(e)); };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_bounds, bounds6, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "bounds upload");
+    cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
+    cudaEventRecord(e0, c->stream);
+    LbvhBuf b; b.bounds = d_bounds; b.keys = d_keys; b.vals = d_vals; b.cbounds = d_cb; b.left = d_left; b.right = d_right; b.parent = d_parent;
+    b.size = d_size; b.axis = d_axis; b.flag = d_flag; b.bb = d_bb; b.n = n;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int grid = (int)std::min<size_t>((size_t)sms * 8, (total + 255) / 256);
+    k_lbvh_init<<<1, 32, 0, c->stream>>>(b);
+    k_lbvh_bounds<<<grid, 256, 0, c->stream>>>(b);
+    k_lbvh_keys<<<grid, 256, 0, c->stream>>>(b);
+    if ((e = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, c->stream)) != cudaSuccess) return fail(e, "radix sort");
+    b.keys = d_keys2; b.vals = d_vals2;
+    k_lbvh_hierarchy<<<grid, 256, 0, c->stream>>>(b, d_keys2);
+    k_lbvh_refit<<<grid, 256, 0, c->stream>>>(b);
+    k_lbvh_emit<<<grid, 256, 0, c->stream>>>(b, d_nodes, d_order);
+    cudaEventRecord(e1, c->stream);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "kernel launch");
+    if ((e = cudaMemcpyAsync(nodes_out, d_nodes, total * sizeof(arn_node), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e, "node download");
+    if ((e = cudaMemcpyAsync(order_out, d_order, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e, "order download");
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "build");
+    if (build_ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *build_ms_out = ms; }
+    *n_nodes_out = (uint32_t)total;
+    cleanup();
     return ARN_OK;
 }
 

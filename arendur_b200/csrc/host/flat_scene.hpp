@@ -159,15 +159,19 @@ public:
         }
     }
 
-    int build(int strategy) {
+    float last_build_ms = 0.f;       // device time of the last GPU build
+    // BVH::new + Scene::new.  `gpu` != NULL: the tree comes from arn_bvh_build_gpu (LBVH, not the reference's
+    // topology) instead of the reference's host builder.
+    int build(int strategy, arn_ctx* gpu = nullptr) {
         uint32_t n = (uint32_t)prims.size();
         if (n == 0) return fail(ARN_E_INVALID, "scene has no components");
         std::vector<float> b6((size_t)n * 6), cost(n);
         for (uint32_t i = 0; i < n; i++) component_bounds(i, &b6[(size_t)i * 6], &cost[i]);
         nodes.resize(2 * (size_t)n); order.resize(n);
         uint32_t nn = 0;
-        int rc = arn_bvh_build(n, b6.data(), cost.data(), strategy, nodes.data(), order.data(), &nn);
-        if (rc != ARN_OK) return fail(rc, "arn_bvh_build failed");
+        int rc = gpu ? arn_bvh_build_gpu(gpu, n, b6.data(), nodes.data(), order.data(), &nn, &last_build_ms)
+                     : arn_bvh_build(n, b6.data(), cost.data(), strategy, nodes.data(), order.data(), &nn);
+        if (rc != ARN_OK) return fail(rc, gpu ? std::string("arn_bvh_build_gpu failed: ") + arn_last_error(gpu) : std::string("arn_bvh_build failed"));
         nodes.resize(nn);
         // Scene::new: power().to_xyz().y per light (renderer/scene.rs:36-41, component/shape.rs:160-167)
         light_func.clear(); light_list.clear();

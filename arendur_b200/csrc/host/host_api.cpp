@@ -228,6 +228,12 @@ int arn_hscene_load_obj(arn_hscene* h, const char* path, const float* transform1
     return rc;
 }
 int arn_hscene_build(arn_hscene* h, int strategy) { if (!h) return ARN_E_INVALID; return h->fs.build(strategy); }
+int arn_hscene_build_gpu(arn_hscene* h, arn_ctx* ctx, float* build_ms_out) {
+    if (!h || !ctx) return ARN_E_INVALID;
+    int rc = h->fs.build(ARN_BVH_SAH, ctx);
+    if (rc == ARN_OK && build_ms_out) *build_ms_out = h->fs.last_build_ms;
+    return rc;
+}
 const arn_scene_desc* arn_hscene_desc(const arn_hscene* h) { return (h && h->fs.built) ? &h->fs.desc : nullptr; }
 
 int arn_camera_make(const float* parent_view16, const float* screen4, float znear, float zfar, float fov, int has_lens,

@@ -146,7 +146,7 @@ def cornell_scene(res_x=256, res_y=256, sampledx=4, sampledy=4, seed=0, fixture=
 
 
 # ---------------------------------------------------------------- C4
-def c4_box_scene(cells=1291, seed=0x5EED, res=1024, sampledx=4, sampledy=4):
+def c4_box_scene(cells=1291, seed=0x5EED, res=1024, sampledx=4, sampledy=4, build=True):
     """closed box [-4,4]^3 of six noise-displaced height-field walls
     (6 * 2 * cells^2 triangles), Lambertian kd 0.7, the two emissive spheres of cb.json inside."""
     hs = api.HostScene()
@@ -168,7 +168,8 @@ def c4_box_scene(cells=1291, seed=0x5EED, res=1024, sampledx=4, sampledy=4):
         m = np.eye(4, dtype=np.float32); m[3, 0:3] = (x, y, z); return m     # rows = columns (translation in column w)
     hs.add_sphere(1.5, -2.0, 2.0, 6.28, lightm, emission=(15.5, 10.5, 5.5), transform=tr(-1.5, 0.0, 1.0))
     hs.add_sphere(1.5, -2.0, 2.0, 6.28, lightm, emission=(7.5, 7.5, 10.5), transform=tr(1.5, 1.5, -1.0))
-    hs.build()
+    if build:
+        hs.build()          # build=False: the caller builds (HostScene.build_gpu)
     view = np.eye(4, dtype=np.float32); view[3, 0:3] = (0.0, 0.0, 3.5)      # camera at z = -3.5 looking +z
     cam = api.make_camera(view, (-1.0, -1.0, 1.0, 1.0), 0.1, 1000.0, 1.2707964, res, res)
     film = api.make_film(res, res)

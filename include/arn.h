@@ -258,6 +258,16 @@ int  arn_ctx_create(int device, arn_ctx** out);
 void arn_ctx_destroy(arn_ctx* ctx);
 const char* arn_last_error(const arn_ctx* ctx);   /* ctx may be NULL: last global error */
 
+/* Device BVH build: a linear BVH (63-bit Morton order, Karras hierarchy, bottom-up
+ * bounds) over the same component bounds, emitted in the same pre-order 32-byte node layout and ordered
+ * component list as arn_bvh_build (`LinearNode`, component/bvh.rs:136-146,219-243), for scenes where the
+ * host build of the reference's SAH tree (seconds at 10^7 triangles) dominates start-up.  The topology is
+ * NOT the reference's: hits agree except where primitives tie in t or a transformed-sphere hit rewrote the
+ * ray earlier in a different visiting order.  bounds6 / nodes_out / order_out are HOST buffers
+ * (2n-1 nodes, n entries); build_ms_out (may be NULL) = device time of the build without the copies. */
+int arn_bvh_build_gpu(arn_ctx* ctx, uint32_t n, const float* bounds6, arn_node* nodes_out,
+                      uint32_t* order_out, uint32_t* n_nodes_out, float* build_ms_out);
+
 /* Upload a flattened scene (copies; desc buffers may be freed afterwards).
  * The handle is immutable and may be used from any host thread. */
 int  arn_scene_upload(arn_ctx* ctx, const arn_scene_desc* desc, arn_scene** out);

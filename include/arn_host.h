@@ -75,6 +75,10 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
 /* BVH::new(&components, strategy) + Scene::new(lights, bvh) (component/bvh.rs:58-79,
  * renderer/scene.rs:31-51).  After this the description is complete. */
 int arn_hscene_build(arn_hscene* h, int strategy);
+/* The same with the tree built on the device by arn_bvh_build_gpu (include/arn.h): start-up in
+ * milliseconds instead of seconds at 10^7 triangles, at the price of the reference's topology
+ * (tie-breaks may differ).  build_ms_out may be NULL. */
+int arn_hscene_build_gpu(arn_hscene* h, arn_ctx* ctx, float* build_ms_out);
 
 /* The flattened description; pointers stay valid until the hscene is modified or destroyed. */
 const arn_scene_desc* arn_hscene_desc(const arn_hscene* h);

@@ -8,14 +8,23 @@ from arendur_b200 import api, scenes, _lib as L
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 1291
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 sx = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+gpu_build = os.environ.get("C4_GPU_BUILD") == "1"     # tree from arn_bvh_build_gpu instead of the reference's host SAH build
 t = time.time()
-hs, cam, film, smp, prm = scenes.c4_box_scene(cells=cells, res=res, sampledx=sx, sampledy=sx)
-d = hs.desc()
-print(f"c4 cells={cells}: {d.n_triangles} triangles, {d.n_nodes} nodes, build+flatten {time.time()-t:.1f} s", flush=True)
+hs, cam, film, smp, prm = scenes.c4_box_scene(cells=cells, res=res, sampledx=sx, sampledy=sx, build=not gpu_build)
+if gpu_build:
+    t1 = time.time()
+    ctx0 = api.Context(0)
+    t2 = time.time()
+    d, ms = hs.build_gpu(ctx0)
+    print(f"c4 cells={cells}: {d.n_triangles} triangles, {d.n_nodes} nodes; mesh generation {t1-t:.1f} s, GPU LBVH build {ms:.1f} ms on the device, "
+          f"{time.time()-t2:.2f} s incl. bounds, copies and light table", flush=True)
+else:
+    d = hs.desc()
+    print(f"c4 cells={cells}: {d.n_triangles} triangles, {d.n_nodes} nodes, build+flatten {time.time()-t:.1f} s", flush=True)
 import torch
 if not torch.cuda.is_available():
     sys.exit(0)
-ctx = api.Context(0)
+ctx = ctx0 if gpu_build else api.Context(0)
 t = time.time(); sc = ctx.upload(d); print(f"upload {time.time()-t:.1f} s")
 for rep in range(2):
     f, st = sc.render_pt(cam, film, smp, prm)
