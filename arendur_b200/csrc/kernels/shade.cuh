@@ -409,6 +409,82 @@ ARN_NOINL float3 lobe_eval(const Lobe& x, float3 wo, float3 wi) {
     default: return as_eval<false>(x, wo, wi);
     }
 }
+// lobe_eval + lobe_pdf of ONE lobe for the same (wo, wi) in one call: the half vector, D(wh) and Lambda(wo) the two
+// share are computed once.  Every value is produced by the same expression as in lobe_eval / lobe_pdf, so the
+// results are bit-identical to calling them separately (D is even in wh: its inputs are squares of wh's components).
+// `want_f` = false skips the value (Bsdf::evaluate only adds lobes on the matching side, bsdf.rs:82-98).
+template <bool BECK> ARN_DEV void as_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, float3& f, float& pdf) {
+    float3 whs = wo + wi;
+    float3 wh = normalize(whs);
+    const bool need_pdf = !(wo.z * wi.z < 0.f);
+    const bool need_f = want_f && !relative_eq(length2(whs), 0.f);
+    float D = 0.f;
+    if (need_pdf || need_f) D = dist_D<BECK>(x.alpha, x.alpha, wh);
+    pdf = 0.f; f = grey(0.f);
+    if (need_pdf) {
+        float dp = D * dist_visible<BECK>(x.alpha, x.alpha, wo) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo));
+        pdf = 0.5f * (dp / (4.f * dot(wo, wh)) + fabsf(cos_theta(wi)) * ARN_INV_PI);
+    }
+    if (need_f) {
+        float to = 1.f - powi5(1.f - 0.5f * fabsf(cos_theta(wo)));
+        float ti = 1.f - powi5(1.f - 0.5f * fabsf(cos_theta(wi)));
+        float3 diffuse = (28.f / (23.f * ARN_PI)) * x.a * (grey(1.f) - x.b) * to * ti;
+        float cost = dot(wi, wh);
+        float3 schlick = x.b + powi5(1.f - cost) * (grey(1.f) - x.b);
+        float3 specular = D * schlick / (4.f * fabsf(dot(wi, wh)) * fmaxf(fabsf(cos_theta(wi)), fabsf(cos_theta(wo))));
+        f = diffuse + specular;
+    }
+}
+ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, float3& f, float& pdf) {
+    switch (x.kind) {
+    case LOBE_TS_R: {
+        float3 wh = normalize(wo + wi);
+        const bool need_pdf = !(wo.z * wi.z <= 0.f);
+        const bool need_f = want_f && !any_nan(wh);
+        pdf = 0.f; f = grey(0.f);
+        if (!(need_pdf || need_f)) return;
+        float D = dist_D<false>(x.alpha, x.alpha, wh);
+        float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
+        if (need_pdf) pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) / (4.f * dot(wo, wh));
+        if (need_f) {
+            float li = dist_lambda<false>(x.alpha, x.alpha, wi);
+            f = x.a * D * (1.f / (1.f + lo + li)) * grey(fresnel_dielectric(dot(wi, wh), x.c0, x.c1)) / (4.f * fabsf(wo.z) * fabsf(wi.z));
+        }
+        return;
+    }
+    case LOBE_TS_T: {
+        pdf = 0.f; f = grey(0.f);
+        if (wo.z * wi.z > 0.f) return;
+        float eta = wo.z > 0.f ? x.c1 / x.c0 : x.c0 / x.c1;
+        float3 wh = normalize(wo + wi * eta);
+        if (any_inf(wh) || any_nan(wh)) { pdf = 1.f; if (want_f) f = grey(1.f); return; }
+        float D = dist_D<false>(x.alpha, x.alpha, wh);
+        float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
+        {
+            float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+            float dhdi = eta * eta * fabsf(dot(wi, wh)) / (sqrt_denom * sqrt_denom);
+            pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) * dhdi;
+        }
+        if (want_f) {
+            if (wh.z < 0.f) wh = -wh;
+            float cosoh = dot(wo, wh);
+            float3 fr = grey(fresnel_dielectric(cosoh, x.c0, x.c1));
+            float cosih = dot(wi, wh);
+            float sqrt_denom = cosoh + eta * cosih;
+            float li = dist_lambda<false>(x.alpha, x.alpha, wi);
+            f = x.a * D * (1.f / (1.f + lo + li)) * (grey(1.f) - fr) * fabsf(cosih) * fabsf(cosoh)
+              / (fabsf(cos_theta(wo)) * fabsf(cos_theta(wi)) * sqrt_denom * sqrt_denom);
+        }
+        return;
+    }
+    case LOBE_AS_BECK: as_eval_pdf<true>(x, wo, wi, want_f, f, pdf); return;
+    case LOBE_AS_TROW: as_eval_pdf<false>(x, wo, wi, want_f, f, pdf); return;
+    default:
+        pdf = lobe_pdf(x, wo, wi);
+        f = want_f ? lobe_eval(x, wo, wi) : grey(0.f);
+        return;
+    }
+}
 template <bool BECK> ARN_DEV Sampled as_sample(const Lobe& x, float3 wo, float2 u) {      // microfacet.rs:597-611
     Sampled r; r.type = BXDF_REFLECTION | BXDF_GLOSSY;
     float3 wi;
@@ -548,6 +624,22 @@ ARN_DEV float bsdf_pdf(const Bsdf& b, float3 wow, float3 wiw) {
     for (int i = 0; i < b.n; i++) pdfsum += fmaxf(lobe_pdf(b.lobe[i], wo, wi), 0.f);
     return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
 }
+// Bsdf::evaluate + Bsdf::pdf for the same pair of directions (the NEE light sample needs both, scene.rs:98-101)
+ARN_DEV void bsdf_eval_pdf(const Bsdf& b, float3 wow, float3 wiw, float3& f, float& pdf) {
+    float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
+    bool is_reflection = dot(wow, b.ng) * dot(wiw, b.ng) > 0.f;
+    f = grey(0.f);
+    float pdfsum = 0.f;
+    for (int i = 0; i < b.n; i++) {
+        uint32_t k = lobe_type(b.lobe[i].kind);
+        bool match = (is_reflection && (k & BXDF_REFLECTION)) || (!is_reflection && (k & BXDF_TRANSMISSION));
+        float3 fi; float pi;
+        lobe_eval_pdf(b.lobe[i], wo, wi, match, fi, pi);
+        if (match) f = f + fi;
+        pdfsum += fmaxf(pi, 0.f);
+    }
+    pdf = wo.z == 0.f ? 0.f : (b.n == 0 ? pdfsum : pdfsum / (float)b.n);
+}
 // Bsdf::evaluate_sampled with BXDF_ALL (bsdf.rs:100-145)
 ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
@@ -568,8 +660,10 @@ ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     for (int k = 0; k < b.n; k++) {
         uint32_t t = lobe_type(b.lobe[k].kind);
         if ((t & ret.type) && ((is_reflection && (t & BXDF_REFLECTION)) || (!is_reflection && (t & BXDF_TRANSMISSION)))) {
-            ret.f = ret.f + lobe_eval(b.lobe[k], wo, wi);
-            pdfsum += fmaxf(lobe_pdf(b.lobe[k], wo, wi), 0.f);
+            float3 fk; float pk;
+            lobe_eval_pdf(b.lobe[k], wo, wi, true, fk, pk);
+            ret.f = ret.f + fk;
+            pdfsum += fmaxf(pk, 0.f);
         }
     }
     ret.pdf = pdfsum / (float)match_count;

@@ -333,8 +333,9 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                     float3 wi = normalize(ls.pfrom - ls.pto);
                     float3 A1 = grey(0.f);
                     if (!(ls.pdf == 0.f || is_black(ls.radiance))) {
-                        float3 f = bsdf_eval_k<DIFFUSE>(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns));
-                        float spdf = bsdf_pdf_k<DIFFUSE>(bsdf, s.wo, wi);
+                        float3 f; float spdf;
+                        if (DIFFUSE) { f = bsdf_eval_k<true>(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns)); spdf = bsdf_pdf_k<true>(bsdf, s.wo, wi); }
+                        else { bsdf_eval_pdf(bsdf, s.wo, wi, f, spdf); f = f * fabsf(dot(wi, s.ns)); }
                         if (spdf == 0.f) f = grey(0.f);
                         float weight = delta ? 1.f : power_heuristic(ls.pdf, spdf);    // is_delta: no MIS weight (scene.rs:107-115); x * 1 is exact
                         A1 = ls.radiance * f * weight / ls.pdf;
