@@ -528,9 +528,16 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     long lastx = dx + cw % dx, lasty = dy + chh % dy;
     std::vector<int4> rects; std::vector<unsigned long long> prefix; prefix.push_back(0);
     for (long ix = 0, t = 0; ix < nx; ix++) for (long iy = 0; iy < ny; iy++, t++) {
-        if ((uint32_t)(t % world) != prm->rank) continue;
         long cdx = ix == nx - 1 ? lastx : dx, cdy = iy == ny - 1 ? lasty : dy;
-        // tile coordinates are relative to the crop window origin in the reference (ix*dx, iy*dy): crop_min is (0,0) in every config
+        // sic: tiles are laid out from (0, 0), not from crop.pmin (film.rs:118-121); a tile that, grown by the filter
+        // radius, does not meet the crop window makes the reference panic (`.intersect(..).unwrap()`, film.rs:129)
+        {
+            long rx = (long)film->filter_radius_x, ry = (long)film->filter_radius_y;
+            long gx0 = std::max(ix * dx - rx, (long)film->crop_min_x), gx1 = std::min(ix * dx + cdx + rx, (long)film->crop_max_x);
+            long gy0 = std::max(iy * dy - ry, (long)film->crop_min_y), gy1 = std::min(iy * dy + cdy + ry, (long)film->crop_max_y);
+            if (gx0 > gx1 || gy0 > gy1) return set_err(c, ARN_E_INVALID, "arn_render_pt: a film tile does not meet the crop window (Film::spawn_tiles lays tiles out from (0,0) and panics on this, film.rs:118-129)");
+        }
+        if ((uint32_t)(t % world) != prm->rank) continue;
         rects.push_back(make_int4((int)(ix * dx), (int)(iy * dy), (int)cdx, (int)cdy));
         prefix.push_back(prefix.back() + (unsigned long long)cdx * (unsigned long long)cdy);
     }
@@ -563,6 +570,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     if (film->filter_kind == ARN_FILTER_GAUSSIAN) wp.filt_a = -film->filter_a;                                           // neg_alpha (:104)
     wp.crop_x0 = film->crop_min_x; wp.crop_y0 = film->crop_min_y; wp.crop_w = cw; wp.crop_h = chh;
     wp.fr_x = film->filter_radius_x; wp.fr_y = film->filter_radius_y;
+    wp.tile_dx = (int)dx; wp.tile_dy = (int)dy; wp.tile_lastx = (int)lastx; wp.tile_lasty = (int)lasty; wp.tiles_nx = (int)nx; wp.tiles_ny = (int)ny;
+    wp.tile_rx = (int)(long)film->filter_radius_x; wp.tile_ry = (int)(long)film->filter_radius_y;       // filter_radius.cast()
     wp.seed = smp->seed; wp.max_depth = prm->max_depth; wp.min_depth = prm->min_depth; wp.rr_threshold = prm->rr_threshold;
     wp.n_tiles = (uint32_t)rects.size(); wp.tile_rect = c->d_tile_rect; wp.tile_prefix = c->d_tile_prefix;
     wp.spp_begin = s0; wp.spp_count = s1 - s0;

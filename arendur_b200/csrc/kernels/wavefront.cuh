@@ -74,6 +74,7 @@ struct WaveParams {
     uint32_t filt_kind; float filt_a, filt_b;   // film filter (see filter1)
     int crop_x0, crop_y0, crop_w, crop_h;
     float fr_x, fr_y;
+    int tile_dx, tile_dy, tile_lastx, tile_lasty, tiles_nx, tiles_ny, tile_rx, tile_ry;   // spawn_tiles grid: tile size, size of the last tile, count, sink growth (film.rs:104-135)
     uint32_t seed;
     uint32_t max_depth, min_depth; float rr_threshold;
     uint32_t n_tiles;
@@ -467,6 +468,15 @@ ARN_DEV float filter1(const WaveParams& p, float x, float r) {
     }
 }
 
+// FilmTile sink of the tile that owns tile pixel (px, py): the tile grown by the (truncated) filter radius; the crop
+// window clip is applied by the callers.  Only differs from the crop clip for fractional radii.
+ARN_DEV void tile_sink(const WaveParams& p, int px, int py, int& sx0, int& sy0, int& sx1, int& sy1) {
+    int ix = min(px / p.tile_dx, p.tiles_nx - 1), iy = min(py / p.tile_dy, p.tiles_ny - 1);
+    sx0 = ix * p.tile_dx - p.tile_rx; sy0 = iy * p.tile_dy - p.tile_ry;
+    sx1 = ix * p.tile_dx + (ix == p.tiles_nx - 1 ? p.tile_lastx : p.tile_dx) + p.tile_rx;
+    sy1 = iy * p.tile_dy + (iy == p.tiles_ny - 1 ? p.tile_lasty : p.tile_dy) + p.tile_ry;
+}
+
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
     unsigned long long invalid = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -483,6 +493,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant_
         // the tile sink (tile grown by the radius, clipped to the crop window) never clips more
         // than the crop window does for samples inside the tile (DESIGN.md "Film")
         x0 = max(x0, p.crop_x0); y0 = max(y0, p.crop_y0); x1 = min(x1, p.crop_x0 + p.crop_w); y1 = min(y1, p.crop_y0 + p.crop_h);
+        {
+            uint32_t pix = pb.pix[i]; int sx0, sy0, sx1, sy1;
+            tile_sink(p, (int)(pix & 0xffffu), (int)(pix >> 16), sx0, sy0, sx1, sy1);
+            x0 = max(x0, sx0); y0 = max(y0, sy0); x1 = min(x1, sx1); y1 = min(y1, sy1);
+        }
         for (int y = y0; y < y1; y++) {
             float wy = filter1(p, ((float)y + 0.5f) - pos.y, p.fr_y);
             for (int x = x0; x < x1; x++) {
@@ -514,6 +529,8 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
         uint32_t s_end = (uint32_t)((g1 < wave_base + n ? g1 : wave_base + n) - wave_base);
         uint32_t pix = pb.pix[s_begin];
         int px = (int)(pix & 0xffffu), py = (int)(pix >> 16);
+        int sx0, sy0, sx1, sy1;
+        tile_sink(p, px, py, sx0, sy0, sx1, sy1);
         float4 acc[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -528,6 +545,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
             int x0 = (int)cx, y0 = (int)cy, x1 = (int)fx + 1, y1 = (int)fy + 1;   // truncation toward zero
             if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
             if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
+            x0 = max(x0, sx0); y0 = max(y0, sy0); x1 = min(x1, sx1); y1 = min(y1, sy1);
             float wv = 0.f;
             if (lane < 9) wv = filter1(p, ((float)(px - 4 + (int)lane) + 0.5f) - pos.x, p.fr_x);
             else if (lane < 18) wv = filter1(p, ((float)(py - 4 + (int)lane - 9) + 0.5f) - pos.y, p.fr_y);
@@ -557,11 +575,12 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
     if (lane == 0 && invalid) atomicAdd(&q.stats[3], invalid);
 }
 
-// diagnostic: per-sample radiance, indexed ((y*crop_w + x)*spp_count + (s - spp_begin)) (parity tests)
+// diagnostic: per-sample radiance, indexed ((y*crop_w + x)*spp_count + (s - spp_begin)) by the TILE pixel (x, y),
+// which runs over [0, crop_w) x [0, crop_h) whatever crop.pmin is (film.rs:118-121) (parity tests)
 __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_constant__ WaveParams p, PathBuf pb, float4* __restrict__ out, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pix = pb.pix[i]; uint32_t x = pix & 0xffffu, y = pix >> 16;
-        size_t idx = ((size_t)(y - p.crop_y0) * p.crop_w + (x - p.crop_x0)) * p.spp_count + (pb.smp[i] - p.spp_begin);
+        size_t idx = ((size_t)y * p.crop_w + x) * p.spp_count + (pb.smp[i] - p.spp_begin);
         out[idx] = pb.L[i];
     }
 }

@@ -116,7 +116,7 @@ int arn_oracle_render_pt(arn_oracle_scene* h, const arn_camera* cam, const arn_f
     if (!h || !cam || !film || !smp || !prm || !film_out) return ARN_E_INVALID;
     if (h->s.light_prims.empty()) return ARN_E_INVALID;   // the reference panics (index out of bounds, scene.rs:53-55)
     RayStats st;
-    render_pt(h->s, *cam, *film, *smp, *prm, film_out, &st, nthreads);
+    if (!render_pt(h->s, *cam, *film, *smp, *prm, film_out, &st, nthreads)) return ARN_E_INVALID;   // spawn_tiles' unwrap panics (film.rs:129)
     if (stats_out) {
         std::memset(stats_out, 0, sizeof *stats_out);
         stats_out->camera_rays = st.camera; stats_out->extend_rays = st.extend; stats_out->shadow_rays = st.shadow;
@@ -130,7 +130,7 @@ int arn_oracle_render_pt_samples(arn_oracle_scene* h, const arn_camera* cam, con
                                  const arn_pt_params* prm, float* film_out, float* radiance_out, int nthreads) {
     if (!h || !cam || !film || !smp || !prm || !film_out || !radiance_out || h->s.light_prims.empty()) return ARN_E_INVALID;
     RayStats st;
-    render_pt(h->s, *cam, *film, *smp, *prm, film_out, &st, nthreads, radiance_out);
+    if (!render_pt(h->s, *cam, *film, *smp, *prm, film_out, &st, nthreads, radiance_out)) return ARN_E_INVALID;
     return ARN_OK;
 }
 

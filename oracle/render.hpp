@@ -310,7 +310,10 @@ inline bool ibox_intersect(const IBox& a, const IBox& b, IBox* o) {           //
 }
 struct FilmTile { IBox bounding, sink; std::vector<Float> px; };              // px: 4 floats per sink pixel
 // Film::spawn_tiles (film.rs:104-135); tiles in ix-major order
-inline std::vector<FilmTile> spawn_tiles(const arn_film& film, long nx, long ny) {
+// `ok` turns false where the reference panics: `.intersect(&self.crop_window).unwrap()` (film.rs:129) on a tile that,
+// grown by the filter radius, does not meet the crop window — tiles are laid out from (0, 0), NOT from crop.pmin (sic).
+inline std::vector<FilmTile> spawn_tiles(const arn_film& film, long nx, long ny, bool* ok = nullptr) {
+    if (ok) *ok = true;
     IBox crop = {film.crop_min_x, film.crop_min_y, film.crop_max_x, film.crop_max_y};
     long ex = crop.x1 - crop.x0, ey = crop.y1 - crop.y0;
     long dx = ex / nx, dy = ey / ny;
@@ -323,7 +326,7 @@ inline std::vector<FilmTile> spawn_tiles(const arn_film& film, long nx, long ny)
             long cdy = iy == ny - 1 ? lasty : dy;
             FilmTile t; t.bounding = IBox{ix * dx, iy * dy, ix * dx + cdx, iy * dy + cdy};
             IBox grown = {t.bounding.x0 - rx, t.bounding.y0 - ry, t.bounding.x1 + rx, t.bounding.y1 + ry};
-            ibox_intersect(grown, crop, &t.sink);
+            if (!ibox_intersect(grown, crop, &t.sink) && ok) *ok = false;
             ret.push_back(t);
         }
     }
@@ -353,10 +356,13 @@ inline void tile_add_sample(FilmTile& t, const arn_film& film, V2 pos, RGB spect
 }
 
 // PTRenderer::render (renderer/pt.rs:128-176) up to collect_into's merge (film.rs:171-183, 82-101)
-inline void render_pt(const Scene& s, const arn_camera& cam, const arn_film& film, const arn_sampler& smp,
+// radiance_out (diagnostic) is indexed by the TILE pixel (x, y) in [0, crop width) x [0, crop height).
+inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& film, const arn_sampler& smp,
                       const arn_pt_params& prm, Float* film_out, RayStats* stats, int nthreads, Float* radiance_out = nullptr) {
     long nx = prm.tiles_x ? prm.tiles_x : 16, ny = prm.tiles_y ? prm.tiles_y : 16;
-    std::vector<FilmTile> tiles = spawn_tiles(film, nx, ny);
+    bool tiles_ok = true;
+    std::vector<FilmTile> tiles = spawn_tiles(film, nx, ny, &tiles_ok);
+    if (!tiles_ok) return false;
     uint32_t spp = smp.sampledx * smp.sampledy;
     uint32_t s0 = prm.spp_begin, s1 = prm.spp_end ? prm.spp_end : spp;
     uint32_t world = prm.world_size ? prm.world_size : 1;
@@ -382,7 +388,7 @@ inline void render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
                     tstats[tid].camera++;
                     RGB L = calculate_lighting(s, ray, sampler, prm.max_depth, prm.min_depth, prm.rr_threshold, &tstats[tid]);
                     if (radiance_out) {
-                        size_t ri = (((size_t)(y - film.crop_min_y) * (size_t)(film.crop_max_x - film.crop_min_x) + (size_t)(x - film.crop_min_x)) * (s1 - s0) + (si - s0)) * 4;
+                        size_t ri = (((size_t)y * (size_t)(film.crop_max_x - film.crop_min_x) + (size_t)x) * (s1 - s0) + (si - s0)) * 4;
                         radiance_out[ri] = L.x; radiance_out[ri + 1] = L.y; radiance_out[ri + 2] = L.z; radiance_out[ri + 3] = 0.f;
                     }
                     if (rgb_valid(L)) tile_add_sample(tile, film, pfilm, L);
@@ -412,6 +418,7 @@ inline void render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
         stats->invalid += t.invalid; stats->extend_bounce += t.extend_bounce;
         stats->trav.nodes += t.trav.nodes; stats->trav.tris += t.trav.tris; stats->trav.spheres += t.trav.spheres;
     }
+    return true;
 }
 
 // TilePixel::finalize + ToNorm<u8>::from_norm (film.rs:338-344, spectrum/macros.rs:164-180)

@@ -108,3 +108,44 @@ def test_ortho_camera_bit_exact(ctx, lens):
     assert same.mean() >= 1.0 - 1e-4, f"{(~same).sum()} of {same.size} samples differ"
     assert (orad[..., :3].max(-1) > 0).mean() > 0.1
     sc.close(); osc.close()
+
+
+def test_crop_window_quirks_oracle():
+    """Film::spawn_tiles lays its tiles out from (0, 0), not from crop.pmin, and unwraps the intersection of every grown
+    tile with the crop window (film.rs:118-129): a crop window away from the origin panics; a slightly offset one
+    renders the pixels [0, w) x [0, h) and keeps what falls inside the window."""
+    hs, cam, _, smp, prm = scenes.cornell_scene(64, 48, 1, 1)
+    osc = O.OracleScene(hs.desc())
+    far = api.make_film(64, 48, crop=(32, 24, 64, 48))
+    out = np.zeros((24, 32, 4), f32); st = L.Stats(); trav = np.zeros(3, np.uint64)
+    import ctypes as C
+    rc = osc.lib.arn_oracle_render_pt(osc.h, C.byref(cam), C.byref(far), C.byref(smp), C.byref(prm), out.ctypes.data_as(C.c_void_p),
+                                      C.byref(st), trav.ctypes.data_as(C.c_void_p), 2)
+    assert rc == L.ARN_E_INVALID
+    near = api.make_film(64, 48, crop=(3, 2, 51, 34))                 # 48 x 32 window: 3 x 2 pixel tiles from (0, 0)
+    f, st, _ = osc.render_pt(cam, near, smp, prm)
+    assert st.camera_rays == 48 * 32 and f[..., 3].max() > 0
+    # samples exist for pixels [0, 48) x [0, 32) only; the window [3, 51) x [2, 34) keeps their splats (radius 4 reaches its far edge)
+    assert f[0, 0, 3] != 0 and f[-1, -1, 3] != 0
+    small = api.make_film(64, 48, crop=(3, 2, 51, 34), filter_radius=(0.5, 0.5))
+    f2, _, _ = osc.render_pt(cam, small, smp, prm)
+    assert np.all(f2[-2:, :, 3] == 0) and np.all(f2[:, -3:, 3] == 0) and f2[0, 0, 3] != 0      # pixels 48..50 / 32..33 get no sample
+    osc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius", [(4.0, 4.0), (2.7, 1.3)])
+def test_crop_window_quirks_gpu(ctx, radius):
+    hs, cam, _, smp, prm = scenes.cornell_scene(64, 48, 2, 2)
+    sc = ctx.upload(hs.desc()); osc = O.OracleScene(hs.desc())
+    with pytest.raises(api.ArnError) as e:
+        sc.render_pt(cam, api.make_film(64, 48, crop=(32, 24, 64, 48), filter_radius=radius), smp, prm)
+    assert e.value.code == L.ARN_E_INVALID
+    for crop in ((3, 2, 51, 34), (0, 0, 60, 41), (1, 0, 64, 48)):       # offset window; sizes the 16 x 16 grid does not divide
+        film = api.make_film(64, 48, crop=crop, filter_radius=radius)
+        gf, st = sc.render_pt(cam, film, smp, prm)
+        rf, ost, _ = osc.render_pt(cam, film, smp, prm)
+        assert st.camera_rays == ost.camera_rays
+        assert np.abs(gf - rf).max() <= 2e-6 * np.abs(rf).max(), (crop, np.abs(gf - rf).max() / np.abs(rf).max())
+        assert np.array_equal(gf[..., 3] == 0, rf[..., 3] == 0), crop        # the same film pixels are touched (fractional radii: tile sinks)
+    sc.close(); osc.close()
