@@ -72,11 +72,11 @@ def make_sampler(sampledx, sampledy, ndim=8, seed=0):
     return s
 
 
-def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, tiles=(16, 16)):
+def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, tiles=(16, 16), min_depth=None, rr_threshold=0.05):
     p = L.PTParams()
     p.max_depth = max_depth
-    p.min_depth = max_depth // 2      # renderer/pt.rs:48
-    p.rr_threshold = 0.05             # renderer/pt.rs:47
+    p.min_depth = max_depth // 2 if min_depth is None else min_depth      # renderer/pt.rs:48
+    p.rr_threshold = rr_threshold                                         # renderer/pt.rs:47
     p.tiles_x, p.tiles_y = tiles
     p.rank, p.world_size = rank, world_size
     p.spp_begin, p.spp_end = spp_begin, spp_end

@@ -401,3 +401,50 @@ def test_c4_full_size(ctx):
     assert g2["t"].tobytes() == oh["t"].tobytes()
     assert (g2["prim_id"] != oh["prim_id"]).mean() < 1e-3
     sc2.close()
+
+
+def test_sample_ranges_waves_tile_grids_and_roulette(ctx):
+    """The knobs bench.py and the multi-GPU partition rely on: sample sub-ranges add up to the whole render, a wave
+    capacity smaller than one pixel row splits pixels' samples across waves without changing any sample, other tile
+    grids / rank counts partition the frame, and non-default Russian-roulette constants follow the oracle."""
+    hs, cam, film, smp, _ = scenes.cornell_scene(48, 36, 3, 3)
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    prm = api.make_pt_params(max_depth=5)
+    full, rad_full, st_full = sc.render_pt_samples(cam, film, smp, prm)
+    # (1) sample ranges
+    acc = np.zeros_like(full); rays = 0
+    for b, e in ((0, 3), (3, 4), (4, 9)):
+        p = api.make_pt_params(max_depth=5, spp_begin=b, spp_end=e)
+        f, r, st = sc.render_pt_samples(cam, film, smp, p)
+        assert np.array_equal(r, rad_full[:, :, b:e])
+        acc += f; rays += st.extend_rays + st.shadow_rays + st.mis_rays
+    assert rays == st_full.extend_rays + st_full.shadow_rays + st_full.mis_rays
+    assert np.allclose(acc, full, rtol=1e-5, atol=1e-6)
+    # (2) tiny waves: 1024 samples per wave = 113.8 pixels of 9 samples -> pixels straddle waves
+    ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 1024)
+    f_small, rad_small, st_small = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
+    assert np.array_equal(rad_small, rad_full) and np.allclose(f_small, full, rtol=1e-5, atol=1e-6)
+    assert st_small.kernel_launches > 10 * st_full.kernel_launches
+    # (3) 5 x 4 tile grid over 3 ranks, against the oracle's same partition
+    total = np.zeros_like(full)
+    for rank in range(3):
+        p = api.make_pt_params(max_depth=5, tiles=(5, 4), rank=rank, world_size=3)
+        gf, st = sc.render_pt(cam, film, smp, p)
+        rf, ost, _ = osc.render_pt(cam, film, smp, p)
+        assert st.camera_rays == ost.camera_rays > 0
+        assert np.abs(gf - rf).max() <= 2e-6 * np.abs(rf).max()
+        total += gf
+    p = api.make_pt_params(max_depth=5, tiles=(5, 4))
+    whole, _ = sc.render_pt(cam, film, smp, p)
+    assert np.allclose(total, whole, rtol=1e-5, atol=1e-6)
+    # (4) roulette from the first bounce with a high threshold
+    p = api.make_pt_params(max_depth=7, min_depth=1, rr_threshold=0.6)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, p)
+    _, orad = osc.render_pt_samples(cam, film, smp, p)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.mean() >= 1.0 - 1e-4
+    _, ost, _ = osc.render_pt(cam, film, smp, p)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays)
+    sc.close(); osc.close()
