@@ -448,3 +448,82 @@ def test_sample_ranges_waves_tile_grids_and_roulette(ctx):
     _, ost, _ = osc.render_pt(cam, film, smp, p)
     assert (st.extend_rays, st.shadow_rays, st.mis_rays) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays)
     sc.close(); osc.close()
+
+
+def test_upload_and_render_argument_errors(ctx, cornell_small):
+    """Error convention of the C-ABI: malformed scenes and arguments come back as negative codes
+    with a message, never as a crash or a silently wrong render."""
+    import ctypes as C
+    hs, cam, film, smp, prm = cornell_small
+    d = hs.desc()
+
+    def clone():
+        c = L.SceneDesc()
+        C.memmove(C.byref(c), C.byref(d), C.sizeof(L.SceneDesc))
+        return c
+
+    def upload_fails(desc, code):
+        with pytest.raises(api.ArnError) as e:
+            ctx.upload(desc)
+        assert e.value.code == code, (e.value.code, str(e.value))
+        assert len(str(e.value)) > 10
+
+    nodes = hs.nodes().copy()
+    # child index past the end of the node array
+    bad = nodes.copy(); bad[0, 6] = d.n_nodes + 5
+    c1 = clone(); c1.nodes = bad.ctypes.data_as(C.POINTER(L.Node)); upload_fails(c1, L.ARN_E_INVALID)
+    # a cycle: the root's second child is the root's first child's ancestor
+    bad = nodes.copy()
+    inner = [i for i in range(1, d.n_nodes) if (bad[i, 7] >> 2) == 0][0]
+    bad[inner, 6] = 0x7fffffff
+    c2 = clone(); c2.nodes = bad.ctypes.data_as(C.POINTER(L.Node)); upload_fails(c2, L.ARN_E_INVALID)
+    # leaf range past the component list
+    leaf = [i for i in range(d.n_nodes) if (bad[i, 7] >> 2) != 0][0]
+    bad = nodes.copy(); bad[leaf, 6] = d.n_prims
+    c3 = clone(); c3.nodes = bad.ctypes.data_as(C.POINTER(L.Node)); upload_fails(c3, L.ARN_E_INVALID)
+    # triangle index out of range
+    idx = np.ctypeslib.as_array(d.indices, (d.n_triangles * 3,)).copy(); idx[7] = d.n_vertices
+    c4 = clone(); c4.indices = idx.ctypes.data_as(C.POINTER(C.c_uint32)); upload_fails(c4, L.ARN_E_INVALID)
+    # a triangle as a light: unsupported (and useless in the reference: surface_area() == 0)
+    lp = np.ctypeslib.as_array(d.light_prims, (d.n_lights,)).copy(); lp[0] = 0
+    c5 = clone(); c5.light_prims = lp.ctypes.data_as(C.POINTER(C.c_uint32)); upload_fails(c5, L.ARN_E_UNSUPPORTED)
+    # analytic light reference without a table
+    lp = np.ctypeslib.as_array(d.light_prims, (d.n_lights,)).copy(); lp[0] = L.ARN_LIGHT_ANALYTIC | 3
+    c6 = clone(); c6.light_prims = lp.ctypes.data_as(C.POINTER(C.c_uint32)); upload_fails(c6, L.ARN_E_INVALID)
+    # a tree deeper than the traversal stack: a left-leaning chain of 70 interior nodes over 71 coincident triangles
+    n = 71
+    chain = np.zeros((2 * n - 1, 8), np.uint32); cf = chain.view(np.float32)
+    cf[:, 0:3] = (0, 0, 3); cf[:, 3:6] = (1, 1, 3)
+    # pre-order: interior i has first child i+1; subtree(i+1) has 2*(n-2-i)+1 nodes; second child = i + 1 + that
+    for i in range(n - 1):
+        sub_next = 2 * (n - 2 - i) + 1
+        chain[i, 6] = sub_next + 1; chain[i, 7] = 0
+    chain[n - 1, 6] = 0; chain[n - 1, 7] = (1 << 2) | 3                         # the deepest leaf: slot 0
+    for j in range(n - 1):                                                      # the right-hand leaves, innermost first
+        chain[n + j, 6] = 1 + j; chain[n + j, 7] = (1 << 2) | 3
+    deep = api.HostScene()
+    mat = deep.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+    tri = np.float32([[0, 0, 3], [1, 0, 3], [0, 1, 3]])
+    for _ in range(n):
+        deep.add_mesh(tri, np.uint32([0, 1, 2]), mat)
+    deep.add_light(api.point_light((0, 0, 0), (1, 1, 1)))
+    dd = deep.build()
+    c7 = L.SceneDesc(); C.memmove(C.byref(c7), C.byref(dd), C.sizeof(L.SceneDesc))
+    order = np.arange(n, dtype=np.uint32)
+    c7.nodes = chain.ctypes.data_as(C.POINTER(L.Node)); c7.n_nodes = 2 * n - 1; c7.order = order.ctypes.data_as(C.POINTER(C.c_uint32))
+    upload_fails(c7, L.ARN_E_UNSUPPORTED)
+    # render arguments
+    sc = ctx.upload(d)
+    for bad_prm, code in ((api.make_pt_params(max_depth=0), L.ARN_E_INVALID), (api.make_pt_params(max_depth=8, rank=2, world_size=2), L.ARN_E_INVALID),
+                          (api.make_pt_params(max_depth=8, spp_begin=3, spp_end=2), L.ARN_E_INVALID)):
+        with pytest.raises(api.ArnError) as e:
+            sc.render_pt(cam, film, smp, bad_prm)
+        assert e.value.code == code
+    with pytest.raises(api.ArnError):
+        sc.render_pt(cam, api.make_film(8, 8), smp, prm)                        # 8 x 8 window / 16 x 16 tiles: spawn_tiles divides by zero
+    with pytest.raises(api.ArnError):
+        sc.render_pt(cam, api.make_film(64, 48, filter_kind=9), smp, prm)
+    # and the scene still renders afterwards
+    f, st = sc.render_pt(cam, film, smp, prm)
+    assert st.camera_rays > 0 and np.isfinite(f).all()
+    sc.close()
