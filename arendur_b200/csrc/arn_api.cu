@@ -4,6 +4,7 @@
 // computes anything needs a CUDA device and fails with ARN_E_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include "../../include/arn.h"
 #include "kernels/wavefront.cuh"
 #include "kernels/lbvh.cuh"
+#include "kernels/wide_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace arn;
@@ -206,46 +208,16 @@ void arn_scene_destroy(arn_scene* s) {
     delete s;
 }
 
-// Order-preserving 4-wide collapse of the pre-order binary nodes: wide node of interior node n =
-// records (n.first's children | n.first itself if it is a leaf, n.second's likewise); a record keeps
-// the child's bounds and its reference words (traverse.cuh).  Wide nodes are emitted in pre-order.
-static void collapse_wide(const arn_node* nodes, std::vector<arn_node>& wide, arn_node& root) {
-    auto is_leaf = [&](uint32_t i) { return (nodes[i].len_axis >> 2) != 0; };
-    auto axes_of = [&](uint32_t i) {
-        uint32_t a = i + 1, b = i + nodes[i].offset;
-        return (nodes[i].len_axis & 3u) | ((is_leaf(a) ? 0u : (nodes[a].len_axis & 3u)) << 2) | ((is_leaf(b) ? 0u : (nodes[b].len_axis & 3u)) << 4);
-    };
-    struct Todo { uint32_t node, rec; };              // binary interior node -> the record that refers to it
-    std::vector<Todo> todo;
-    auto make_rec = [&](uint32_t i, arn_node& r, size_t rec_index) {
-        r = nodes[i];
-        if (is_leaf(i)) { r.offset = nodes[i].offset; r.len_axis = ((nodes[i].len_axis >> 2) << 8) | ARN_W_LEAF; }
-        else { r.offset = 0; r.len_axis = (axes_of(i) << 2) | ARN_W_INNER; if (rec_index != (size_t)-1) todo.push_back({i, (uint32_t)rec_index}); }
-    };
-    make_rec(0, root, (size_t)-1);
-    if (is_leaf(0)) return;
-    arn_node empty; std::memset(&empty, 0, sizeof empty);
-    // explicit stack, children pushed so that wide nodes come out in pre-order
-    std::vector<Todo> st; st.push_back({0u, 0xffffffffu});
-    while (!st.empty()) {
-        Todo t = st.back(); st.pop_back();
-        uint32_t w = (uint32_t)(wide.size() / 4);
-        if (t.rec != 0xffffffffu) wide[t.rec].offset = w;
-        wide.resize(wide.size() + 4, empty);
-        uint32_t pair[2] = {t.node + 1, t.node + nodes[t.node].offset};
-        todo.clear();
-        for (int g = 0; g < 2; g++) {
-            uint32_t ch = pair[g];
-            size_t base = (size_t)w * 4 + 2 * g;
-            if (is_leaf(ch)) make_rec(ch, wide[base], base);
-            else { make_rec(ch + 1, wide[base], base); make_rec(ch + nodes[ch].offset, wide[base + 1], base + 1); }
-        }
-        for (size_t k = todo.size(); k-- > 0;) st.push_back(todo[k]);
-    }
-}
-
 int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if (!c || !d || !out) return set_err(c, ARN_E_INVALID, "arn_scene_upload: NULL argument");
+    const bool verbose = std::getenv("ARN_VERBOSE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[arn upload] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     if (!d->n_prims || !d->prims || !d->n_nodes || !d->nodes || !d->order) return set_err(c, ARN_E_INVALID, "arn_scene_upload: scene has no primitives or no BVH");
     if (d->n_triangles && (!d->positions || !d->indices || !d->tri_mesh || !d->meshes)) return set_err(c, ARN_E_INVALID, "arn_scene_upload: triangle arrays missing");
     if (d->n_prims >= 0x80000000u) return set_err(c, ARN_E_INVALID, "arn_scene_upload: too many primitives");
@@ -273,6 +245,7 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
         if (d->light_prims[i] >= d->n_prims || !(d->prims[d->light_prims[i]] & ARN_PRIM_SPHERE))
             return set_err(c, ARN_E_UNSUPPORTED, "lights must be emissive sphere primitives (triangle emitters do not work in arendur: surface_area() == 0, SURVEY.md Appendix A-2)");
     }
+    lap("reference validation");
     // tree walk: bounds of child offsets, leaf ranges, maximum stack depth
     uint32_t max_depth = 0;
     {
@@ -291,48 +264,72 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     }
     if (max_depth > ARN_STACK) return set_err(c, ARN_E_UNSUPPORTED, "BVH deeper than the traversal stack (" + std::to_string(max_depth) + " > " + std::to_string(ARN_STACK) + ")");
 
+    lap("tree walk");
     cudaSetDevice(c->device);
     arn_scene* s = new arn_scene; s->ctx = c; s->max_depth = max_depth;
-    auto fail = [&](int rc) { arn_scene_destroy(s); return rc; };
+    std::vector<void*> scratch;          // device scratch of this upload, freed after its final sync
+    auto fail = [&](int rc) { cudaStreamSynchronize(c->stream); for (void* p : scratch) cudaFree(p); arn_scene_destroy(s); return rc; };
     int rc;
     // nodes: same 32-byte records, read on the device as float4 pairs
     const arn_node* dn = nullptr;
     if ((rc = dev_upload(s, d->nodes, d->n_nodes, &dn)) != ARN_OK) return fail(rc);
     s->dev.nodes = (const float4*)dn;
-    {   // 4-wide collapse (kernels/traverse.cuh, traverse4)
-        std::vector<arn_node> wide;
-        arn_node root;
-        collapse_wide(d->nodes, wide, root);
-        const arn_node* dw = nullptr;
-        if ((rc = dev_upload(s, wide.data(), wide.size(), &dw)) != ARN_OK) return fail(rc);
-        s->dev.wide = (const float4*)dw;
-        std::memcpy(&s->dev.root0, &root, 16); std::memcpy(&s->dev.root1, (const char*)&root + 16, 16);
-    }
-    // ordered 48-byte primitive slots
-    std::vector<float4> slots((size_t)d->n_prims * 3);
-    for (uint32_t k = 0; k < d->n_prims; k++) {
-        uint32_t comp = d->order[k], ref = d->prims[comp];
-        float4 a = make_float4(0, 0, 0, 0), b = a, cc = a;
-        if (ref & ARN_PRIM_SPHERE) { uint32_t w = comp | ARN_PRIM_SPHERE; std::memcpy(&a.w, &w, 4); }
+    lap("node upload");
+    {   // 4-wide collapse on the device (kernels/wide_build.cuh; layout: kernels/traverse.cuh, traverse4)
+        auto is_leaf = [&](uint32_t i) { return (d->nodes[i].len_axis >> 2) != 0; };
+        arn_node root = d->nodes[0];
+        if (is_leaf(0)) root.len_axis = ((root.len_axis >> 2) << 8) | ARN_W_LEAF;
         else {
-            const float* p0 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref];
-            const float* p1 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref + 1];
-            const float* p2 = d->positions + 3 * (size_t)d->indices[3 * (size_t)ref + 2];
-            a = make_float4(p0[0], p0[1], p0[2], 0); std::memcpy(&a.w, &comp, 4);
-            b = make_float4(p1[0], p1[1], p1[2], 0); cc = make_float4(p2[0], p2[1], p2[2], 0);
+            uint32_t a = 1, b = d->nodes[0].offset;
+            uint32_t axes = (d->nodes[0].len_axis & 3u) | ((is_leaf(a) ? 0u : (d->nodes[a].len_axis & 3u)) << 2) | ((is_leaf(b) ? 0u : (d->nodes[b].len_axis & 3u)) << 4);
+            root.offset = 0; root.len_axis = (axes << 2) | ARN_W_INNER;
         }
-        slots[3 * (size_t)k] = a; slots[3 * (size_t)k + 1] = b; slots[3 * (size_t)k + 2] = cc;
+        std::memcpy(&s->dev.root0, &root, 16); std::memcpy(&s->dev.root1, (const char*)&root + 16, 16);
+        const size_t n_interior = ((size_t)d->n_nodes - 1) / 2;        // full binary tree; every wide node is rooted at an interior node
+        if (n_interior > 0) {
+            arn_node* d_wide = nullptr; uint2 *f0 = nullptr, *f1 = nullptr; uint32_t *d_counts = nullptr;
+            cudaError_t ce;
+            if ((ce = cudaMalloc(&d_wide, n_interior * 4 * sizeof(arn_node))) != cudaSuccess) { set_err(c, ARN_E_OOM, std::string("wide nodes: ") + cudaGetErrorString(ce)); return fail(ARN_E_OOM); }
+            s->allocs.push_back(d_wide); s->bytes += n_interior * 4 * sizeof(arn_node);
+            if (cudaMalloc(&f0, n_interior * sizeof(uint2)) != cudaSuccess || (scratch.push_back(f0), cudaMalloc(&f1, n_interior * sizeof(uint2))) != cudaSuccess
+                || (scratch.push_back(f1), cudaMalloc(&d_counts, (ARN_STACK + 4) * sizeof(uint32_t))) != cudaSuccess) {
+                for (void* p : scratch) cudaFree(p);
+                set_err(c, ARN_E_OOM, "wide collapse scratch: out of device memory"); return fail(ARN_E_OOM);
+            }
+            scratch.push_back(d_counts);
+            uint32_t* d_wide_count = d_counts + ARN_STACK + 2;
+            k_wide_begin<<<1, 1, 0, c->stream>>>(f0, d_counts, d_wide_count, 1);
+            int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+            const int grid = (int)std::min<size_t>((size_t)sms * 8, (n_interior + 255) / 256);
+            const int levels = (int)(max_depth + 1) / 2 + 1;
+            for (int level = 0; level < levels; level++)
+                k_wide_level<<<grid, 256, 0, c->stream>>>(dn, d_wide, (level & 1) ? f1 : f0, (level & 1) ? f0 : f1, d_counts, level, d_wide_count);
+            s->dev.wide = (const float4*)d_wide;
+        }
     }
-    if ((rc = dev_upload(s, slots.data(), slots.size(), &s->dev.tris)) != ARN_OK) return fail(rc);
+    lap("wide collapse + upload");
     if ((rc = dev_upload(s, d->spheres, d->n_spheres, &s->dev.spheres)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->indices, (size_t)d->n_triangles * 3, &s->dev.indices)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->positions, (size_t)d->n_vertices * 3, &s->dev.positions)) != ARN_OK) return fail(rc);
+    if ((rc = dev_upload(s, d->prims, d->n_prims, &s->dev.prims)) != ARN_OK) return fail(rc);
+    {   // ordered 48-byte primitive slots, gathered on the device from the arrays just uploaded
+        uint32_t* d_order = nullptr; float4* d_slots = nullptr;
+        if (cudaMalloc(&d_order, (size_t)d->n_prims * 4) != cudaSuccess) { set_err(c, ARN_E_OOM, "component order: out of device memory"); return fail(ARN_E_OOM); }
+        scratch.push_back(d_order);
+        if (cudaMalloc(&d_slots, (size_t)d->n_prims * 48) != cudaSuccess) { set_err(c, ARN_E_OOM, "primitive slots: out of device memory"); return fail(ARN_E_OOM); }
+        s->allocs.push_back(d_slots); s->bytes += (size_t)d->n_prims * 48;
+        cudaMemcpyAsync(d_order, d->order, (size_t)d->n_prims * 4, cudaMemcpyHostToDevice, c->stream);
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const int grid = (int)std::min<size_t>((size_t)sms * 8, ((size_t)d->n_prims + 255) / 256);
+        k_build_slots<<<grid, 256, 0, c->stream>>>(d_order, s->dev.prims, s->dev.indices, s->dev.positions, d_slots, d->n_prims);
+        s->dev.tris = d_slots;
+    }
+    lap("slots (device gather)");
     if ((rc = dev_upload(s, d->normals, d->normals ? (size_t)d->n_vertices * 3 : 0, &s->dev.normals)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->uvs, d->uvs ? (size_t)d->n_vertices * 2 : 0, &s->dev.uvs)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->tri_mesh, d->n_triangles, &s->dev.tri_mesh)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->meshes, d->n_meshes, &s->dev.meshes)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->materials, d->n_materials, &s->dev.materials)) != ARN_OK) return fail(rc);
-    if ((rc = dev_upload(s, d->prims, d->n_prims, &s->dev.prims)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_prims, d->n_lights, &s->dev.light_prims)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->analytic_lights, d->n_analytic_lights, &s->dev.analytic)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_func, d->n_lights, &s->dev.light_func)) != ARN_OK) return fail(rc);
@@ -344,7 +341,11 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     }
     s->dev.light_integral = d->light_func_integral;
     s->dev.n_lights = d->n_lights; s->dev.n_nodes = d->n_nodes; s->dev.n_prims = d->n_prims; s->dev.n_spheres = d->n_spheres;
+    lap("shading arrays upload");
     cudaError_t e = cudaStreamSynchronize(c->stream);     // the staging vector `slots` dies here
+    if (e == cudaSuccess) e = cudaGetLastError();
+    for (void* p : scratch) cudaFree(p);
+    lap("sync");
     if (e != cudaSuccess) { set_err(c, ARN_E_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); return fail(ARN_E_CUDA); }
     *out = s;
     return ARN_OK;
