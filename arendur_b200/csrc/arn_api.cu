@@ -47,7 +47,7 @@ struct arn_ctx {
     unsigned long long* d_ctr = nullptr;
     bool opt_count = false;
     int opt_width = 0;           // ARN_OPT_BVH_WIDTH: 0 auto, 2 binary, 4 wide
-    int g_trace_w = 0, g_closest_w = 0, g_any_w = 0;
+    int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
     size_t opt_wave = 0;
 };
 
@@ -158,8 +158,10 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
-    c->g_shade = grid_for(c, (const void*)k_shade<false>);
-    c->g_shade_d = grid_for(c, (const void*)k_shade<true>);
+    c->g_shade = grid_for(c, (const void*)k_shade<SHADE_GENERIC>);
+    c->g_shade_p = grid_for(c, (const void*)k_shade<SHADE_PLASTIC>);
+    c->g_shade_g = grid_for(c, (const void*)k_shade<SHADE_GLASS>);
+    c->g_shade_d = grid_for(c, (const void*)k_shade<SHADE_DIFFUSE>);
     c->g_resolve = grid_for(c, (const void*)k_resolve);
     c->g_accum = grid_for(c, (const void*)k_accumulate);
     c->g_accum_px = grid_for(c, (const void*)k_accumulate_px);
@@ -603,8 +605,11 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         const uint32_t CLS_MASK = 0xF8u, NEE_MASK = (1u << 2) | (1u << 10) | (1u << 11);
         for (uint32_t b = 0; b < prm->max_depth; b++) {
             // shade(b): consumes the class queues, fills active[cur^1] + connect / shadow / light-ray queues
-            if (s->class_mask & 0x1Cu) { k_shade<false><<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
-            if (s->class_mask & 0x03u) { k_shade<true><<<c->g_shade_d, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
+            // heavy classes first: the tail of the bounce is cheap Lambert work
+            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
+            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
+            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
+            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
             k_reset<<<1, 1, 0, c->stream>>>(c->q, CLS_MASK | (1u << cur));
             cur ^= 1;
             trace(0, (int)b + 1);                                  // path rays of bounce b+1, shadow + light rays of bounce b

@@ -328,6 +328,21 @@ ARN_DEV uint32_t lobe_type(int k) {
     default: return BXDF_REFLECTION | BXDF_GLOSSY;       // TS_R, Ashikhmin–Shirley
     }
 }
+// Lobe-kind masks of the shade kernel instances: a kernel that only ever meets some lobe kinds (its hits were sorted
+// by material class) tells the compiler so, and the switches below shrink to those cases.  Same code, fewer
+// instructions to fetch: the generic instance is 228 KB of SASS and instruction-cache bound.
+#define LOBES_ALL 0xFFu
+#define LOBES_PLASTIC (1u << LOBE_AS_BECK)                                                   /* material/plastic.rs:40-63 */
+#define LOBES_GLASS ((1u << LOBE_FRESNEL) | (1u << LOBE_TS_R) | (1u << LOBE_TS_T))           /* material/glass.rs:42-80 */
+template <uint32_t M> ARN_DEV int known_kind(int k) {
+    if (M == LOBES_ALL) return k;
+    int r = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) if ((M >> j) & 1u) r = j;          // lowest kind in the mask
+#pragma unroll
+    for (int j = 0; j < 8; j++) if (((M >> j) & 1u) && k == j) r = j;
+    return r;
+}
 template <bool BECK> ARN_DEV float as_pdf(const Lobe& x, float3 wo, float3 wi) {        // microfacet.rs:613-623
     if (wo.z * wi.z < 0.f) return 0.f;
     float3 wh = normalize(wo + wi);
@@ -346,8 +361,8 @@ template <bool BECK> ARN_DEV float3 as_eval(const Lobe& x, float3 wo, float3 wi)
         / (4.f * fabsf(dot(wi, wh)) * fmaxf(fabsf(cos_theta(wi)), fabsf(cos_theta(wo))));
     return diffuse + specular;
 }
-ARN_NOINL float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
-    switch (x.kind) {
+template <uint32_t M> ARN_NOINL float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
+    switch (known_kind<M>(x.kind)) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: return wo.z * wi.z > 0.f ? fabsf(cos_theta(wi)) * ARN_INV_PI : 0.f;
     case LOBE_LAMBERT_T: return wo.z * wi.z >= 0.f ? 0.f : fabsf(cos_theta(wi)) * ARN_INV_PI;
     case LOBE_FRESNEL: return 0.f;
@@ -369,8 +384,8 @@ ARN_NOINL float lobe_pdf(const Lobe& x, float3 wo, float3 wi) {
     default: return as_pdf<false>(x, wo, wi);
     }
 }
-ARN_NOINL float3 lobe_eval(const Lobe& x, float3 wo, float3 wi) {
-    switch (x.kind) {
+template <uint32_t M> ARN_NOINL float3 lobe_eval(const Lobe& x, float3 wo, float3 wi) {
+    switch (known_kind<M>(x.kind)) {
     case LOBE_LAMBERT_R: case LOBE_LAMBERT_T: return x.a * ARN_INV_PI;
     case LOBE_OREN_NAYAR: {
         float sti = sin_theta(wi), sto = sin_theta(wo);
@@ -435,8 +450,8 @@ template <bool BECK> ARN_DEV void as_eval_pdf(const Lobe& x, float3 wo, float3 w
         f = diffuse + specular;
     }
 }
-ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, float3& f, float& pdf) {
-    switch (x.kind) {
+template <uint32_t M> ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, float3& f, float& pdf) {
+    switch (known_kind<M>(x.kind)) {
     case LOBE_TS_R: {
         float3 wh = normalize(wo + wi);
         const bool need_pdf = !(wo.z * wi.z <= 0.f);
@@ -479,9 +494,10 @@ ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, f
     }
     case LOBE_AS_BECK: as_eval_pdf<true>(x, wo, wi, want_f, f, pdf); return;
     case LOBE_AS_TROW: as_eval_pdf<false>(x, wo, wi, want_f, f, pdf); return;
+    case LOBE_FRESNEL: pdf = 0.f; f = grey(0.f); return;                 // specular: no value, no density (fresnel.rs:150-161)
     default:
-        pdf = lobe_pdf(x, wo, wi);
-        f = want_f ? lobe_eval(x, wo, wi) : grey(0.f);
+        pdf = lobe_pdf<M>(x, wo, wi);
+        f = want_f ? lobe_eval<M>(x, wo, wi) : grey(0.f);
         return;
     }
 }
@@ -492,27 +508,27 @@ template <bool BECK> ARN_DEV Sampled as_sample(const Lobe& x, float3 wo, float2 
         u.x *= 2.f;
         float3 wh = dist_sample_wh<BECK>(x.alpha, x.alpha, wo, u);
         wi = normalize(2.f * wh * dot(wo, wh) - wo);
-        if (wo.z * wi.z <= 0.f) { r.f = grey(0.f); r.wi = wi; r.pdf = as_pdf<BECK>(x, wo, wi); return r; }
+        if (wo.z * wi.z <= 0.f) { r.wi = wi; as_eval_pdf<BECK>(x, wo, wi, false, r.f, r.pdf); return r; }
     } else {
         u.x = (1.f - u.x) * 2.f;
         wi = sample_cosw_hemisphere(u);
         if (wi.z < 0.f) wi.z = -wi.z;
     }
-    r.f = as_eval<BECK>(x, wo, wi); r.wi = wi; r.pdf = as_pdf<BECK>(x, wo, wi);
+    r.wi = wi; as_eval_pdf<BECK>(x, wo, wi, true, r.f, r.pdf);
     return r;
 }
-ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
-    Sampled r; r.type = lobe_type(x.kind);
-    switch (x.kind) {
+template <uint32_t M> ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
+    Sampled r; r.type = lobe_type(known_kind<M>(x.kind));
+    switch (known_kind<M>(x.kind)) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
         float3 wi = sample_cosw_hemisphere(u);
         if (wo.z < 0.f) wi.z = -wi.z;
-        r.pdf = lobe_pdf(x, wo, wi); r.f = lobe_eval(x, wo, wi); r.wi = wi; return r;
+        lobe_eval_pdf<M>(x, wo, wi, true, r.f, r.pdf); r.wi = wi; return r;
     }
     case LOBE_LAMBERT_T: {
         float3 wi = sample_cosw_hemisphere(u);
         if (wo.z > 0.f) wi.z = -wi.z;
-        r.pdf = lobe_pdf(x, wo, wi); r.f = lobe_eval(x, wo, wi); r.wi = wi; return r;
+        lobe_eval_pdf<M>(x, wo, wi, true, r.f, r.pdf); r.wi = wi; return r;
     }
     case LOBE_FRESNEL: {                                                     // fresnel.rs:163-196
         float ct = cos_theta(wo);
@@ -537,14 +553,15 @@ ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
         r.pdf = dist_pdf<false>(x.alpha, x.alpha, wo, wh) / (4.f * dot(wo, wh));
         float3 wi = normalize(2.f * wh * dot(wo, wh) - wo);
         r.wi = wi;
-        r.f = (wo.z * wi.z <= 0.f) ? grey(0.f) : lobe_eval(x, wo, wi);
+        r.f = grey(0.f);
+        if (!(wo.z * wi.z <= 0.f)) { float unused; lobe_eval_pdf<M>(x, wo, wi, true, r.f, unused); }
         return r;
     }
     case LOBE_TS_T: {                                                        // :493-511
         float3 wh = dist_sample_wh<false>(x.alpha, x.alpha, wo, u);
         float eta = wo.z > 0.f ? x.c0 / x.c1 : x.c1 / x.c0;
         float3 wi;
-        if (refract(wo, wh, eta, wi)) { r.pdf = lobe_pdf(x, wo, wi); r.f = lobe_eval(x, wo, wi); r.wi = wi; }
+        if (refract(wo, wh, eta, wi)) { lobe_eval_pdf<M>(x, wo, wi, true, r.f, r.pdf); r.wi = wi; }
         else { r.f = grey(0.f); r.wi = f3(0.f, 0.f, 0.f); r.pdf = 0.f; }
         return r;
     }
@@ -612,7 +629,7 @@ ARN_DEV float3 bsdf_eval(const Bsdf& b, float3 wow, float3 wiw) {
     float3 ret = grey(0.f);
     for (int i = 0; i < b.n; i++) {
         uint32_t k = lobe_type(b.lobe[i].kind);
-        if ((is_reflection && (k & BXDF_REFLECTION)) || (!is_reflection && (k & BXDF_TRANSMISSION))) ret = ret + lobe_eval(b.lobe[i], wo, wi);
+        if ((is_reflection && (k & BXDF_REFLECTION)) || (!is_reflection && (k & BXDF_TRANSMISSION))) ret = ret + lobe_eval<LOBES_ALL>(b.lobe[i], wo, wi);
     }
     return ret;
 }
@@ -621,35 +638,35 @@ ARN_DEV float bsdf_pdf(const Bsdf& b, float3 wow, float3 wiw) {
     float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
     if (wo.z == 0.f) return 0.f;
     float pdfsum = 0.f;
-    for (int i = 0; i < b.n; i++) pdfsum += fmaxf(lobe_pdf(b.lobe[i], wo, wi), 0.f);
+    for (int i = 0; i < b.n; i++) pdfsum += fmaxf(lobe_pdf<LOBES_ALL>(b.lobe[i], wo, wi), 0.f);
     return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
 }
 // Bsdf::evaluate + Bsdf::pdf for the same pair of directions (the NEE light sample needs both, scene.rs:98-101)
-ARN_DEV void bsdf_eval_pdf(const Bsdf& b, float3 wow, float3 wiw, float3& f, float& pdf) {
+template <uint32_t M> ARN_DEV void bsdf_eval_pdf(const Bsdf& b, float3 wow, float3 wiw, float3& f, float& pdf) {
     float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
     bool is_reflection = dot(wow, b.ng) * dot(wiw, b.ng) > 0.f;
     f = grey(0.f);
     float pdfsum = 0.f;
     for (int i = 0; i < b.n; i++) {
-        uint32_t k = lobe_type(b.lobe[i].kind);
+        uint32_t k = lobe_type(known_kind<M>(b.lobe[i].kind));
         bool match = (is_reflection && (k & BXDF_REFLECTION)) || (!is_reflection && (k & BXDF_TRANSMISSION));
         float3 fi; float pi;
-        lobe_eval_pdf(b.lobe[i], wo, wi, match, fi, pi);
+        lobe_eval_pdf<M>(b.lobe[i], wo, wi, match, fi, pi);
         if (match) f = f + fi;
         pdfsum += fmaxf(pi, 0.f);
     }
     pdf = wo.z == 0.f ? 0.f : (b.n == 0 ? pdfsum : pdfsum / (float)b.n);
 }
 // Bsdf::evaluate_sampled with BXDF_ALL (bsdf.rs:100-145)
-ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
+template <uint32_t M> ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
     int match_count = b.n;
     if (match_count == 0) return ret;
     float3 wo = normalize(to_local(b, wow));
     int idx = (int)floorf(u.x * (float)match_count); if (idx > match_count - 1) idx = match_count - 1;
-    Sampled s = lobe_sample(b.lobe[idx], wo, u);
+    Sampled s = lobe_sample<M>(b.lobe[idx], wo, u);
     if (s.pdf == 0.f) return ret;
-    bool is_specular = (lobe_type(b.lobe[idx].kind) & BXDF_SPECULAR) != 0;
+    bool is_specular = (lobe_type(known_kind<M>(b.lobe[idx].kind)) & BXDF_SPECULAR) != 0;
     ret = s; ret.type = s.type & BXDF_ALL;
     float3 wi = ret.wi;
     ret.wi = to_parent(b, wi);
@@ -658,10 +675,10 @@ ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, float2 u) {
     bool is_reflection = dot(wow, b.ng) * dot(ret.wi, b.ng) > 0.f;
     float pdfsum = 0.f;
     for (int k = 0; k < b.n; k++) {
-        uint32_t t = lobe_type(b.lobe[k].kind);
+        uint32_t t = lobe_type(known_kind<M>(b.lobe[k].kind));
         if ((t & ret.type) && ((is_reflection && (t & BXDF_REFLECTION)) || (!is_reflection && (t & BXDF_TRANSMISSION)))) {
             float3 fk; float pk;
-            lobe_eval_pdf(b.lobe[k], wo, wi, true, fk, pk);
+            lobe_eval_pdf<M>(b.lobe[k], wo, wi, true, fk, pk);
             ret.f = ret.f + fk;
             pdfsum += fmaxf(pk, 0.f);
         }
@@ -704,8 +721,8 @@ template <bool DIFFUSE> ARN_DEV float bsdf_pdf_k(const Bsdf& b, float3 wow, floa
     if (b.n > 0) pdfsum += fmaxf(diffuse_lobe_pdf(wo, wi), 0.f);
     return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
 }
-template <bool DIFFUSE> ARN_DEV Sampled bsdf_sample_k(const Bsdf& b, float3 wow, float2 u) {
-    if (!DIFFUSE) return bsdf_sample(b, wow, u);
+template <bool DIFFUSE, uint32_t M> ARN_DEV Sampled bsdf_sample_k(const Bsdf& b, float3 wow, float2 u) {
+    if (!DIFFUSE) return bsdf_sample<M>(b, wow, u);
     Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
     if (b.n == 0) return ret;
     float3 wo = normalize(to_local(b, wow));

@@ -257,14 +257,22 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
 }
 
 // ---- K3 shade ------------------------------------------------------------------------------------
-// DIFFUSE = true: classes 1, 0 (matte: one Lambert / Oren–Nayar lobe, inlined fast path, fewer registers);
-// DIFFUSE = false: classes 3, 2, 4 (glass, plastic, translucent: generic lobe code).
-template <bool DIFFUSE>
-__global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
-    // One launch over the concatenation of the class queues, each padded to a multiple of 32 so that
-    // every warp shades ONE material class; heavy classes (glass, plastic) first, so that the tail of
-    // the launch is made of cheap Lambert work and near-empty classes cost no launch of their own.
-    const uint32_t ORDER = DIFFUSE ? 0x55501u : 0x55423u;    // nibble k = class shaded k-th (5 = none): 1, 0 | 3, 2, 4
+// One instance per group of material classes (hits arrive sorted by class, so a launch only meets its own lobes):
+//   SHADE_DIFFUSE  classes 1, 0  matte: one Lambert / Oren–Nayar lobe, inlined fast path, fewer registers
+//   SHADE_GLASS    class 3       Fresnel + Torrance–Sparrow reflection / transmission lobes
+//   SHADE_PLASTIC  class 2       one Ashikhmin–Shirley (Beckmann) lobe
+//   SHADE_GENERIC  class 4       translucent, and anything else: every lobe kind
+#define SHADE_GENERIC 0
+#define SHADE_DIFFUSE 1
+#define SHADE_PLASTIC 2
+#define SHADE_GLASS 3
+template <int KIND>
+__global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
+    constexpr bool DIFFUSE = KIND == SHADE_DIFFUSE;
+    constexpr uint32_t LOBES = KIND == SHADE_PLASTIC ? LOBES_PLASTIC : (KIND == SHADE_GLASS ? LOBES_GLASS : LOBES_ALL);
+    // One launch over the concatenation of this instance's class queues, each padded to a multiple of 32 so that
+    // every warp shades ONE material class.
+    const uint32_t ORDER = KIND == SHADE_DIFFUSE ? 0x55501u : (KIND == SHADE_GLASS ? 0x55553u : (KIND == SHADE_PLASTIC ? 0x55552u : 0x55554u));   // nibble k = class shaded k-th (5 = none)
     uint32_t seg_start[ARN_NCLS + 1];
     seg_start[0] = 0;
 #pragma unroll
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                     if (!(ls.pdf == 0.f || is_black(ls.radiance))) {
                         float3 f; float spdf;
                         if (DIFFUSE) { f = bsdf_eval_k<true>(bsdf, s.wo, wi) * fabsf(dot(wi, s.ns)); spdf = bsdf_pdf_k<true>(bsdf, s.wo, wi); }
-                        else { bsdf_eval_pdf(bsdf, s.wo, wi, f, spdf); f = f * fabsf(dot(wi, s.ns)); }
+                        else { bsdf_eval_pdf<LOBES>(bsdf, s.wo, wi, f, spdf); f = f * fabsf(dot(wi, s.ns)); }
                         if (spdf == 0.f) f = grey(0.f);
                         float weight = delta ? 1.f : power_heuristic(ls.pdf, spdf);    // is_delta: no MIS weight (scene.rs:107-115); x * 1 is exact
                         A1 = ls.radiance * f * weight / ls.pdf;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                     // samples stop at lpdf == 0, specular ones trace a ray that can only add black.
                     float3 A2 = grey(0.f);
                     Sampled bs; bs.f = grey(0.f); bs.wi = f3(0.f, 1.f, 0.f); bs.pdf = 0.f; bs.type = 0;
-                    if (!delta) bs = bsdf_sample_k<DIFFUSE>(bsdf, s.wo, uscatter);
+                    if (!delta) bs = bsdf_sample_k<DIFFUSE, LOBES>(bsdf, s.wo, uscatter);
                     float3 f2v = bs.f * fabsf(dot(bs.wi, s.ns));
                     if (!is_black(f2v) && bs.pdf > 0.f) {
                         float weight = 1.f; bool skip = false;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : 
                 }
                 // sample the BSDF for the next direction (pt.rs:92-107)
                 float3 wo = -raydir;
-                Sampled bs = bsdf_sample_k<DIFFUSE>(bsdf, wo, sm.next_2d());
+                Sampled bs = bsdf_sample_k<DIFFUSE, LOBES>(bsdf, wo, sm.next_2d());
                 spec = (bs.type & BXDF_SPECULAR) != 0;
                 alive = !(is_black(bs.f) || bs.pdf == 0.f);
                 if (alive) {

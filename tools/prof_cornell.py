@@ -7,7 +7,10 @@ res, sx = int(sys.argv[1]), int(sys.argv[2])
 hs, cam, film, smp, prm = scenes.cornell_scene(res, res, sx, sx)
 if len(sys.argv) > 3:
     prm = api.make_pt_params(max_depth=int(sys.argv[3]))
-ctx = api.Context(0); sc = ctx.upload(hs.desc())
+ctx = api.Context(0)
+if os.environ.get("GPU_BUILD") == "1":        # tree from arn_bvh_build_gpu (LBVH) instead of the reference's SAH tree
+    hs.build_gpu(ctx)
+sc = ctx.upload(hs.desc())
 reps = int(os.environ.get("REPS", "1"))
 for _ in range(reps):
     f, st = sc.render_pt(cam, film, smp, prm)
