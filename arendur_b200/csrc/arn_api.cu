@@ -19,6 +19,8 @@
 
 using namespace arn;
 
+#define ARN_MAX_PIPES 8
+
 namespace {
 std::string g_last_error;
 std::mutex g_err_mutex;
@@ -30,12 +32,12 @@ struct arn_ctx {
     int sm_count = 0;
     std::string err;
     std::mutex mu;
-    // wavefront buffers (allocated lazily, sized to wave capacity)
-    size_t wave_cap = 0;
-    PathBuf pb{};
-    Queues q{};
-    void* pool = nullptr;
-    size_t pool_bytes = 0;
+    // wave pipelines: each owns a stream and a set of wavefront buffers (allocated lazily, sized to the wave
+    // capacity).  Consecutive waves of a render go to consecutive pipelines and run concurrently, so the thin
+    // late-bounce launches of one wave overlap the wide early launches of the next.  pipes[0] runs on `stream`.
+    struct Pipe { cudaStream_t stream = nullptr; size_t wave_cap = 0; PathBuf pb{}; Queues q{}; void* pool = nullptr; cudaEvent_t done = nullptr; };
+    Pipe pipes[ARN_MAX_PIPES];
+    int opt_pipes = 4;
     // tile tables
     int4* d_tile_rect = nullptr; unsigned long long* d_tile_prefix = nullptr; size_t tile_cap = 0;
     // event pool for per-kernel timing
@@ -93,9 +95,9 @@ cudaEvent_t get_event(arn_ctx* c, size_t i) {
     return c->events[i];
 }
 
-int ensure_wave(arn_ctx* c, size_t cap) {
+int ensure_wave(arn_ctx* ctx, arn_ctx::Pipe* c, size_t cap) {
     if (c->wave_cap >= cap) return ARN_OK;
-    if (c->pool) { cudaFree(c->pool); c->pool = nullptr; }
+    if (c->pool) { cudaFree(c->pool); c->pool = nullptr; c->wave_cap = 0; }
     // one pool, carved into 256-byte aligned SoA streams
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -107,8 +109,7 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4), o_qs = carve(cap * 4), o_qm = carve(cap * 4);
     size_t o_cls[ARN_NCLS]; for (int k = 0; k < ARN_NCLS; k++) o_cls[k] = carve(cap * 4);
     size_t o_counts = carve(64), o_stats = carve(64);
-    CUDA_TRY(c, cudaMalloc(&c->pool, off));
-    c->pool_bytes = off;
+    CUDA_TRY(ctx, cudaMalloc(&c->pool, off));
     char* b = (char*)c->pool;
     c->pb.ray_o = (float4*)(b + o_ray_o); c->pb.ray_d = (float4*)(b + o_ray_d); c->pb.beta = (float4*)(b + o_beta); c->pb.L = (float4*)(b + o_L);
     c->pb.pfilm = (float2*)(b + o_pfilm); c->pb.pix = (uint32_t*)(b + o_pix); c->pb.smp = (uint32_t*)(b + o_smp); c->pb.st = (uint32_t*)(b + o_st);
@@ -123,10 +124,10 @@ int ensure_wave(arn_ctx* c, size_t cap) {
     return ARN_OK;
 }
 
-size_t wave_capacity_default() {
+size_t wave_capacity_default(int pipes) {
     const char* e = std::getenv("ARN_WAVE");
     if (e) { long v = std::atol(e); if (v >= 1024) return (size_t)v; }
-    return (size_t)1 << 20;
+    return pipes >= 3 ? (size_t)1 << 19 : (size_t)1 << 20;
 }
 
 }  // namespace
@@ -155,6 +156,10 @@ int arn_ctx_create(int device, arn_ctx** out) {
     if (prop.major != 10) { delete c; return set_err(nullptr, ARN_E_UNSUPPORTED, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor)); }
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->pipes[0].stream = c->stream;
+    for (int i = 1; i < ARN_MAX_PIPES; i++) CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->pipes[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ARN_MAX_PIPES; i++) CUDA_TRY(nullptr, cudaEventCreateWithFlags(&c->pipes[i].done, cudaEventDisableTiming));
+    { const char* e = std::getenv("ARN_PIPES"); if (e) { int v = std::atoi(e); if (v >= 1 && v <= ARN_MAX_PIPES) c->opt_pipes = v; } }
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
@@ -178,7 +183,12 @@ void arn_ctx_destroy(arn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->pool) cudaFree(c->pool);
+    for (int i = 0; i < ARN_MAX_PIPES; i++) {
+        if (c->pipes[i].stream) cudaStreamSynchronize(c->pipes[i].stream);
+        if (c->pipes[i].pool) cudaFree(c->pipes[i].pool);
+        if (c->pipes[i].done) cudaEventDestroy(c->pipes[i].done);
+        if (i > 0 && c->pipes[i].stream) cudaStreamDestroy(c->pipes[i].stream);
+    }
     if (c->d_tile_rect) cudaFree(c->d_tile_rect);
     if (c->d_tile_prefix) cudaFree(c->d_tile_prefix);
     if (c->d_rays) cudaFree(c->d_rays);
@@ -194,6 +204,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     switch (option) {
     case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
     case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2 or 4"); c->opt_width = (int)value; return ARN_OK;
+    case ARN_OPT_PIPELINES: if (value < 1 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 1..8"); c->opt_pipes = (int)value; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -558,9 +569,13 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     CUDA_TRY(c, cudaMemcpyAsync(c->d_tile_prefix, prefix.data(), prefix.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
 
     unsigned long long total = prefix.back() * (unsigned long long)(s1 - s0);
-    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default();
+    // measured on C3 (tools/prof_cornell.py): 1 pipeline x 2^20 samples 400.8 ms, 2 x 2^20 350.5, 4 x 2^20 336.2, 4 x 2^19 330.8 (= 8 x 2^19)
+    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default(c->opt_count ? 1 : c->opt_pipes);
     if ((unsigned long long)cap > total) cap = (size_t)((total + ARN_BLOCK - 1) / ARN_BLOCK * ARN_BLOCK);
-    int rc = ensure_wave(c, cap); if (rc != ARN_OK) return rc;
+    const unsigned long long n_waves = (total + cap - 1) / cap;
+    // per-kernel event timing needs serial launches: it is only taken with one pipeline (ARN_OPT_PIPELINES = 1)
+    const int np = (int)std::min<unsigned long long>((unsigned long long)(c->opt_count ? 1 : c->opt_pipes), n_waves);
+    for (int i = 0; i < np; i++) { int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc; }
 
     WaveParams wp;
     std::memcpy(wp.raster_view, cam->raster_view, 64); std::memcpy(wp.view_parent, cam->view_parent, 64);
@@ -579,26 +594,32 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     wp.n_tiles = (uint32_t)rects.size(); wp.tile_rect = c->d_tile_rect; wp.tile_prefix = c->d_tile_prefix;
     wp.spp_begin = s0; wp.spp_count = s1 - s0;
 
-    CUDA_TRY(c, cudaMemsetAsync(c->q.stats, 0, 64, c->stream));
     size_t ev = 0;
     cudaEvent_t e_begin = get_event(c, ev++), e_end = get_event(c, ev++);
-    const bool time_kernels = stats != nullptr;
+    const bool time_kernels = stats != nullptr && np == 1;
     std::vector<std::pair<size_t, int>> ext_events;      // (event index, bounce)
     uint64_t launches = 0;
     cudaEventRecord(e_begin, c->stream);
-    for (unsigned long long base = 0; base < total; base += cap) {
+    for (int i = 0; i < np; i++) {
+        if (i > 0) cudaStreamWaitEvent(c->pipes[i].stream, e_begin, 0);       // after the tile tables / whatever the caller queued
+        CUDA_TRY(c, cudaMemsetAsync(c->pipes[i].q.stats, 0, 64, c->pipes[i].stream));
+    }
+    const bool wide = use_wide(s);
+    unsigned long long wave = 0;
+    for (unsigned long long base = 0; base < total; base += cap, wave++) {
+        arn_ctx::Pipe& P = c->pipes[wave % (unsigned long long)np];
+        cudaStream_t st = P.stream;
         uint32_t n = (uint32_t)std::min<unsigned long long>(cap, total - base);
-        k_begin_wave<<<1, 1, 0, c->stream>>>(c->q, n);
-        k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, base, n);
+        k_begin_wave<<<1, 1, 0, st>>>(P.q, n);
+        k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, base, n);
         launches += 2;
         int cur = 0;
-        const bool wide = use_wide(s);
         auto trace = [&](int first, int bounce) {
-            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), c->stream); ext_events.push_back({i0, bounce}); }
-            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
-            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
-            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, c->stream>>>(s->dev, c->pb, c->q, cur, first);
-            if (time_kernels) cudaEventRecord(get_event(c, ev++), c->stream);
+            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), st); ext_events.push_back({i0, bounce}); }
+            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
+            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
+            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
+            if (time_kernels) cudaEventRecord(get_event(c, ev++), st);
         };
         trace(1, 0);                                               // camera rays
         launches += 1;
@@ -606,32 +627,37 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         for (uint32_t b = 0; b < prm->max_depth; b++) {
             // shade(b): consumes the class queues, fills active[cur^1] + connect / shadow / light-ray queues
             // heavy classes first: the tail of the bounce is cheap Lambert work
-            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
-            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
-            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
-            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, c->stream>>>(s->dev, wp, c->pb, c->q, cur); launches++; }
-            k_reset<<<1, 1, 0, c->stream>>>(c->q, CLS_MASK | (1u << cur));
+            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
+            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
+            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
+            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
+            k_reset<<<1, 1, 0, st>>>(P.q, CLS_MASK | (1u << cur));
             cur ^= 1;
             trace(0, (int)b + 1);                                  // path rays of bounce b+1, shadow + light rays of bounce b
-            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, c->stream>>>(c->pb, c->q);
-            k_reset<<<1, 1, 0, c->stream>>>(c->q, NEE_MASK);
+            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, st>>>(P.pb, P.q);
+            k_reset<<<1, 1, 0, st>>>(P.q, NEE_MASK);
             launches += 4;
         }
         if (film->filter_radius_x <= 4.f && film->filter_radius_y <= 4.f && film->filter_radius_x >= 0.5f && film->filter_radius_y >= 0.5f) {
             unsigned long long npix = (base + n - 1) / wp.spp_count - base / wp.spp_count + 1;
             int blocks = (int)std::min<unsigned long long>((unsigned long long)c->g_accum_px, (npix * 32 + ARN_BLOCK - 1) / ARN_BLOCK);
-            k_accumulate_px<<<std::max(blocks, 1), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, base, n);
+            k_accumulate_px<<<std::max(blocks, 1), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, (float4*)film_dev, base, n);
         } else
-        k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, c->q, (float4*)film_dev, n);
+        k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, (float4*)film_dev, n);
         launches += 1;
-        if (radiance_dev) { k_store_radiance<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, c->stream>>>(wp, c->pb, radiance_dev, n); launches += 1; }
+        if (radiance_dev) { k_store_radiance<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, radiance_dev, n); launches += 1; }
         CUDA_TRY(c, cudaGetLastError());
     }
+    // join: everything the pipelines did is ordered before whatever follows on the context's stream
+    for (int i = 1; i < np; i++) { cudaEventRecord(c->pipes[i].done, c->pipes[i].stream); cudaStreamWaitEvent(c->stream, c->pipes[i].done, 0); }
     cudaEventRecord(e_end, c->stream);
     if (stats) {
-        unsigned long long hs[8];
-        CUDA_TRY(c, cudaMemcpyAsync(hs, c->q.stats, 64, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        unsigned long long hs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, one[8];
+        for (int i = 0; i < np; i++) {
+            CUDA_TRY(c, cudaMemcpyAsync(one, c->pipes[i].q.stats, 64, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 8; k++) hs[k] += one[k];
+        }
         std::memset(stats, 0, sizeof *stats);
         stats->camera_rays = total; stats->extend_rays = hs[0]; stats->shadow_rays = hs[1]; stats->mis_rays = hs[2];
         stats->invalid_samples = hs[3]; stats->extend_bounce_rays = hs[4]; stats->kernel_launches = launches;

@@ -27,6 +27,10 @@ if not torch.cuda.is_available():
 ctx = ctx0 if gpu_build else api.Context(0)
 t = time.time(); sc = ctx.upload(d); print(f"upload {time.time()-t:.1f} s")
 for rep in range(2):
+    f, st_fast = sc.render_pt(cam, film, smp, prm)
+print(f"c4 render {res}^2 x {sx*sx} spp, default pipelines: {st_fast.gpu_ms:.1f} ms, all rays {(st_fast.extend_rays + st_fast.shadow_rays + st_fast.mis_rays)/st_fast.gpu_ms/1e3:.1f} Mrays/s")
+ctx.set_option(L.ARN_OPT_PIPELINES, 1)          # per-kernel timings need serial launches
+for rep in range(2):
     f, st = sc.render_pt(cam, film, smp, prm)
 rays = st.extend_rays + st.shadow_rays + st.mis_rays
 print(f"c4 render {res}^2 x {sx*sx} spp: {st.gpu_ms:.1f} ms, all rays {rays/st.gpu_ms/1e3:.1f} Mrays/s; extend {st.extend_rays} rays in {st.extend_ms:.1f} ms = {st.extend_rays/st.extend_ms/1e3:.1f} Mrays/s; "

@@ -15,4 +15,4 @@ reps = int(os.environ.get("REPS", "1"))
 for _ in range(reps):
     f, st = sc.render_pt(cam, film, smp, prm)
 rays = st.extend_rays + st.shadow_rays + st.mis_rays
-print(f"cornell {res}^2 x {sx*sx}spp: {st.gpu_ms:.2f} ms, {rays/st.gpu_ms/1e3:.1f} Mrays/s, extend {st.extend_ms:.2f} ms / {st.extend_rays} rays, shadow {st.shadow_rays} mis {st.mis_rays}")
+print(f"cornell {res}^2 x {sx*sx}spp: {st.gpu_ms:.2f} ms, {rays/st.gpu_ms/1e3:.1f} Mrays/s, extend {st.extend_ms:.2f} ms (needs ARN_PIPES=1) / {st.extend_rays} rays, shadow {st.shadow_rays} mis {st.mis_rays}")
