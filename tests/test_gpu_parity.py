@@ -427,6 +427,19 @@ def test_sample_ranges_waves_tile_grids_and_roulette(ctx):
     ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
     assert np.array_equal(rad_small, rad_full) and np.allclose(f_small, full, rtol=1e-5, atol=1e-6)
     assert st_small.kernel_launches > 10 * st_full.kernel_launches
+    # (2b) 1, 2 and 8 concurrent wave pipelines over those tiny waves: same samples, same film up to addition order;
+    # per-kernel timings only exist with serial launches
+    for pipes in (1, 2, 8):
+        ctx.set_option(L.ARN_OPT_PIPELINES, pipes)
+        ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 2048)
+        f_p, rad_p, st_p = sc.render_pt_samples(cam, film, smp, prm)
+        assert np.array_equal(rad_p, rad_full) and np.allclose(f_p, full, rtol=1e-5, atol=1e-6), pipes
+        assert (st_p.extend_rays, st_p.shadow_rays, st_p.mis_rays) == (st_full.extend_rays, st_full.shadow_rays, st_full.mis_rays)
+        assert (st_p.extend_ms > 0) == (pipes == 1)
+    ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
+    ctx.set_option(L.ARN_OPT_PIPELINES, 4)
+    with pytest.raises(api.ArnError):
+        ctx.set_option(L.ARN_OPT_PIPELINES, 9)
     # (3) 5 x 4 tile grid over 3 ranks, against the oracle's same partition
     total = np.zeros_like(full)
     for rank in range(3):
