@@ -535,7 +535,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     if (prm->max_depth == 0 || prm->max_depth > 80) return set_err(c, ARN_E_INVALID, "arn_render_pt: max_depth must be in 1..80");
     uint32_t world = prm->world_size ? prm->world_size : 1;
     if (prm->rank >= world) return set_err(c, ARN_E_INVALID, "arn_render_pt: rank >= world_size");
-    // Film::spawn_tiles(nx, ny) (filming/film.rs:104-135), ix-major order; this rank takes t % world == rank
+    // Film::spawn_tiles(nx, ny) (filming/film.rs:104-135), ix-major order; this rank takes the tiles with (ix + iy) % world == rank
+    // (diagonal interleave: every rank gets a share of every row and column of the picture, so the costly regions are spread)
     long nx = prm->tiles_x ? prm->tiles_x : 16, ny = prm->tiles_y ? prm->tiles_y : 16;
     long dx = cw / nx, dy = chh / ny;
     if (dx <= 0 || dy <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: crop window smaller than the tile grid (spawn_tiles divides by zero)");
@@ -551,7 +552,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             long gy0 = std::max(iy * dy - ry, (long)film->crop_min_y), gy1 = std::min(iy * dy + cdy + ry, (long)film->crop_max_y);
             if (gx0 > gx1 || gy0 > gy1) return set_err(c, ARN_E_INVALID, "arn_render_pt: a film tile does not meet the crop window (Film::spawn_tiles lays tiles out from (0,0) and panics on this, film.rs:118-129)");
         }
-        if ((uint32_t)(t % world) != prm->rank) continue;
+        if ((uint32_t)((ix + iy) % (long)world) != prm->rank) continue;
         rects.push_back(make_int4((int)(ix * dx), (int)(iy * dy), (int)cdx, (int)cdy));
         prefix.push_back(prefix.back() + (unsigned long long)cdx * (unsigned long long)cdy);
     }

@@ -6,7 +6,7 @@ full PT bounce loop (depth 8, area-light NEE + MIS, Russian roulette), 1024 spp.
 pass of the whole hot path (generate -> extend -> shade -> connect -> accumulate) over a batch of
 64 spp x 1024 x 1024 camera samples (sample indices [64k, 64k+64)); the default 16 timed steps
 are exactly the 1024 spp of C3 accumulated into one film.  At N GPUs the same frame is
-tile-partitioned (16x16 tiles, t % N) and every step renders 64*N spp, i.e. per-GPU work is fixed
+tile-partitioned (16x16 tiles, (ix + iy) % N) and every step renders 64*N spp, i.e. per-GPU work is fixed
 ("weak"); the per-rank films are summed with one NCCL reduce per step inside the timed region
 (Film::merge_into semantics).
 
@@ -302,7 +302,7 @@ def main():
             "metric": "Mrays/s (primary + incoherent bounce: every BVH traversal) on the Cornell box", "value": rays_all / (total_ms_max * 1e-3) / 1e6, "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_step": spp_step, "tiles": "16x16, t % N", "l2": "256 MB flush write between timed steps; wave buffers (4 x 124 MB) also exceed L2", "wave_pipelines": PIPELINES,
+            "config": {"workload": WORKLOAD, "spp_per_step": spp_step, "tiles": "16x16, (ix + iy) % N", "l2": "256 MB flush write between timed steps; wave buffers (4 x 124 MB) also exceed L2", "wave_pipelines": PIPELINES,
                        "film_reduce": "ncclReduce per step" if world > 1 else "none (1 GPU)"},
             "spp_per_s": samples_all / (total_ms_max * 1e-3),
             "rays_per_sample": rays_all / max(1.0, samples_all),

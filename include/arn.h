@@ -196,7 +196,7 @@ typedef struct arn_pt_params {
     uint32_t min_depth;
     float    rr_threshold;
     uint32_t tiles_x, tiles_y;   /* tile grid for multi-GPU partitioning (16,16)       */
-    uint32_t rank, world_size;   /* this context renders tiles t with t % world == rank */
+    uint32_t rank, world_size;   /* this context renders the tiles (ix, iy) with (ix + iy) % world == rank */
     uint32_t spp_begin, spp_end; /* sample index range to render, [0, spp) for all      */
 } arn_pt_params;
 

@@ -373,7 +373,7 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
         for (;;) {
             size_t ti = next_tile.fetch_add(1);
             if (ti >= tiles.size()) break;
-            if (ti % world != prm.rank) continue;
+            if (((ti / (size_t)ny) + (ti % (size_t)ny)) % world != prm.rank) continue;   // tile (ix, iy) -> rank (ix + iy) % world: diagonal interleave
             FilmTile& tile = tiles[ti];
             ParitySampler sampler; sampler.seed = smp.seed; sampler.spp = spp;
             for (long y = tile.bounding.y0; y < tile.bounding.y1; y++) for (long x = tile.bounding.x0; x < tile.bounding.x1; x++) {
