@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 RES = 1024
 SPP_TOTAL_X = 32          # 32 x 32 = 1024 spp
 SPP_PER_STEP = 64
+TILES = tuple(int(v) for v in os.environ.get("BENCH_TILES", "16,16").split(","))   # Film::spawn_tiles grid (pt.rs:131 uses 16 x 16)
 PIPELINES = 4            # concurrent wave pipelines of the timed region (the library default; ARN_OPT_PIPELINES)
 WORKLOAD = "C3: Cornell box 1024x1024, PT depth 8 + area-light NEE/MIS, 1024 spp (64 spp per step)"
 
@@ -187,7 +188,7 @@ def main():
 
     def params(step):
         k = step % n_slices
-        return api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=k * spp_step, spp_end=(k + 1) * spp_step)
+        return api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=k * spp_step, spp_end=(k + 1) * spp_step, tiles=TILES)
 
     def barrier():
         if dist is not None:
@@ -302,7 +303,7 @@ def main():
             "metric": "Mrays/s (primary + incoherent bounce: every BVH traversal) on the Cornell box", "value": rays_all / (total_ms_max * 1e-3) / 1e6, "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_step": spp_step, "tiles": "16x16, (ix + iy) % N", "l2": "256 MB flush write between timed steps; wave buffers (4 x 124 MB) also exceed L2", "wave_pipelines": PIPELINES,
+            "config": {"workload": WORKLOAD, "spp_per_step": spp_step, "tiles": f"{TILES[0]}x{TILES[1]}, (ix + iy) % N", "l2": "256 MB flush write between timed steps; wave buffers (4 x 124 MB) also exceed L2", "wave_pipelines": PIPELINES,
                        "film_reduce": "ncclReduce per step" if world > 1 else "none (1 GPU)"},
             "spp_per_s": samples_all / (total_ms_max * 1e-3),
             "rays_per_sample": rays_all / max(1.0, samples_all),
