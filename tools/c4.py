@@ -42,3 +42,11 @@ bpr = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_sph
 print(f"Nn/ray {stc.extend_nodes/stc.extend_rays:.1f} Nt/ray {stc.extend_tris/stc.extend_rays:.2f} bytes/ray {bpr:.0f} -> extend algorithmic {bpr*st.extend_rays/st.extend_ms/1e6:.0f} GB/s of 6457 measured")
 g, _ = api.film_finalize(f)
 print("image mean", g.reshape(-1, 3).mean(0), "finite", np.isfinite(g).all())
+if os.environ.get("C4_CPU") == "1":        # CPU restatement on a bounded sample: the same view at 256 x 256, 1 spp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    osc = O.OracleScene(d)
+    cam2 = api.make_camera(np.float32([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 3.5, 1]]), (-1.0, -1.0, 1.0, 1.0), 0.1, 1000.0, 1.2707964, 256, 256)
+    t = time.time(); _, ost, _ = osc.render_pt(cam2, api.make_film(256, 256), api.make_sampler(1, 1, 8, 0), prm, nthreads=os.cpu_count()); dt = time.time() - t
+    orays = ost.extend_rays + ost.shadow_rays + ost.mis_rays
+    print(f"c4 CPU restatement, {os.cpu_count()} threads, 256^2 x 1 spp sample: {dt:.2f} s, {orays/dt/1e6:.2f} Mrays/s")
