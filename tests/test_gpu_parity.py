@@ -563,3 +563,61 @@ def test_full_cornell_render_matches_reference_png(ctx):
     assert np.quantile(err, 0.99) < 0.025 and err.max() < 0.05, (np.quantile(err, 0.99), err.max())
     assert np.abs(mine - ref).mean() < 0.5                                 # 8-bit levels; measured 0.23 (max 2.4)
     sc.close()
+
+
+def test_sphere_only_scene_bit_exact(ctx):
+    """No triangle at all: 60 spheres — full, z-clipped, phi-clipped, bare and under rotation / translation / non-uniform
+    scale — of every material kind, two of them emissive, plus a spot light (shape/sphere.rs:133-317,
+    component/transformed.rs:70-158, component/shape.rs:74-168).  Hits and every camera sample equal the oracle's."""
+    rng = np.random.default_rng(17)
+    hs = api.HostScene()
+    hs.add_light(api.spot_light((0, 6, 0), (0, -1, 0.1), (30, 30, 30), 1.0, 0.6))
+    mats = [hs.add_material(m) for m in (
+        api.material(L.ARN_MAT_MATTE, kd=(0.7, 0.6, 0.5)), api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.6, 0.7), sigma=20.0),
+        api.material(L.ARN_MAT_PLASTIC, kd=(0.4, 0.3, 0.2), ks=(0.5, 0.5, 0.5), roughness=0.1),
+        api.material(L.ARN_MAT_GLASS, kd=(0.6, 0.6, 0.6), ks=(0.9, 0.9, 0.9), roughness=0.05, eta=1.5),
+        api.material(L.ARN_MAT_TRANSLUCENT, kd=(0.5, 0.5, 0.4), ks=(0.3, 0.3, 0.3), roughness=0.3, dissolve=0.5))]
+
+    def rot(axis, a):
+        c, s_ = math.cos(a), math.sin(a)
+        m = np.eye(4, dtype=np.float64)
+        i, j = [(1, 2), (0, 2), (0, 1)][axis]
+        m[i, i], m[i, j], m[j, i], m[j, j] = c, -s_, s_, c
+        return m
+
+    for k in range(60):
+        radius = float(rng.uniform(0.3, 0.9))
+        zmin = -radius if k % 3 else float(rng.uniform(-0.8, -0.1)) * radius
+        zmax = radius if k % 4 else float(rng.uniform(0.2, 0.9)) * radius
+        phimax = 2 * math.pi if k % 5 else float(rng.uniform(1.0, 5.5))
+        m = np.eye(4)
+        m[:3, 3] = rng.uniform([-4, 0.5, -4], [4, 4, 4])
+        if k % 2:
+            m = m @ rot(int(rng.integers(0, 3)), float(rng.uniform(0, 6.28))) @ np.diag([*rng.uniform(0.6, 1.5, 3), 1.0])
+        tr = None if k % 7 == 0 else m.T.astype(np.float32)              # rows = columns of the matrix; every 7th sphere is bare (at the origin)
+        em = (9.0, 8.0, 7.0) if k in (3, 11) else None
+        hs.add_sphere(radius if tr is not None else 0.25, zmin if tr is not None else -0.25, zmax if tr is not None else 0.25, phimax, mats[k % 5], emission=em, transform=tr)
+    # a big ground sphere
+    g = np.eye(4); g[1, 3] = -200.0
+    hs.add_sphere(200.0, -200.0, 200.0, 2 * math.pi, mats[0], transform=g.T.astype(np.float32))
+    hs.build()
+    d = hs.desc()
+    assert d.n_triangles == 0 and d.n_spheres == 61
+    view_parent = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, -1, 0], [0, 2.0, 10.0, 1]], np.float32)
+    cam = api.make_camera(np.linalg.inv(view_parent.T).T.astype(np.float32).reshape(-1), (-1.2, -0.9, 1.2, 0.9), 0.1, 1000.0, 1.0, 96, 72)
+    film, smp, prm = api.make_film(96, 72), api.make_sampler(2, 2, 8, 5), api.make_pt_params(max_depth=6)
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    n = 100_000
+    rays = np.zeros(n, api.RAY_DTYPE)
+    rays["o"] = rng.uniform([-5, 0.2, -5], [5, 5, 8], (n, 3)).astype(np.float32)
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    rays["d"] = v.astype(np.float32); rays["tmax"] = np.inf
+    gh, oh = sc.intersect_closest(rays), osc.intersect_closest(rays)
+    assert (oh["prim_id"] >= 0).mean() > 0.4
+    _assert_hits_equal(gh, oh)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.mean() >= 1.0 - 2e-4, f"{(~same).sum()} of {same.size} samples differ"
+    assert (orad[..., :3].max(-1) > 0).mean() > 0.05          # a dark scene: one spot cone and two small emitters
+    sc.close(); osc.close()
