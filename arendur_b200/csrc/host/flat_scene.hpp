@@ -94,8 +94,10 @@ public:
     }
 
     // Sphere::new (shape/sphere.rs:133-156) + ShapedPrimitive (+ TransformedComposable)
+    // `in_lights` = false: an emissive primitive that arencli does not push to `lights` (an instance made by
+    // ComponentDesc::Transformed, arencli.rs:162-181): it shows its emission when hit, but is never sampled.
     int add_sphere(float radius, float zmin, float zmax, float phimax, uint32_t material, const float* emission3,
-                   const float* transform16) {
+                   const float* transform16, bool in_lights = true, bool* transform_kept = nullptr) {
         if (!(radius > 0.f)) return fail(ARN_E_INVALID, "Sphere radius should be positive");
         if (!(zmin < zmax)) return fail(ARN_E_INVALID, "zmin should be lower than zmax");
         if (material >= materials.size()) return fail(ARN_E_INVALID, "sphere material id out of range");
@@ -115,12 +117,13 @@ public:
             // arencli.rs:133-146: a non-invertible transform silently degrades to the bare primitive
             if (invert(lp, &pl)) s.has_transform = 1; else { lp = Mat4::identity(); pl = Mat4::identity(); }
         }
+        if (transform_kept) *transform_kept = s.has_transform != 0;
         lp.to_array(s.local_parent); pl.to_array(s.parent_local);
         uint32_t sid = (uint32_t)spheres.size();
         spheres.push_back(s);
         uint32_t comp = (uint32_t)prims.size();
         prims.push_back(ARN_PRIM_SPHERE | sid);
-        if (s.emissive) light_prims.push_back(comp);                             // `lights.push(sp.clone())`
+        if (s.emissive && in_lights) light_prims.push_back(comp);                // `lights.push(sp.clone())`
         built = false;
         return (int)comp;
     }

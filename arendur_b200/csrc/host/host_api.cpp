@@ -319,12 +319,32 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
     std::string base = base_dir ? std::string(base_dir) : std::string();
     if (!base.empty() && base.back() != '/') base.push_back('/');
     std::map<std::string, int> materials;
+    struct ShapedRecord { float radius, zmin, zmax, phimax; uint32_t material; bool emissive; float emission[3]; bool transformed; };
+    std::map<std::string, ShapedRecord> shaped_by_name;          // `primitives` (arencli.rs:90): what a Transformed component may refer to
     // pass 1: meshes in file order; pass 2: shaped primitives in file order (fixed component order)
     for (int pass = 0; pass < 2; pass++) for (const Json& c : comps->arr) {
         const Json* value = c.get("value");
         if (!value || value->is_null()) continue;                         // "ignoring empty component"
         const Json* mesh = value->get("Mesh"); const Json* shaped = value->get("Shaped");
-        if (value->get("Transformed")) return fs.fail(ARN_E_UNSUPPORTED, "Transformed components (instancing of named primitives) are not flattened yet");
+        const Json* transformed = value->get("Transformed");
+        if (pass == 1 && transformed) {
+            // ComponentDesc::Transformed{transform, original} (arencli.rs:162-181): TransformedComposable over a primitive
+            // already in `primitives`.  One level — an instance of a BARE sphere — is exactly a transformed sphere; an
+            // instance of an already transformed primitive would round-trip rays through two matrices in turn, which the
+            // flattened sphere record does not model.  The instance is not pushed to `lights` even when it is emissive.
+            const Json* orig = transformed->get("original"); const Json* tr = transformed->get("transform");
+            float t16[16];
+            if (!orig || orig->kind != Json::Str || !tr || !json_matrix(*tr, t16)) return fs.fail(ARN_E_INVALID, "malformed Transformed component");
+            { Mat4 m = Mat4::from_array(t16), inv; if (!invert(m, &inv)) continue; }          // "load transformed failed, invalid matrix invert"
+            auto it = shaped_by_name.find(orig->str);
+            if (it == shaped_by_name.end()) continue;                                      // "original doesn't exists": skipped
+            const ShapedRecord& r = it->second;
+            if (r.transformed) return fs.fail(ARN_E_UNSUPPORTED, "Transformed component over an already transformed primitive (nested TransformedComposable) is not flattened");
+            int rc = fs.add_sphere(r.radius, r.zmin, r.zmax, r.phimax, r.material, r.emissive ? r.emission : nullptr, t16, false);
+            if (rc < 0) return rc;
+            const Json* nm = c.get("name");
+            if (nm && nm->kind == Json::Str) { ShapedRecord inst = r; inst.transformed = true; shaped_by_name[nm->str] = inst; }
+        }
         if (pass == 0 && mesh) {
             const Json* fn = mesh->get("filename");
             if (!fn || fn->kind != Json::Str) return fs.fail(ARN_E_INVALID, "Mesh without filename");
@@ -356,8 +376,16 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
             float t16[16]; const float* tp = nullptr;
             const Json* tr = shaped->get("transform");
             if (tr && !tr->is_null()) { if (!json_matrix(*tr, t16)) return fs.fail(ARN_E_INVALID, "malformed shape transform"); tp = t16; }
-            int rc = fs.add_sphere(radius, zmin, zmax, phimax, (uint32_t)it->second, ep, tp);
+            bool kept = false;
+            int rc = fs.add_sphere(radius, zmin, zmax, phimax, (uint32_t)it->second, ep, tp, true, &kept);
             if (rc < 0) return rc;
+            const Json* nm = c.get("name");
+            if (nm && nm->kind == Json::Str) {
+                ShapedRecord r; r.radius = radius; r.zmin = zmin; r.zmax = zmax; r.phimax = phimax; r.material = (uint32_t)it->second;
+                r.emissive = ep != nullptr; if (ep) { r.emission[0] = ep[0]; r.emission[1] = ep[1]; r.emission[2] = ep[2]; }
+                r.transformed = kept;
+                shaped_by_name[nm->str] = r;
+            }
         }
     }
     // sampler: StrataSampler {sampledx, sampledy, ndim} (sample/strata.rs:93-164)

@@ -621,3 +621,32 @@ def test_sphere_only_scene_bit_exact(ctx):
     assert same.mean() >= 1.0 - 2e-4, f"{(~same).sum()} of {same.size} samples differ"
     assert (orad[..., :3].max(-1) > 0).mean() > 0.05          # a dark scene: one spot cone and two small emitters
     sc.close(); osc.close()
+
+
+def test_transformed_instance_of_an_emitter(ctx, tmp_path):
+    """arencli's ComponentDesc::Transformed (arencli.rs:162-181): the instance of an emissive sphere glows when a path
+    hits it directly but is not one of `Scene.lights` (never sampled, and a BSDF-sampled ray that reaches it is not
+    `ptr::eq` to the sampled light).  Scene read from a JSON file; GPU == oracle per sample."""
+    import json, os, shutil
+    mini = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mini_scene")
+    src = json.load(open(os.path.join(mini, "scene.json")))
+    for f in ("room.obj", "room.mtl"):
+        shutil.copy(os.path.join(mini, f), tmp_path / f)
+    src["components"] += [
+        {"name": "bulb", "value": {"Shaped": {"shape": {"Sphere": {"radius": 0.3, "zmin": -1.0, "zmax": 1.0, "phimax": 6.28}},
+                                              "material": {"name": "lamp_matte", "value": None},
+                                              "light": {"name": "bulb_light", "value": {"Constant": {"value": {"inner": [4.0, 4.0, 4.0]}}}}, "transform": None}}},
+        {"name": "bulb2", "value": {"Transformed": {"transform": [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [-0.7, 1.0, 0.5, 1]], "original": "bulb"}}}]
+    p = tmp_path / "scene.json"; p.write_text(json.dumps(src))
+    hs = api.HostScene()
+    cam, film, smp, prm, _ = hs.load_json(p, base_dir=tmp_path)
+    d = hs.build()
+    assert d.n_spheres == 3 and d.n_lights == 2
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.mean() >= 1.0 - 1e-4, f"{(~same).sum()} of {same.size} samples differ"
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays)
+    sc.close(); osc.close()

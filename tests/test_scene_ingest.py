@@ -13,6 +13,7 @@ from arendur_b200 import api, scenes, _lib as L
 
 REF = "/root/reference/examples/cornellbox"
 have_ref = os.path.exists(os.path.join(REF, "cb.json"))
+MINI_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mini_scene")
 
 
 def _desc_arrays(d):
@@ -165,3 +166,41 @@ def test_json_errors(tmp_path):
     with pytest.raises(api.ArnError) as e:
         api.HostScene().load_json(p)
     assert e.value.code == L.ARN_E_INVALID          # malformed Point light
+
+
+def test_json_transformed_components(tmp_path):
+    """ComponentDesc::Transformed (examples/arencli.rs:162-181): an instance of a bare named sphere becomes a transformed
+    sphere that is NOT in `lights` even when emissive; a missing original or a singular matrix skips the component (the
+    reference prints and continues); an instance of an already transformed primitive is rejected (nested round trip)."""
+    import json, shutil
+    src = json.load(open(os.path.join(MINI_DIR, "scene.json")))
+    for f in ("room.obj", "room.mtl"):
+        shutil.copy(os.path.join(MINI_DIR, f), tmp_path / f)
+    bulb = {"name": "bulb", "value": {"Shaped": {
+        "shape": {"Sphere": {"radius": 0.3, "zmin": -1.0, "zmax": 1.0, "phimax": 6.28}},
+        "material": {"name": "lamp_matte", "value": None},
+        "light": {"name": "bulb_light", "value": {"Constant": {"value": {"inner": [4.0, 4.0, 4.0]}}}},
+        "transform": None}}}
+    move = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [-0.7, 1.0, 0.5, 1]]
+    singular = [[1, 0, 0, 0], [0, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    src["components"] += [bulb,
+                          {"name": "bulb2", "value": {"Transformed": {"transform": move, "original": "bulb"}}},
+                          {"name": "ghost", "value": {"Transformed": {"transform": move, "original": "nobody"}}},
+                          {"name": "flat", "value": {"Transformed": {"transform": singular, "original": "bulb"}}}]
+    p = tmp_path / "scene.json"
+    p.write_text(json.dumps(src))
+    hs = api.HostScene()
+    hs.load_json(p, base_dir=tmp_path)
+    d = hs.build()
+    assert d.n_spheres == 3                                   # lamp, bulb, bulb2 (ghost and flat are skipped)
+    bulb_s, inst = d.spheres[1], d.spheres[2]
+    assert bulb_s.has_transform == 0 and inst.has_transform == 1 and inst.emissive == 1
+    assert list(inst.local_parent)[12:15] == [np.float32(-0.7), 1.0, 0.5] and inst.radius == bulb_s.radius
+    assert d.n_lights == 2                                    # lamp and bulb: the instance is not a light
+    lp = np.ctypeslib.as_array(d.light_prims, (2,))
+    assert (d.prims[lp[0]] & 0x7fffffff, d.prims[lp[1]] & 0x7fffffff) == (0, 1)
+    src["components"].append({"name": "lamp2", "value": {"Transformed": {"transform": move, "original": "lamp"}}})
+    p.write_text(json.dumps(src))
+    with pytest.raises(api.ArnError) as e:
+        api.HostScene().load_json(p, base_dir=tmp_path)
+    assert e.value.code == L.ARN_E_UNSUPPORTED
