@@ -292,11 +292,20 @@ def main():
         peak, peak_src = load_peaks()
         n_ext_launch = timing_steps * (prm0.max_depth + 1) * max(1, (RES * RES * spp_step // world + (1 << 20) - 1) // (1 << 20))
         achieved = bytes_per_ray * ext_rays / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        traffic = None
+        traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_trace_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_trace_dram_bytes_per_launch")
+                # the limit that actually binds on the cache-resident Cornell scene: FP32 issue.  Instructions per
+                # ray come from the committed ncu capture of this kernel on this workload, the rate from the live timing above.
+                if ext_ms > 0 and tj.get("k_trace_thread_inst_per_ray"):
+                    rays_s = ext_rays / (ext_ms * 1e-3)
+                    issue = {"thread_inst_per_ray": tj["k_trace_thread_inst_per_ray"], "achieved_thread_inst_per_s": tj["k_trace_thread_inst_per_ray"] * rays_s,
+                             "peak_thread_inst_per_s": tj["fp32_issue_peak_thread_inst_per_s"], "frac": tj["k_trace_thread_inst_per_ray"] * rays_s / tj["fp32_issue_peak_thread_inst_per_s"],
+                             "warp_issue_frac": tj["k_trace_warp_inst_per_ray"] * rays_s / (148 * 4 * 1.965e9),
+                             "source": "instructions per ray: profiles/r01_e_trace_full.txt (ncu); peak: tools/fp32_issue.cu measured on this GPU model (profiles/r01_fp32_issue.json)"}
             except Exception:
                 traffic = None
         line = {
@@ -314,7 +323,7 @@ def main():
                          "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": ext_rays / max(1, n_ext_launch),
                          "trace_mrays_s": ext_rays / (ext_ms * 1e-3) / 1e6 if ext_ms > 0 else 0.0, "trace_share_of_step": ext_ms / serial_ms if serial_ms > 0 else 0.0,
                          "timing": f"CUDA events around every k_trace launch of {timing_steps} steps re-run with ONE wave pipeline (serial launches; {serial_ms / timing_steps:.1f} ms per step); value and e2e run {PIPELINES} concurrent wave pipelines",
-                         "incoherent_mrays_s": inc_rays / (inc_ms * 1e-3) / 1e6 if inc_ms > 0 else 0.0,
+                         "incoherent_mrays_s": inc_rays / (inc_ms * 1e-3) / 1e6 if inc_ms > 0 else 0.0, "fp32_issue": issue,
                          "note": "Cornell scene (0.2 MB) is cache resident: the HBM roofline is the contract's denominator, not the binding limit (DESIGN.md)"},
             "clocks": clk,
         }
