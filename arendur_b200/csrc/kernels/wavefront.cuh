@@ -19,7 +19,9 @@
 
 namespace arn {
 
+#ifndef ARN_BLOCK
 #define ARN_BLOCK 256
+#endif
 #ifndef ARN_TRAV_MINB
 #define ARN_TRAV_MINB 3
 #endif
