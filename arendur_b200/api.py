@@ -320,11 +320,14 @@ class Scene:
         self._check(self.lib.arn_intersect_closest_counted_dev(self.s, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), ctr))
         return int(ctr[0]), int(ctr[1]), int(ctr[2])
 
-    def render_pt(self, cam, film, sampler, params):
-        """PTRenderer::render up to the tile merge. Returns (film (h,w,4) float32 host array, Stats)."""
+    def render_pt(self, cam, film, sampler, params, out=None):
+        """PTRenderer::render up to the tile merge. Returns (film (h,w,4) float32 host array, Stats).
+        `out`: an existing (h, w, 4) float32 host array to receive the film (e.g. pinned memory)."""
         w = film.crop_max_x - film.crop_min_x
         h = film.crop_max_y - film.crop_min_y
-        out = np.zeros((h, w, 4), dtype=np.float32)
+        if out is None:
+            out = np.zeros((h, w, 4), dtype=np.float32)
+        assert out.shape == (h, w, 4) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
         st = L.Stats()
         self._check(self.lib.arn_render_pt(self.s, C.byref(cam), C.byref(film), C.byref(sampler), C.byref(params), _ptr(out), C.byref(st)))
         return out, st

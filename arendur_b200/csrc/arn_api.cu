@@ -47,6 +47,7 @@ struct arn_ctx {
     // scratch for batched queries through host buffers
     void* d_rays = nullptr; void* d_hits = nullptr; size_t rays_cap = 0;
     unsigned long long* d_ctr = nullptr;
+    void* d_film = nullptr; size_t film_cap = 0;     // arn_render_pt's device film
     bool opt_count = false;
     int opt_width = 0;           // ARN_OPT_BVH_WIDTH: 0 auto, 2 binary, 4 wide
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
@@ -57,6 +58,7 @@ struct arn_scene {
     arn_ctx* ctx = nullptr;
     DevScene dev{};
     std::vector<void*> allocs;
+    char* pool = nullptr; size_t pool_size = 0, pool_off = 0;   // one device allocation per scene, carved in 256-byte steps
     uint32_t max_depth = 0;
     uint32_t class_mask = 0;     // shading classes present in the material table
     uint64_t bytes = 0;
@@ -72,12 +74,18 @@ int set_err(arn_ctx* c, int code, const std::string& msg) {
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     return set_err(ctx, e_ == cudaErrorMemoryAllocation ? ARN_E_OOM : ARN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+void* pool_take(arn_scene* s, size_t bytes) {
+    size_t o = s->pool_off;
+    if (!s->pool || o + align256(bytes) > s->pool_size) return nullptr;
+    s->pool_off = o + align256(bytes);
+    return s->pool + o;
+}
 template <typename T, typename P> int dev_upload(arn_scene* s, const T* host, size_t n, P* out) {
     *out = nullptr;
     if (n == 0 || !host) return ARN_OK;
-    void* d = nullptr;
-    CUDA_TRY(s->ctx, cudaMalloc(&d, n * sizeof(T)));
-    s->allocs.push_back(d);
+    void* d = pool_take(s, n * sizeof(T));
+    if (!d) return set_err(s->ctx, ARN_E_OOM, "scene pool exhausted (internal sizing error)");
     CUDA_TRY(s->ctx, cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream));
     s->bytes += n * sizeof(T);
     *out = (P)d;
@@ -194,6 +202,7 @@ void arn_ctx_destroy(arn_ctx* c) {
     if (c->d_rays) cudaFree(c->d_rays);
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->d_film) cudaFree(c->d_film);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -283,6 +292,25 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     std::vector<void*> scratch;          // device scratch of this upload, freed after its final sync
     auto fail = [&](int rc) { cudaStreamSynchronize(c->stream); for (void* p : scratch) cudaFree(p); arn_scene_destroy(s); return rc; };
     int rc;
+    // one device allocation for the whole scene (and one for the upload's scratch): 2 cudaMalloc instead of 20
+    const size_t n_interior_all = ((size_t)d->n_nodes - 1) / 2;
+    {
+        size_t total = align256((size_t)d->n_nodes * sizeof(arn_node)) + align256(n_interior_all * 4 * sizeof(arn_node)) + align256((size_t)d->n_prims * 48)
+                     + align256((size_t)d->n_spheres * sizeof(arn_sphere)) + align256((size_t)d->n_triangles * 12) + align256((size_t)d->n_vertices * 12) * 2
+                     + align256((size_t)d->n_vertices * 8) + align256((size_t)d->n_triangles * 4) + align256((size_t)d->n_meshes * sizeof(arn_mesh))
+                     + align256((size_t)d->n_materials * sizeof(arn_material)) + align256((size_t)d->n_prims * 4) + align256((size_t)d->n_lights * 4) * 2
+                     + align256((size_t)d->n_analytic_lights * sizeof(arn_analytic_light)) + align256(((size_t)d->n_lights + 1) * 4) + 4096;
+        void* pool = nullptr;
+        cudaError_t ce = cudaMalloc(&pool, total);
+        if (ce != cudaSuccess) { set_err(c, ARN_E_OOM, std::string("scene memory: ") + cudaGetErrorString(ce)); return fail(ARN_E_OOM); }
+        s->allocs.push_back(pool); s->pool = (char*)pool; s->pool_size = total;
+        size_t sbytes = align256(n_interior_all * sizeof(uint2)) * 2 + align256((ARN_STACK + 4) * sizeof(uint32_t)) + align256((size_t)d->n_prims * 4);
+        void* sp = nullptr;
+        if (cudaMalloc(&sp, sbytes) != cudaSuccess) { set_err(c, ARN_E_OOM, "upload scratch: out of device memory"); return fail(ARN_E_OOM); }
+        scratch.push_back(sp);
+    }
+    char* scratch_p = (char*)scratch[0];
+    auto scratch_take = [&](size_t bytes) { char* r = scratch_p; scratch_p += align256(bytes); return (void*)r; };
     // nodes: same 32-byte records, read on the device as float4 pairs
     const arn_node* dn = nullptr;
     if ((rc = dev_upload(s, d->nodes, d->n_nodes, &dn)) != ARN_OK) return fail(rc);
@@ -300,16 +328,10 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
         std::memcpy(&s->dev.root0, &root, 16); std::memcpy(&s->dev.root1, (const char*)&root + 16, 16);
         const size_t n_interior = ((size_t)d->n_nodes - 1) / 2;        // full binary tree; every wide node is rooted at an interior node
         if (n_interior > 0) {
-            arn_node* d_wide = nullptr; uint2 *f0 = nullptr, *f1 = nullptr; uint32_t *d_counts = nullptr;
-            cudaError_t ce;
-            if ((ce = cudaMalloc(&d_wide, n_interior * 4 * sizeof(arn_node))) != cudaSuccess) { set_err(c, ARN_E_OOM, std::string("wide nodes: ") + cudaGetErrorString(ce)); return fail(ARN_E_OOM); }
-            s->allocs.push_back(d_wide); s->bytes += n_interior * 4 * sizeof(arn_node);
-            if (cudaMalloc(&f0, n_interior * sizeof(uint2)) != cudaSuccess || (scratch.push_back(f0), cudaMalloc(&f1, n_interior * sizeof(uint2))) != cudaSuccess
-                || (scratch.push_back(f1), cudaMalloc(&d_counts, (ARN_STACK + 4) * sizeof(uint32_t))) != cudaSuccess) {
-                for (void* p : scratch) cudaFree(p);
-                set_err(c, ARN_E_OOM, "wide collapse scratch: out of device memory"); return fail(ARN_E_OOM);
-            }
-            scratch.push_back(d_counts);
+            arn_node* d_wide = (arn_node*)pool_take(s, n_interior * 4 * sizeof(arn_node));
+            if (!d_wide) { set_err(c, ARN_E_OOM, "scene pool exhausted (wide nodes)"); return fail(ARN_E_OOM); }
+            uint2* f0 = (uint2*)scratch_take(n_interior * sizeof(uint2)); uint2* f1 = (uint2*)scratch_take(n_interior * sizeof(uint2));
+            uint32_t* d_counts = (uint32_t*)scratch_take((ARN_STACK + 4) * sizeof(uint32_t));
             uint32_t* d_wide_count = d_counts + ARN_STACK + 2;
             k_wide_begin<<<1, 1, 0, c->stream>>>(f0, d_counts, d_wide_count, 1);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -326,11 +348,9 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if ((rc = dev_upload(s, d->positions, (size_t)d->n_vertices * 3, &s->dev.positions)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->prims, d->n_prims, &s->dev.prims)) != ARN_OK) return fail(rc);
     {   // ordered 48-byte primitive slots, gathered on the device from the arrays just uploaded
-        uint32_t* d_order = nullptr; float4* d_slots = nullptr;
-        if (cudaMalloc(&d_order, (size_t)d->n_prims * 4) != cudaSuccess) { set_err(c, ARN_E_OOM, "component order: out of device memory"); return fail(ARN_E_OOM); }
-        scratch.push_back(d_order);
-        if (cudaMalloc(&d_slots, (size_t)d->n_prims * 48) != cudaSuccess) { set_err(c, ARN_E_OOM, "primitive slots: out of device memory"); return fail(ARN_E_OOM); }
-        s->allocs.push_back(d_slots); s->bytes += (size_t)d->n_prims * 48;
+        uint32_t* d_order = (uint32_t*)scratch_take((size_t)d->n_prims * 4);
+        float4* d_slots = (float4*)pool_take(s, (size_t)d->n_prims * 48);
+        if (!d_slots) { set_err(c, ARN_E_OOM, "scene pool exhausted (primitive slots)"); return fail(ARN_E_OOM); }
         cudaMemcpyAsync(d_order, d->order, (size_t)d->n_prims * 4, cudaMemcpyHostToDevice, c->stream);
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         const int grid = (int)std::min<size_t>((size_t)sms * 8, ((size_t)d->n_prims + 255) / 256);
@@ -709,8 +729,13 @@ int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, con
     long cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
     if (cw <= 0 || chh <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty crop window");
     size_t bytes = (size_t)cw * (size_t)chh * 16;
-    void* d_film = nullptr;
-    CUDA_TRY(c, cudaMalloc(&d_film, bytes));
+    // the device film lives with the context and only grows: no allocation on the steady-state path
+    if (c->film_cap < bytes) {
+        if (c->d_film) { cudaStreamSynchronize(c->stream); cudaFree(c->d_film); c->d_film = nullptr; c->film_cap = 0; }
+        CUDA_TRY(c, cudaMalloc(&c->d_film, bytes));
+        c->film_cap = bytes;
+    }
+    void* d_film = c->d_film;
     cudaMemsetAsync(d_film, 0, bytes, c->stream);
     arn_stats local;
     int rc = arn_render_pt_dev(s, cam, film, smp, prm, d_film, stats ? stats : &local);
@@ -719,7 +744,6 @@ int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, con
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = set_err(c, ARN_E_CUDA, std::string("film download: ") + cudaGetErrorString(e));
     }
-    cudaFree(d_film);
     return rc;
 }
 

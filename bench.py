@@ -261,17 +261,19 @@ def main():
     scene_bytes = int(desc.n_nodes * 32 + desc.n_prims * 48 + desc.n_spheres * 176 + desc.n_triangles * 16 + desc.n_vertices * 32
                       + desc.n_meshes * 16 + desc.n_materials * 48 + desc.n_prims * 4 + desc.n_lights * 12 + 4)
     e2e_rays, e2e_ms = 0, 0.0
-    host_film = np.zeros((RES, RES, 4), np.float32)
+    host_film = torch.empty((RES, RES, 4), dtype=torch.float32, pin_memory=True).numpy()      # pinned: the D2H read of the result
     e2e_steps = max(1, min(args.steps, 4))
-    for k in range(e2e_steps):
+    for k in range(-1, e2e_steps):                                       # k = -1: one untimed warm-up of this path (first-use allocations)
         barrier()
         t0 = time.perf_counter()
         sc2 = ctx.upload(desc)                                           # H2D of the flattened scene
-        f, st = sc2.render_pt(cam, film, smp, params(k))                 # render + film D2H (synchronous)
+        f, st = sc2.render_pt(cam, film, smp, params(max(k, 0)), out=host_film)  # render + film D2H into pinned memory (synchronous)
         if dist is not None:                                             # multi-GPU: gather on rank 0 through NCCL as well
             t = torch.from_numpy(f).cuda(); dist.reduce(t, dst=0); f = t.cpu().numpy()
         sc2.close()
         barrier()
+        if k < 0:
+            continue
         e2e_ms += (time.perf_counter() - t0) * 1e3
         e2e_rays += st.extend_rays + st.shadow_rays + st.mis_rays
 
