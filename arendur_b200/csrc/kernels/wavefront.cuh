@@ -309,14 +309,18 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 uint32_t pix = pb.pix[pid];
                 Sampler sm; sm.init(p.seed, pix & 0xffffu, pix >> 16, pb.smp[pid], (st >> 16) & 0xffu, st >> 24);
                 float4 b4 = pb.beta[pid]; float3 beta = f3(b4.x, b4.y, b4.z);
-                float4 l4 = pb.L[pid]; float3 L = f3(l4.x, l4.y, l4.z);
                 uint32_t ref = sc.prims[prim];
                 Surf s; uint32_t mat;
                 if (ref & ARN_PRIM_SPHERE) {
                     const DevSphere& sp = sc.spheres[ref & ~ARN_PRIM_SPHERE];
                     surf_sphere(sp, f3(hr.y, hr.z, hr.w), raydir, s);
                     mat = sp.material;
-                    if ((bounces == 0 || spec) && sp.emissive) L = L + beta * light_le(sp, s.pos, -raydir);   // pt.rs:72-78
+                    if ((bounces == 0 || spec) && sp.emissive) {                                              // pt.rs:72-78
+                        // the only place a shade launch changes L: touch the radiance stream for these hits only
+                        float4 l4 = pb.L[pid];
+                        float3 L = f3(l4.x, l4.y, l4.z) + beta * light_le(sp, s.pos, -raydir);
+                        pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
+                    }
                 } else {
                     surf_triangle(sc, ref, hr.y, hr.z, hr.w, raydir, s);
                     mat = sc.meshes[sc.tri_mesh[ref]].material;
@@ -416,7 +420,6 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                         else beta = beta / (1.f - qq);
                     }
                 }
-                pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
                 if (alive) {
                     pb.beta[pid] = make_float4(beta.x, beta.y, beta.z, 0.f);
                     pb.st[pid] = (bounces & 0xffu) | ((spec ? 1u : 0u) << 8) | ((sm.i1d & 0xffu) << 16) | (sm.i2d << 24);
