@@ -389,10 +389,15 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                             flags |= NEE_MIS; has_mis = true;
                         }
                     }
-                    pb.a1[pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
-                    pb.a2[pid] = make_float4(A2.x, A2.y, A2.z, __uint_as_float(lcomp));
-                    pb.beta_old[pid] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(flags));
-                    nee = true;
+                    // A direct-light term that is exactly zero adds beta * (0 / p_light) = +0 to L: it needs no record and no
+                    // resolve, provided p_light is a positive finite number (0 / 0 and 0 / NaN must still poison the sample as
+                    // they do in the reference, scene.rs:65 + pt.rs:89,152-156).  NaN terms are not "black" and keep their record.
+                    nee = has_mis || !is_black(A1) || !(lightpdf > 0.f && lightpdf < ARN_INF) || !(beta.x < ARN_INF && beta.y < ARN_INF && beta.z < ARN_INF);
+                    if (nee) {
+                        pb.a1[pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
+                        pb.a2[pid] = make_float4(A2.x, A2.y, A2.z, __uint_as_float(lcomp));
+                        pb.beta_old[pid] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(flags));
+                    }
                 }
                 // sample the BSDF for the next direction (pt.rs:92-107)
                 float3 wo = -raydir;
@@ -444,10 +449,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q) {
         uint32_t pid = q.connect[i];
         float4 bo = pb.beta_old[pid];
         uint32_t flags = __float_as_uint(bo.w);
-        float4 a1 = pb.a1[pid], a2 = pb.a2[pid];
+        float4 a1 = pb.a1[pid];
         float3 ret = f3(a1.x, a1.y, a1.z);
         if ((flags & NEE_SHADOW) && pb.occluded[pid]) ret = grey(0.f);
-        if ((flags & NEE_MIS) && pb.mis_ok[pid]) ret = ret + f3(a2.x, a2.y, a2.z);
+        if ((flags & NEE_MIS) && pb.mis_ok[pid]) { float4 a2 = pb.a2[pid]; ret = ret + f3(a2.x, a2.y, a2.z); }
+        if (is_black(ret) && a1.w > 0.f && a1.w < ARN_INF && bo.x < ARN_INF && bo.y < ARN_INF && bo.z < ARN_INF) continue;   // L + beta * (+0) = L: leave the radiance stream alone
         float3 term = ret / a1.w;                                        // evaluate_direct(..) / lightpdf
         float4 l4 = pb.L[pid];
         float3 L = f3(l4.x, l4.y, l4.z) + f3(bo.x, bo.y, bo.z) * term;   // ret += beta * term
