@@ -219,7 +219,8 @@ typedef struct arn_stats {
     uint64_t invalid_samples;    /* radiance replaced by black (pt.rs:152-156)              */
     uint64_t kernel_launches;    /* kernels of this library launched by the call            */
     double   gpu_ms;             /* device time of the call, CUDA events                    */
-    double   extend_ms;          /* device time of the k_trace launches (path + shadow + light rays)   */
+    double   extend_ms;          /* device time of the k_trace launches (path + shadow + light rays); needs serial
+                                    launches: 0 unless ARN_OPT_PIPELINES is 1                              */
     double   extend_bounce_ms;   /* ... without each wave's first launch (camera rays): incoherent rays */
     uint64_t extend_bounce_rays; /* rays traced by those launches (path rays of bounces >= 1, shadow, light) */
     /* filled only when ARN_OPT_COUNT_TRAVERSAL is on (instrumented kernels, not for timing):
@@ -308,7 +309,8 @@ int arn_render_pt_dev(arn_scene* scene, const arn_camera* cam, const arn_film* f
 
 /* Diagnostic twin of arn_render_pt (parity tests): additionally returns the radiance
  * `calculate_lighting` produced for every camera sample (renderer/pt.rs:144-148),
- * radiance_out[((y*crop_w + x)*n_spp + s)*4 + {0,1,2}], HOST buffer of crop_w*crop_h*n_spp*4 floats. */
+ * radiance_out[((y*crop_w + x)*n_spp + s)*4 + {0,1,2}], HOST buffer of crop_w*crop_h*n_spp*4 floats; (x, y) is the
+ * TILE pixel, which runs over [0, crop_w) x [0, crop_h) whatever crop.pmin is (Film::spawn_tiles, film.rs:118-121). */
 int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_film* film,
                           const arn_sampler* sampler, const arn_pt_params* params,
                           float* film_out, float* radiance_out, arn_stats* stats);
