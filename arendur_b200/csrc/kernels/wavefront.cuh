@@ -196,13 +196,13 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
         if (gi < s1) {
             uint32_t pid = 0; int cls = -1;
             if (gi < n_ext) {
-                pid = ids[gi];
-                float4 o = pb.ray_o[pid], d = pb.ray_d[pid];
+                pid = __ldcs(&ids[gi]);
+                float4 o = __ldcs(&pb.ray_o[pid]), d = __ldcs(&pb.ray_d[pid]);     // streaming: keep L1 for nodes, slots and the stacks
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
                 HitRec h;
                 trace_ray<false, MODE>(sc, r, h, ctr);
-                pb.hit_prim[pid] = h.prim;
-                pb.hit[pid] = make_float4(h.t, h.a, h.b, h.c);
+                __stcs(&pb.hit_prim[pid], h.prim);
+                __stcs(&pb.hit[pid], make_float4(h.t, h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
                     if (ref & ARN_PRIM_SPHERE) {
@@ -217,21 +217,21 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
         } else if (gi < s2) {
             uint32_t j = gi - s1;
             if (j < n_sh) {
-                uint32_t pid = q.shadow[j];
-                float4 o = pb.sh_o[pid], d = pb.sh_d[pid];
+                uint32_t pid = __ldcs(&q.shadow[j]);
+                float4 o = __ldcs(&pb.sh_o[pid]), d = __ldcs(&pb.sh_d[pid]);
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
                 HitRec h; trace_ray<true, MODE>(sc, r, h, ctr);
-                pb.occluded[pid] = h.prim >= 0 ? 1u : 0u;
+                __stcs(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
             }
         } else {
             uint32_t j = gi - s2;
             if (j < n_mis) {
-                uint32_t pid = q.mis[j];
-                float4 o = pb.mis_o[pid], d = pb.mis_d[pid];
+                uint32_t pid = __ldcs(&q.mis[j]);
+                float4 o = __ldcs(&pb.mis_o[pid]), d = __ldcs(&pb.mis_d[pid]);
                 float3 wi = f3(d.x, d.y, d.z);
                 TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
                 HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
-                uint32_t lcomp = __float_as_uint(pb.a2[pid].w);
+                uint32_t lcomp = __float_as_uint(__ldcs(&pb.a2[pid]).w);
                 uint32_t ok = 0;
                 if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
                     const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
                     if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
                     ok = is_black(light_le(sp, pos, -wi)) ? 0u : 1u;       // lsi.le(-wi)
                 }
-                pb.mis_ok[pid] = ok;
+                __stcs(&pb.mis_ok[pid], ok);
             }
         }
     }
