@@ -37,7 +37,7 @@ struct arn_ctx {
     // late-bounce launches of one wave overlap the wide early launches of the next.  pipes[0] runs on `stream`.
     struct Pipe { cudaStream_t stream = nullptr; size_t wave_cap = 0; PathBuf pb{}; Queues q{}; void* pool = nullptr; cudaEvent_t done = nullptr; };
     Pipe pipes[ARN_MAX_PIPES];
-    int opt_pipes = 4;
+    int opt_pipes = 0;           // ARN_OPT_PIPELINES: 0 = auto (4, or 8 for trees large enough for the 4-wide walk)
     // tile tables
     int4* d_tile_rect = nullptr; unsigned long long* d_tile_prefix = nullptr; size_t tile_cap = 0;
     // event pool for per-kernel timing
@@ -132,9 +132,10 @@ int ensure_wave(arn_ctx* ctx, arn_ctx::Pipe* c, size_t cap) {
     return ARN_OK;
 }
 
-size_t wave_capacity_default(int pipes) {
+size_t wave_capacity_default(int pipes, bool big_scene) {
     const char* e = std::getenv("ARN_WAVE");
     if (e) { long v = std::atol(e); if (v >= 1024) return (size_t)v; }
+    if (big_scene && pipes >= 6) return (size_t)1 << 17;
     return pipes >= 3 ? (size_t)1 << 19 : (size_t)1 << 20;
 }
 
@@ -213,7 +214,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     switch (option) {
     case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
     case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2 or 4"); c->opt_width = (int)value; return ARN_OK;
-    case ARN_OPT_PIPELINES: if (value < 1 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 1..8"); c->opt_pipes = (int)value; return ARN_OK;
+    case ARN_OPT_PIPELINES: if (value < 0 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 0 (auto) ..8"); c->opt_pipes = (int)value; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -591,11 +592,14 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
 
     unsigned long long total = prefix.back() * (unsigned long long)(s1 - s0);
     // measured on C3 (tools/prof_cornell.py): 1 pipeline x 2^20 samples 400.8 ms, 2 x 2^20 350.5, 4 x 2^20 336.2, 4 x 2^19 330.8 (= 8 x 2^19)
-    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default(c->opt_count ? 1 : c->opt_pipes);
+    // large scenes (DRAM-latency-bound trace) prefer more and smaller waves: C4 4 x 2^19 191.7 ms, 8 x 2^18 188.8, 8 x 2^17 185.9, 8 x 2^16 190.4
+    const bool big = s->dev.n_nodes >= ARN_WIDE_MIN_NODES;
+    const int pipes_wanted = c->opt_count ? 1 : (c->opt_pipes ? c->opt_pipes : (big ? 8 : 4));
+    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default(pipes_wanted, big);
     if ((unsigned long long)cap > total) cap = (size_t)((total + ARN_BLOCK - 1) / ARN_BLOCK * ARN_BLOCK);
     const unsigned long long n_waves = (total + cap - 1) / cap;
     // per-kernel event timing needs serial launches: it is only taken with one pipeline (ARN_OPT_PIPELINES = 1)
-    const int np = (int)std::min<unsigned long long>((unsigned long long)(c->opt_count ? 1 : c->opt_pipes), n_waves);
+    const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
     for (int i = 0; i < np; i++) { int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc; }
 
     WaveParams wp;

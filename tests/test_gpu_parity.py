@@ -437,7 +437,7 @@ def test_sample_ranges_waves_tile_grids_and_roulette(ctx):
         assert (st_p.extend_rays, st_p.shadow_rays, st_p.mis_rays) == (st_full.extend_rays, st_full.shadow_rays, st_full.mis_rays)
         assert (st_p.extend_ms > 0) == (pipes == 1)
     ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
-    ctx.set_option(L.ARN_OPT_PIPELINES, 4)
+    ctx.set_option(L.ARN_OPT_PIPELINES, 0)
     with pytest.raises(api.ArnError):
         ctx.set_option(L.ARN_OPT_PIPELINES, 9)
     # (3) 5 x 4 tile grid over 3 ranks, against the oracle's same partition
