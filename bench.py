@@ -243,7 +243,7 @@ def main():
             ext_ms += st.extend_ms; ext_rays += st.extend_rays + st.shadow_rays + st.mis_rays
             inc_ms += st.extend_bounce_ms; inc_rays += st.extend_bounce_rays
             serial_ms += st.gpu_ms
-    ctx.set_option(L.ARN_OPT_PIPELINES, PIPELINES)
+    ctx.set_option(L.ARN_OPT_PIPELINES, 0)              # back to auto (= PIPELINES for this scene)
     torch.cuda.synchronize()
     del scratch_t
 
