@@ -182,16 +182,23 @@ ARN_DEV int shading_class(const arn_material& m) {
 //   shadow ray : any hit (LightSample::occluded, lighting/mod.rs:125-133)      -> occluded[pid]
 //   light ray  : closest hit, `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155) -> mis_ok[pid]
 template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc, PathBuf pb, Queues q, int cur, int first) {
+// the 4-wide instance serves trees that miss the caches: it trades a few spills for a fourth resident block per SM
+// (64 registers; C4 k_trace 36.3 -> 35.9 ms, whole frame +4 %); the binary instance stays at three (80 registers)
+__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB + 1 : ARN_TRAV_MINB) k_trace(DevScene sc, PathBuf pb, Queues q, int cur, int first) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t n_ext = q.counts[cur], n_sh = q.counts[10], n_mis = q.counts[11];
     const uint32_t s1 = (n_ext + 31u) & ~31u, s2 = s1 + ((n_sh + 31u) & ~31u), s3 = s2 + ((n_mis + 31u) & ~31u);
     const uint32_t* __restrict__ ids = q.active[cur];
+    // staging state lives in shared memory, not in registers: the traversal below is register-bound (occupancy) and
+    // would otherwise carry five row pointers and five fill counters through every walk
     __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
-    WarpStage st[ARN_NCLS];
+    __shared__ uint32_t stage_fill[ARN_NCLS][ARN_BLOCK / 32];
+    if ((threadIdx.x & 31u) == 0) {
 #pragma unroll
-    for (int c = 0; c < ARN_NCLS; c++) { st[c].row = stage_rows[c][threadIdx.x >> 5]; st[c].fill = 0; }
+        for (int c = 0; c < ARN_NCLS; c++) stage_fill[c][threadIdx.x >> 5] = 0;
+    }
+    __syncwarp();
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {
         if (gi < s1) {
             uint32_t pid = 0; int cls = -1;
@@ -213,7 +220,13 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
                 }
             }
 #pragma unroll
-            for (int c = 0; c < ARN_NCLS; c++) stage_push(st[c], cls == c, pid, q.cls[c], &q.counts[3 + c]);
+            for (int c = 0; c < ARN_NCLS; c++) {
+                WarpStage t; t.row = stage_rows[c][threadIdx.x >> 5]; t.fill = stage_fill[c][threadIdx.x >> 5];
+                __syncwarp();
+                stage_push(t, cls == c, pid, q.cls[c], &q.counts[3 + c]);
+                if ((threadIdx.x & 31u) == 0) stage_fill[c][threadIdx.x >> 5] = t.fill;
+                __syncwarp();
+            }
         } else if (gi < s2) {
             uint32_t j = gi - s1;
             if (j < n_sh) {
@@ -244,7 +257,10 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace(DevScene sc,
         }
     }
 #pragma unroll
-    for (int c = 0; c < ARN_NCLS; c++) stage_flush(st[c], q.cls[c], &q.counts[3 + c]);
+    for (int c = 0; c < ARN_NCLS; c++) {
+        WarpStage t; t.row = stage_rows[c][threadIdx.x >> 5]; t.fill = stage_fill[c][threadIdx.x >> 5];
+        stage_flush(t, q.cls[c], &q.counts[3 + c]);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&q.stats[0], (unsigned long long)n_ext);
         atomicAdd(&q.stats[1], (unsigned long long)n_sh);
