@@ -8,9 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarn_b200.so")
+LIB_PATH = os.environ.get("ARN_LIB_PATH") or os.path.join(_HERE, "libarn_b200.so")   # ARN_LIB_PATH: A/B builds of the same library (tools/)
 
-ARN_OK, ARN_E_INVALID, ARN_E_CUDA, ARN_E_OOM, ARN_E_IO, ARN_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+ARN_OK, ARN_E_INVALID, ARN_E_CUDA, ARN_E_OOM, ARN_E_IO, ARN_E_UNSUPPORTED, ARN_E_NCCL = 0, -1, -2, -3, -4, -5, -6
 ARN_PRIM_SPHERE = 0x80000000
 ARN_BVH_SAH, ARN_BVH_MIDDLECOUNT, ARN_BVH_MIDPOINT = 0, 1, 2
 ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY, ARN_OPT_BVH_WIDTH, ARN_OPT_PIPELINES = 1, 2, 3, 4
@@ -80,7 +80,7 @@ class Sampler(C.Structure):
 class PTParams(C.Structure):
     _fields_ = [("max_depth", C.c_uint32), ("min_depth", C.c_uint32), ("rr_threshold", C.c_float),
                 ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32), ("rank", C.c_uint32), ("world_size", C.c_uint32),
-                ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32)]
+                ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32), ("partition_subdiv", C.c_uint32)]
 
 
 class Ray(C.Structure):
@@ -105,6 +105,7 @@ ARN_H_SYMBOLS = [
     "arn_last_error", "arn_scene_upload", "arn_scene_destroy", "arn_intersect_closest", "arn_intersect_any",
     "arn_intersect_closest_dev", "arn_intersect_any_dev", "arn_intersect_closest_counted_dev",
     "arn_bvh_build_gpu", "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_set_option", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
+    "arn_film_reduce", "arn_film_merge", "arn_nccl_unique_id", "arn_nccl_comm_create", "arn_nccl_comm_destroy",
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
@@ -148,6 +149,11 @@ def load():
         "arn_ctx_synchronize": (C.c_int, [vp]),
         "arn_ctx_stream": (vp, [vp]),
         "arn_version": (C.c_char_p, []),
+        "arn_film_reduce": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_int]),
+        "arn_film_merge": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "arn_nccl_unique_id": (C.c_int, [vp]),
+        "arn_nccl_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "arn_nccl_comm_destroy": (C.c_int, [vp]),
         "arn_hscene_create": (C.c_int, [C.POINTER(vp)]),
         "arn_hscene_destroy": (None, [vp]),
         "arn_hscene_last_error": (C.c_char_p, [vp]),

@@ -72,7 +72,7 @@ def make_sampler(sampledx, sampledy, ndim=8, seed=0):
     return s
 
 
-def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, tiles=(16, 16), min_depth=None, rr_threshold=0.05):
+def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, tiles=(16, 16), min_depth=None, rr_threshold=0.05, subdiv=0):
     p = L.PTParams()
     p.max_depth = max_depth
     p.min_depth = max_depth // 2 if min_depth is None else min_depth      # renderer/pt.rs:48
@@ -80,6 +80,7 @@ def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, ti
     p.tiles_x, p.tiles_y = tiles
     p.rank, p.world_size = rank, world_size
     p.spp_begin, p.spp_end = spp_begin, spp_end
+    p.partition_subdiv = subdiv
     return p
 
 
@@ -247,6 +248,44 @@ class Context:
         if rc != 0:
             raise ArnError(rc, self.error())
         return Scene(self, s)
+
+
+class FilmComm:
+    """The NCCL communicator of the multi-GPU film merge (arn_nccl_comm_create / arn_film_reduce, include/arn.h).
+    `exchange(obj_or_None) -> obj` ships rank 0's 128-byte ncclUniqueId to the other ranks (e.g. a
+    torch.distributed broadcast over the launcher's rendezvous): plumbing, any transport will do."""
+
+    def __init__(self, ctx, rank, world_size, exchange):
+        self.ctx, self.lib, self.rank, self.world = ctx, ctx.lib, rank, world_size
+        uid = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self.lib.arn_nccl_unique_id(uid)
+            if rc != 0:
+                raise ArnError(rc, self.lib.arn_last_error(None).decode())
+        data = exchange(bytes(uid) if rank == 0 else None)
+        buf = (C.c_ubyte * 128).from_buffer_copy(data)
+        self.comm = C.c_void_p()
+        rc = self.lib.arn_nccl_comm_create(ctx.c, buf, rank, world_size, C.byref(self.comm))
+        if rc != 0:
+            raise ArnError(rc, ctx.error())
+
+    def reduce(self, film_dev_ptr, n_pixels, root=0):
+        """Film::merge_into across ranks: sum of the per-rank films lands in root's buffer (in place, ctx stream)."""
+        rc = self.lib.arn_film_reduce(self.ctx.c, self.comm, C.c_void_p(film_dev_ptr), n_pixels, root)
+        if rc != 0:
+            raise ArnError(rc, self.ctx.error())
+
+    def close(self):
+        if self.comm:
+            self.lib.arn_nccl_comm_destroy(self.comm)
+            self.comm = C.c_void_p()
+
+
+def film_merge(ctx, dst_dev_ptr, src_dev_ptr, n_pixels):
+    """dst += src on the device (arn_film_merge)."""
+    rc = ctx.lib.arn_film_merge(ctx.c, C.c_void_p(dst_dev_ptr), C.c_void_p(src_dev_ptr), n_pixels)
+    if rc != 0:
+        raise ArnError(rc, ctx.error())
 
 
 def point_light(pos, intensity):

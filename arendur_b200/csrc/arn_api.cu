@@ -3,6 +3,7 @@
 // --fmad=false (see kernels/dev_math.cuh).  There is no CPU fallback: every entry point that
 // computes anything needs a CUDA device and fails with ARN_E_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -31,7 +32,7 @@ struct arn_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     std::string err;
-    std::mutex mu;
+    std::recursive_mutex mu;     // calls on one context are serialised (SURVEY.md §8(b) Threading); recursive: host-buffer entry points call the device ones
     // wave pipelines: each owns a stream and a set of wavefront buffers (allocated lazily, sized to the wave
     // capacity).  Consecutive waves of a render go to consecutive pipelines and run concurrently, so the thin
     // late-bounce launches of one wave overlap the wide early launches of the next.  pipes[0] runs on `stream`.
@@ -159,15 +160,18 @@ int arn_ctx_create(int device, arn_ctx** out) {
     if (device < 0 || device >= ndev) return set_err(nullptr, ARN_E_INVALID, "arn_ctx_create: device index out of range");
     arn_ctx* c = new arn_ctx;
     c->device = device;
-    CUDA_TRY(nullptr, cudaSetDevice(device));
+    // any failure below releases what was created so far (arn_ctx_destroy tolerates a half-built context)
+#define CTX_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { arn_ctx_destroy(c); \
+    return set_err(nullptr, e_ == cudaErrorMemoryAllocation ? ARN_E_OOM : ARN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CTX_TRY( cudaSetDevice(device));
     cudaDeviceProp prop;
-    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) { delete c; return set_err(nullptr, ARN_E_UNSUPPORTED, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor)); }
+    CTX_TRY( cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { arn_ctx_destroy(c); return set_err(nullptr, ARN_E_UNSUPPORTED, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor)); }
     c->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTX_TRY( cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->pipes[0].stream = c->stream;
-    for (int i = 1; i < ARN_MAX_PIPES; i++) CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->pipes[i].stream, cudaStreamNonBlocking));
-    for (int i = 0; i < ARN_MAX_PIPES; i++) CUDA_TRY(nullptr, cudaEventCreateWithFlags(&c->pipes[i].done, cudaEventDisableTiming));
+    for (int i = 1; i < ARN_MAX_PIPES; i++) CTX_TRY( cudaStreamCreateWithFlags(&c->pipes[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ARN_MAX_PIPES; i++) CTX_TRY( cudaEventCreateWithFlags(&c->pipes[i].done, cudaEventDisableTiming));
     { const char* e = std::getenv("ARN_PIPES"); if (e) { int v = std::atoi(e); if (v >= 1 && v <= ARN_MAX_PIPES) c->opt_pipes = v; } }
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
@@ -183,7 +187,8 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_closest_w = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_WIDE>);
     c->g_any = grid_for(c, (const void*)k_any_batch<ARN_TRAV_BINARY>);
     c->g_any_w = grid_for(c, (const void*)k_any_batch<ARN_TRAV_WIDE>);
-    CUDA_TRY(nullptr, cudaMalloc(&c->d_ctr, 64));
+    CTX_TRY( cudaMalloc(&c->d_ctr, 64));
+#undef CTX_TRY
     *out = c;
     return ARN_OK;
 }
@@ -191,7 +196,7 @@ int arn_ctx_create(int device, arn_ctx** out) {
 void arn_ctx_destroy(arn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < ARN_MAX_PIPES; i++) {
         if (c->pipes[i].stream) cudaStreamSynchronize(c->pipes[i].stream);
         if (c->pipes[i].pool) cudaFree(c->pipes[i].pool);
@@ -205,7 +210,7 @@ void arn_ctx_destroy(arn_ctx* c) {
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_film) cudaFree(c->d_film);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -244,6 +249,10 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if (!d->n_prims || !d->prims || !d->n_nodes || !d->nodes || !d->order) return set_err(c, ARN_E_INVALID, "arn_scene_upload: scene has no primitives or no BVH");
     if (d->n_triangles && (!d->positions || !d->indices || !d->tri_mesh || !d->meshes)) return set_err(c, ARN_E_INVALID, "arn_scene_upload: triangle arrays missing");
     if (d->n_prims >= 0x80000000u) return set_err(c, ARN_E_INVALID, "arn_scene_upload: too many primitives");
+    if (d->n_spheres && !d->spheres) return set_err(c, ARN_E_INVALID, "arn_scene_upload: n_spheres > 0 but spheres is NULL");
+    if (d->n_materials && !d->materials) return set_err(c, ARN_E_INVALID, "arn_scene_upload: n_materials > 0 but materials is NULL");
+    if (d->n_lights && (!d->light_prims || !d->light_func || !d->light_cdf)) return set_err(c, ARN_E_INVALID, "arn_scene_upload: n_lights > 0 but light_prims / light_func / light_cdf is NULL");
+    if (d->n_analytic_lights && !d->analytic_lights) return set_err(c, ARN_E_INVALID, "arn_scene_upload: n_analytic_lights > 0 but analytic_lights is NULL");
     // validate references
     for (uint32_t i = 0; i < d->n_prims; i++) {
         uint32_t r = d->prims[i];
@@ -379,6 +388,7 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     cudaError_t e = cudaStreamSynchronize(c->stream);     // the staging vector `slots` dies here
     if (e == cudaSuccess) e = cudaGetLastError();
     for (void* p : scratch) cudaFree(p);
+    scratch.clear();
     lap("sync");
     if (e != cudaSuccess) { set_err(c, ARN_E_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); return fail(ARN_E_CUDA); }
     *out = s;
@@ -397,7 +407,7 @@ static bool use_wide(const arn_scene* s) {
 // ---------------------------------------------------------------- batched queries
 int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void* hits_dev, arn_stats* stats) {
     if (!s || (n && (!rays_dev || !hits_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_dev: NULL argument");
-    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
     const bool wide = use_wide(s);
     int grid = (int)std::min<size_t>((size_t)(wide ? c->g_closest_w : c->g_closest), (n + ARN_BLOCK - 1) / ARN_BLOCK);
@@ -417,7 +427,7 @@ int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void
 }
 int arn_intersect_any_dev(arn_scene* s, const void* rays_dev, size_t n, void* out_dev, arn_stats* stats) {
     if (!s || (n && (!rays_dev || !out_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any_dev: NULL argument");
-    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
     const bool wide = use_wide(s);
     int grid = (int)std::min<size_t>((size_t)(wide ? c->g_any_w : c->g_any), (n + ARN_BLOCK - 1) / ARN_BLOCK);
@@ -448,7 +458,7 @@ static int ensure_ray_scratch(arn_ctx* c, size_t n) {
 }
 int arn_intersect_closest(arn_scene* s, const arn_ray* rays, size_t n, arn_hit* hits) {
     if (!s || (n && (!rays || !hits))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest: NULL argument");
-    arn_ctx* c = s->ctx; std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
     int rc = ensure_ray_scratch(c, n); if (rc != ARN_OK) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_rays, rays, n * sizeof(arn_ray), cudaMemcpyHostToDevice, c->stream));
@@ -459,7 +469,7 @@ int arn_intersect_closest(arn_scene* s, const arn_ray* rays, size_t n, arn_hit* 
 }
 int arn_intersect_any(arn_scene* s, const arn_ray* rays, size_t n, uint8_t* out) {
     if (!s || (n && (!rays || !out))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any: NULL argument");
-    arn_ctx* c = s->ctx; std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
     int rc = ensure_ray_scratch(c, n); if (rc != ARN_OK) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_rays, rays, n * sizeof(arn_ray), cudaMemcpyHostToDevice, c->stream));
@@ -473,7 +483,7 @@ int arn_intersect_any(arn_scene* s, const arn_ray* rays, size_t n, uint8_t* out)
 // tested, summed over the batch (the algorithmic-bytes figure of SURVEY.md §8(d)).  DEVICE buffers.
 int arn_intersect_closest_counted_dev(arn_scene* s, const void* rays_dev, size_t n, void* hits_dev, uint64_t* counters_out) {
     if (!s || !rays_dev || !hits_dev || !counters_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_counted_dev: NULL argument");
-    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 64, c->stream));
     int grid = (int)std::min<size_t>((size_t)c->g_closest, (n + ARN_BLOCK - 1) / ARN_BLOCK);
     if (grid < 1) grid = 1;
@@ -492,7 +502,7 @@ int arn_bvh_build_gpu(arn_ctx* c, uint32_t n, const float* bounds6, arn_node* no
     if (!c || !bounds6 || !nodes_out || !order_out || !n_nodes_out) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: NULL argument");
     if (n == 0) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: no components (recursive_build asserts len != 0)");
     if (n >= 0x40000000u) return set_err(c, ARN_E_INVALID, "arn_bvh_build_gpu: too many components");
-    std::lock_guard<std::mutex> g(c->mu); cudaSetDevice(c->device);
+    std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     const size_t total = 2 * (size_t)n - 1;
     std::vector<void*> allocs;
     auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
@@ -573,11 +583,17 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             long gy0 = std::max(iy * dy - ry, (long)film->crop_min_y), gy1 = std::min(iy * dy + cdy + ry, (long)film->crop_max_y);
             if (gx0 > gx1 || gy0 > gy1) return set_err(c, ARN_E_INVALID, "arn_render_pt: a film tile does not meet the crop window (Film::spawn_tiles lays tiles out from (0,0) and panics on this, film.rs:118-129)");
         }
-        if ((uint32_t)((ix + iy) % (long)world) != prm->rank) continue;
-        rects.push_back(make_int4((int)(ix * dx), (int)(iy * dy), (int)cdx, (int)cdy));
-        prefix.push_back(prefix.back() + (unsigned long long)cdx * (unsigned long long)cdy);
+        // ranks own whole tiles, or (partition_subdiv = k > 1) the k x k cells of every tile: finer interleave, same film
+        const long sub = prm->partition_subdiv > 1 ? (long)prm->partition_subdiv : 1;
+        const long ncx = std::min(sub, cdx), ncy = std::min(sub, cdy), sdx = cdx / ncx, sdy = cdy / ncy;
+        for (long jx = 0; jx < ncx; jx++) for (long jy = 0; jy < ncy; jy++) {
+            if ((uint32_t)((ix * sub + jx + iy * sub + jy) % (long)world) != prm->rank) continue;
+            long w = jx == ncx - 1 ? cdx - jx * sdx : sdx, h = jy == ncy - 1 ? cdy - jy * sdy : sdy;
+            rects.push_back(make_int4((int)(ix * dx + jx * sdx), (int)(iy * dy + jy * sdy), (int)w, (int)h));
+            prefix.push_back(prefix.back() + (unsigned long long)w * (unsigned long long)h);
+        }
     }
-    std::lock_guard<std::mutex> guard(c->mu);
+    std::lock_guard<std::recursive_mutex> guard(c->mu);
     if (rects.empty()) { if (stats) std::memset(stats, 0, sizeof *stats); return ARN_OK; }
     if (c->tile_cap < rects.size()) {
         if (c->d_tile_rect) cudaFree(c->d_tile_rect);
@@ -705,7 +721,7 @@ int arn_render_pt_dev(arn_scene* s, const arn_camera* cam, const arn_film* film,
 int arn_render_pt_samples(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
                           const arn_pt_params* prm, float* film_out, float* radiance_out, arn_stats* stats) {
     if (!s || !film || !smp || !prm || !film_out || !radiance_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt_samples: NULL argument");
-    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     long cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
     uint32_t spp = smp->sampledx * smp->sampledy; uint32_t s0 = prm->spp_begin, s1 = prm->spp_end ? prm->spp_end : spp;
     if (cw <= 0 || chh <= 0 || s1 <= s0) return set_err(c, ARN_E_INVALID, "arn_render_pt_samples: empty crop window or sample range");
@@ -729,7 +745,7 @@ int arn_render_pt_samples(arn_scene* s, const arn_camera* cam, const arn_film* f
 int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, const arn_sampler* smp,
                   const arn_pt_params* prm, float* film_out, arn_stats* stats) {
     if (!s || !film || !film_out) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_render_pt: NULL argument");
-    arn_ctx* c = s->ctx; cudaSetDevice(c->device);
+    arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     long cw = film->crop_max_x - film->crop_min_x, chh = film->crop_max_y - film->crop_min_y;
     if (cw <= 0 || chh <= 0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty crop window");
     size_t bytes = (size_t)cw * (size_t)chh * 16;
@@ -749,6 +765,106 @@ int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, con
         if (e != cudaSuccess) rc = set_err(c, ARN_E_CUDA, std::string("film download: ") + cudaGetErrorString(e));
     }
     return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- multi-GPU film merge (Film::merge_into across GPUs)
+// NCCL is resolved at first use with dlopen("libnccl.so.2"): a process that already loaded NCCL (torch, or the Rust
+// host's own binding) gets that same copy, a stand-alone host gets the system library, and single-GPU users never
+// touch it.  Only the handful of entry points below is used; their C signatures are NCCL's stable public ABI (nccl.h).
+namespace {
+struct NcclUniqueId { char internal[128]; };          // ncclUniqueId
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (!api.lib) { api.why = std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "?"); return; }
+        api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+        api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclReduce");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Reduce) { api.why = "libnccl.so.2 lacks the expected entry points"; api.lib = nullptr; }
+    });
+    return &api;
+}
+int nccl_fail(arn_ctx* c, const char* what, int r) {
+    NcclApi* a = nccl_api();
+    return set_err(c, ARN_E_NCCL, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(r) : "NCCL error") + " (" + std::to_string(r) + ")");
+}
+__global__ void __launch_bounds__(256) k_film_merge(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[i]; const float4 b = src[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;          // spectrum_sum += .., filter_weight_sum += .. (film.rs:97-98)
+        dst[i] = a;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int arn_nccl_unique_id(void* id128_out) {
+    if (!id128_out) return set_err(nullptr, ARN_E_INVALID, "arn_nccl_unique_id: NULL argument");
+    NcclApi* a = nccl_api();
+    if (!a->lib) return set_err(nullptr, ARN_E_NCCL, a->why);
+    NcclUniqueId id;
+    int r = a->GetUniqueId(&id);
+    if (r != 0) return nccl_fail(nullptr, "ncclGetUniqueId", r);
+    std::memcpy(id128_out, &id, sizeof id);
+    return ARN_OK;
+}
+
+int arn_nccl_comm_create(arn_ctx* c, const void* id128, int rank, int world_size, void** comm_out) {
+    if (!c || !id128 || !comm_out || world_size < 1 || rank < 0 || rank >= world_size) return set_err(c, ARN_E_INVALID, "arn_nccl_comm_create: bad argument");
+    NcclApi* a = nccl_api();
+    if (!a->lib) return set_err(c, ARN_E_NCCL, a->why);
+    cudaSetDevice(c->device);
+    NcclUniqueId id; std::memcpy(&id, id128, sizeof id);
+    void* comm = nullptr;
+    int r = a->CommInitRank(&comm, world_size, id, rank);
+    if (r != 0) return nccl_fail(c, "ncclCommInitRank", r);
+    *comm_out = comm;
+    return ARN_OK;
+}
+
+int arn_nccl_comm_destroy(void* comm) {
+    if (!comm) return ARN_OK;
+    NcclApi* a = nccl_api();
+    if (!a->lib) return set_err(nullptr, ARN_E_NCCL, a->why);
+    int r = a->CommDestroy(comm);
+    return r == 0 ? ARN_OK : nccl_fail(nullptr, "ncclCommDestroy", r);
+}
+
+int arn_film_reduce(arn_ctx* c, void* comm, void* film_dev, size_t n_pixels, int root) {
+    if (!c || !comm || (n_pixels && !film_dev) || root < 0) return set_err(c, ARN_E_INVALID, "arn_film_reduce: bad argument");
+    if (n_pixels == 0) return ARN_OK;
+    NcclApi* a = nccl_api();
+    if (!a->lib) return set_err(c, ARN_E_NCCL, a->why);
+    std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
+    int r = a->Reduce(film_dev, film_dev, n_pixels * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, comm, c->stream);
+    return r == 0 ? ARN_OK : nccl_fail(c, "ncclReduce", r);
+}
+
+int arn_film_merge(arn_ctx* c, void* dst, const void* src, size_t n_pixels) {
+    if (!c || (n_pixels && (!dst || !src))) return set_err(c, ARN_E_INVALID, "arn_film_merge: NULL argument");
+    if (n_pixels == 0) return ARN_OK;
+    std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
+    int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, (n_pixels + 255) / 256);
+    k_film_merge<<<grid, 256, 0, c->stream>>>((float4*)dst, (const float4*)src, n_pixels);
+    CUDA_TRY(c, cudaGetLastError());
+    return ARN_OK;
 }
 
 }  // extern "C"

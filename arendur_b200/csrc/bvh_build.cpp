@@ -45,11 +45,11 @@ inline Bin bin_merge(const Bin& a, const Bin& b) {              // Bucket::union
     return r;
 }
 
-std::atomic<int> g_tasks_left;
 const size_t kParallelCutoff = 1u << 16;
 
 struct Builder {
     int strategy;
+    std::atomic<int> tasks_left{0};      // helper threads this build may still start (per build: concurrent builds do not share it)
 
     void emit_leaf(std::vector<arn_node>& out, const Box& b, uint32_t offset, uint32_t len) {
         arn_node n;
@@ -123,7 +123,7 @@ struct Builder {
         size_t self = out.size();
         arn_node placeholder; std::memset(&placeholder, 0, sizeof placeholder);
         out.push_back(placeholder);
-        bool spawn = n >= kParallelCutoff && g_tasks_left.fetch_sub(1) > 0;
+        bool spawn = n >= kParallelCutoff && tasks_left.fetch_sub(1) > 0;
         if (spawn) {
             std::vector<arn_node> right;
             auto fut = std::async(std::launch::async, [&]() {
@@ -131,12 +131,12 @@ struct Builder {
             });
             build(it, mid_count, offset, scratch, strat, out);
             fut.get();
-            g_tasks_left.fetch_add(1);
+            tasks_left.fetch_add(1);
             size_t second = out.size();
             out.insert(out.end(), right.begin(), right.end());
             finish_interior(out, self, second, axis);
         } else {
-            if (n >= kParallelCutoff) g_tasks_left.fetch_add(1);
+            if (n >= kParallelCutoff) tasks_left.fetch_add(1);
             build(it, mid_count, offset, scratch, strat, out);
             size_t second = out.size();
             build(it + mid_count, n - mid_count, offset + (uint32_t)mid_count, scratch + mid_count, strat, out);
@@ -170,11 +170,10 @@ extern "C" int arn_bvh_build(uint32_t n, const float* bounds6, const float* cost
         it.cost = costs[i]; it.idx = i;
     }
     unsigned hw = std::thread::hardware_concurrency();
-    g_tasks_left.store(hw > 1 ? (int)hw - 1 : 0);
     std::vector<arn_node> nodes;
     try {
         nodes.reserve(2 * (size_t)n);
-        Builder b; b.strategy = strategy;
+        Builder b; b.strategy = strategy; b.tasks_left.store(hw > 1 ? (int)hw - 1 : 0);
         b.build(items.data(), n, 0, scratch.data(), strategy, nodes);
     } catch (...) { return ARN_E_OOM; }
     std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(arn_node));

@@ -422,7 +422,7 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
     std::memset(params, 0, sizeof *params);
     params->max_depth = (uint32_t)md; params->min_depth = params->max_depth / 2; params->rr_threshold = 0.05f;   // renderer/pt.rs:47-48
     params->tiles_x = 16; params->tiles_y = 16; params->rank = 0; params->world_size = 1;                          // pt.rs:131
-    params->spp_begin = 0; params->spp_end = sampler->sampledx * sampler->sampledy;
+    params->spp_begin = 0; params->spp_end = sampler->sampledx * sampler->sampledy; params->partition_subdiv = 0;
     if (outname && outname_cap) { const Json* o = root.get("outputfilename"); std::string s = (o && o->kind == Json::Str) ? o->str : ""; std::snprintf(outname, outname_cap, "%s", s.c_str()); }
     return ARN_OK;
 }

@@ -32,6 +32,7 @@ extern "C" {
 #define ARN_E_OOM         -3   /* host or device allocation failed                 */
 #define ARN_E_IO          -4   /* file could not be read / parsed                  */
 #define ARN_E_UNSUPPORTED -5   /* valid in arendur but outside this hot path       */
+#define ARN_E_NCCL        -6   /* NCCL missing or a collective failed               */
 
 /* ---------------------------------------------------------------- flattened scene */
 
@@ -198,6 +199,10 @@ typedef struct arn_pt_params {
     uint32_t tiles_x, tiles_y;   /* tile grid for multi-GPU partitioning (16,16)       */
     uint32_t rank, world_size;   /* this context renders the tiles (ix, iy) with (ix + iy) % world == rank */
     uint32_t spp_begin, spp_end; /* sample index range to render, [0, spp) for all      */
+    uint32_t partition_subdiv;   /* multi-GPU load balance: 0 or 1 = ranks own whole tiles; k > 1 = every tile is cut into
+                                    k x k cells (the last one absorbs the remainder, like spawn_tiles) and cell (jx, jy) of
+                                    tile (ix, iy) goes to rank (ix*k + jx + iy*k + jy) % world_size.  Only the assignment of
+                                    pixels to ranks changes: tile sinks stay those of the tiles_x x tiles_y grid */
 } arn_pt_params;
 
 typedef struct arn_ray {
@@ -306,6 +311,28 @@ int arn_render_pt(arn_scene* scene, const arn_camera* cam, const arn_film* film,
 int arn_render_pt_dev(arn_scene* scene, const arn_camera* cam, const arn_film* film,
                       const arn_sampler* sampler, const arn_pt_params* params,
                       void* film_dev, arn_stats* stats);
+
+/* ---------------------------------------------------------------- multi-GPU film merge
+ * One arn_ctx (and one process or thread) per GPU; every rank renders its tiles of the frame into a
+ * full-frame device film (arn_render_pt_dev) and the films are summed on the root — `Film::merge_into`
+ * / `Film::collect_into` (filming/film.rs:82-101,171-183) across GPUs.  The exchange is one
+ * ncclReduce(sum) over NVLink/NVSwitch, enqueued on the context's stream.  libnccl.so.2 is resolved
+ * at first use (dlopen), so single-GPU users do not need it. */
+
+/* Sum `film_dev` (n_pixels * float4: sum r, g, b, weight) over the ranks of `nccl_comm` into rank
+ * `root`'s buffer, in place, on the context's stream (asynchronous; other ranks' buffers are left
+ * unchanged).  `nccl_comm` is an ncclComm_t the caller owns (ncclCommInitRank on the Rust side, or
+ * arn_nccl_comm_create below). */
+int arn_film_reduce(arn_ctx* ctx, void* nccl_comm, void* film_dev, size_t n_pixels, int root);
+/* dst += src on the device, pixel by pixel (the per-pixel sum of `Film::merge_into`, film.rs:82-101): lets a root
+ * keep a running film across several reduced slices of samples.  Asynchronous on the context's stream. */
+int arn_film_merge(arn_ctx* ctx, void* dst_film_dev, const void* src_film_dev, size_t n_pixels);
+/* Communicator plumbing for hosts that have no NCCL binding of their own: rank 0 obtains a 128-byte
+ * ncclUniqueId, ships it to the other ranks by any means, and every rank calls arn_nccl_comm_create
+ * on its own context (collective; the context's device becomes the communicator's device). */
+int arn_nccl_unique_id(void* id128_out);
+int arn_nccl_comm_create(arn_ctx* ctx, const void* id128, int rank, int world_size, void** comm_out);
+int arn_nccl_comm_destroy(void* nccl_comm);
 
 /* Diagnostic twin of arn_render_pt (parity tests): additionally returns the radiance
  * `calculate_lighting` produced for every camera sample (renderer/pt.rs:144-148),

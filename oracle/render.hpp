@@ -373,10 +373,17 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
         for (;;) {
             size_t ti = next_tile.fetch_add(1);
             if (ti >= tiles.size()) break;
-            if (((ti / (size_t)ny) + (ti % (size_t)ny)) % world != prm.rank) continue;   // tile (ix, iy) -> rank (ix + iy) % world: diagonal interleave
+            const uint32_t sub = prm.partition_subdiv > 1 ? prm.partition_subdiv : 1;     // arn_pt_params.partition_subdiv (include/arn.h)
+            if (sub == 1 && ((ti / (size_t)ny) + (ti % (size_t)ny)) % world != prm.rank) continue;   // tile (ix, iy) -> rank (ix + iy) % world: diagonal interleave
             FilmTile& tile = tiles[ti];
+            const long tw = tile.bounding.x1 - tile.bounding.x0, thh = tile.bounding.y1 - tile.bounding.y0;
+            const long ncx = std::min<long>(sub, tw), ncy = std::min<long>(sub, thh), sdx = ncx > 0 ? tw / ncx : 1, sdy = ncy > 0 ? thh / ncy : 1;
             ParitySampler sampler; sampler.seed = smp.seed; sampler.spp = spp;
             for (long y = tile.bounding.y0; y < tile.bounding.y1; y++) for (long x = tile.bounding.x0; x < tile.bounding.x1; x++) {
+                if (sub > 1) {      // cell (jx, jy) of tile (ix, iy) -> rank (ix*sub + jx + iy*sub + jy) % world
+                    long jx = std::min((x - tile.bounding.x0) / sdx, ncx - 1), jy = std::min((y - tile.bounding.y0) / sdy, ncy - 1);
+                    if (((ti / (size_t)ny) * sub + (size_t)jx + (ti % (size_t)ny) * sub + (size_t)jy) % world != prm.rank) continue;
+                }
                 sampler.start_pixel((uint32_t)x, (uint32_t)y);
                 for (uint32_t si = s0; si < s1; si++) {
                     sampler.set_sample_index(si);

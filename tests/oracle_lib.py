@@ -202,3 +202,127 @@ def film_finalize(film):
     rgb8 = np.zeros((h, w, 3), np.uint8)
     lib.arn_oracle_film_finalize(_p(f), h * w, _p(rgb), _p(rgb8))
     return rgb, rgb8
+
+
+# ---------------------------------------------------------------- oracle-only scene assembly
+class OracleFlatScene:
+    """The Cornell fixture flattened with the ORACLE's functions only (mesh transform, Sphere::new,
+    bounds, BVH::new, Scene::new's light distribution) — no call into libarn_b200.so.  Used by
+    `bench.py --impl reference` so that the CPU arm never loads the product library, and by
+    tests/test_scene_ingest.py as an independent check of the product's host flattening
+    (examples/arencli.rs:113-197 -> arn_scene_desc)."""
+
+    def __init__(self, fixture=None):
+        lib = load()
+        fixture = fixture or os.path.join(_ROOT, "tests", "golden", "cornell_scene.npz")
+        z = np.load(fixture, allow_pickle=False)
+        self.z = z
+        mats = z["materials"]
+        self.materials = (L.Material * len(mats))()
+        for i, r in enumerate(mats):
+            m = self.materials[i]
+            m.type = int(r[0]); m.kd[:] = [float(v) for v in r[1:4]]; m.ks[:] = [float(v) for v in r[4:7]]
+            sig = np.float32(r[7])
+            if m.type == L.ARN_MAT_MATTE:                                  # material/matte.rs:50-54
+                sig = np.float32(0.0) if sig < 0 else (np.float32(90.0) if not (sig < 90) else sig)
+            m.sigma, m.roughness, m.eta, m.dissolve = float(sig), float(r[8]), float(r[9]), float(r[10])
+            m.alpha = lib.arn_oracle_roughness_to_alpha(C.c_float(float(r[8])))
+        t = np.ascontiguousarray(z["mesh_transform"], np.float32)
+        pos, nrm, uvs, idx, tri_mesh = [], [], [], [], []
+        nm = int(z["n_models"])
+        self.meshes = (L.Mesh * nm)()
+        base = 0
+        any_n = any_uv = False
+        for m in range(nm):
+            p = np.ascontiguousarray(z[f"m{m}_positions"], np.float32)
+            n = np.ascontiguousarray(z[f"m{m}_normals"], np.float32) if f"m{m}_normals" in z.files else None
+            uv = np.ascontiguousarray(z[f"m{m}_texcoords"], np.float32) if f"m{m}_texcoords" in z.files else None
+            op = np.zeros_like(p); on = np.zeros_like(p)
+            lib.arn_oracle_mesh_transform(_p(t), p.shape[0], _p(p), _p(n), _p(op), _p(on) if n is not None else None)
+            pos.append(op); nrm.append(on if n is not None else np.zeros_like(p))
+            uvs.append(uv if uv is not None else np.zeros((p.shape[0], 2), np.float32))
+            ii = np.ascontiguousarray(z[f"m{m}_indices"], np.uint32)
+            ntri = ii.shape[0] // 3
+            idx.append(ii[:ntri * 3] + np.uint32(base)); tri_mesh.append(np.full(ntri, m, np.uint32))
+            me = self.meshes[m]
+            me.material, me.has_normals, me.has_uvs, me.reserved = int(z["model_material"][m]), int(n is not None), int(uv is not None), 0
+            any_n |= n is not None; any_uv |= uv is not None
+            base += p.shape[0]
+        self.positions = np.ascontiguousarray(np.concatenate(pos), np.float32)
+        self.normals = np.ascontiguousarray(np.concatenate(nrm), np.float32) if any_n else None
+        self.uvs = np.ascontiguousarray(np.concatenate(uvs), np.float32) if any_uv else None
+        self.indices = np.ascontiguousarray(np.concatenate(idx), np.uint32)
+        self.tri_mesh = np.ascontiguousarray(np.concatenate(tri_mesh), np.uint32)
+        ntri = self.tri_mesh.shape[0]
+        sph = z["spheres"]
+        self.spheres = (L.Sphere * len(sph))()
+        prims = list(range(ntri)); lights = []
+        for k, r in enumerate(sph):
+            s = self.spheres[k]
+            assert lib.arn_oracle_sphere_new(C.c_float(float(r[0])), C.c_float(float(r[1])), C.c_float(float(r[2])), C.c_float(float(r[3])), C.byref(s)) == 0
+            s.material = int(r[4]); s.emissive = 1; s.emission[:] = [float(v) for v in r[5:8]]
+            lp = np.ascontiguousarray(r[8:24], np.float32); pl = np.zeros(16, np.float32)
+            if lib.arn_oracle_m4_invert(_p(lp), _p(pl)) == 0:
+                s.has_transform = 1
+            else:                                                           # arencli.rs:133-146
+                lp = np.eye(4, dtype=np.float32).reshape(16); pl = lp.copy()
+            s.local_parent[:] = [float(v) for v in lp]; s.parent_local[:] = [float(v) for v in pl]
+            lights.append(len(prims)); prims.append(L.ARN_PRIM_SPHERE | k)
+        self.prims = np.ascontiguousarray(prims, np.uint32)
+        d = L.SceneDesc()
+        d.n_vertices = self.positions.shape[0]
+        d.positions = C.cast(_p(self.positions), L.c_float_p)
+        d.normals = C.cast(_p(self.normals), L.c_float_p) if self.normals is not None else None
+        d.uvs = C.cast(_p(self.uvs), L.c_float_p) if self.uvs is not None else None
+        d.n_triangles = ntri
+        d.indices = C.cast(_p(self.indices), L.c_u32_p); d.tri_mesh = C.cast(_p(self.tri_mesh), L.c_u32_p)
+        d.n_meshes = nm; d.meshes = self.meshes
+        d.n_spheres = len(sph); d.spheres = self.spheres
+        d.n_materials = len(mats); d.materials = self.materials
+        d.n_prims = self.prims.shape[0]; d.prims = C.cast(_p(self.prims), L.c_u32_p)
+        self.desc = d
+        # BVH::new(components, SAH) (component/bvh.rs:58-79)
+        b6, cost = prim_bounds(d)
+        nodes, order = bvh_build(b6, cost, 0)
+        self.nodes = np.ascontiguousarray(nodes); self.order = np.ascontiguousarray(order)
+        d.n_nodes = self.nodes.shape[0]; d.nodes = C.cast(_p(self.nodes), C.POINTER(L.Node)); d.order = C.cast(_p(self.order), L.c_u32_p)
+        # Scene::new (renderer/scene.rs:31-51)
+        self.light_prims = np.ascontiguousarray(lights, np.uint32)
+        self.light_func = np.ascontiguousarray([lib.arn_oracle_light_power_y(C.byref(self.spheres[int(self.prims[i]) & 0x7fffffff])) for i in lights], np.float32)
+        self.light_cdf = np.zeros(len(lights) + 1, np.float32)
+        integ = C.c_float(0.0)
+        lib.arn_oracle_light_distribution(len(lights), _p(self.light_func), _p(self.light_cdf), C.byref(integ))
+        d.n_lights = len(lights); d.light_prims = C.cast(_p(self.light_prims), L.c_u32_p)
+        d.light_func = C.cast(_p(self.light_func), L.c_float_p); d.light_cdf = C.cast(_p(self.light_cdf), L.c_float_p)
+        d.light_func_integral = integ.value
+        d.n_analytic_lights = 0; d.analytic_lights = None
+
+    def camera(self, res_x, res_y):
+        c = self.z["camera"]
+        return camera_make(c[0:16], c[16:20], float(c[20]), float(c[21]), float(c[22]), res_x, res_y)
+
+    def max_depth(self):
+        return int(self.z["max_depth"])
+
+
+def make_film(res_x, res_y):
+    f = L.Film()
+    f.res_x, f.res_y = res_x, res_y
+    f.crop_min_x, f.crop_min_y, f.crop_max_x, f.crop_max_y = 0, 0, res_x, res_y
+    f.filter_radius_x, f.filter_radius_y = 4.0, 4.0
+    return f
+
+
+def make_sampler(sx, sy, ndim=8, seed=0):
+    s = L.Sampler()
+    s.sampledx, s.sampledy, s.ndim, s.seed = sx, sy, ndim, seed
+    return s
+
+
+def make_pt_params(max_depth=8, spp_begin=0, spp_end=0, rank=0, world_size=1, tiles=(16, 16), subdiv=0):
+    p = L.PTParams()
+    p.max_depth, p.min_depth, p.rr_threshold = max_depth, max_depth // 2, 0.05      # renderer/pt.rs:47-48
+    p.tiles_x, p.tiles_y = tiles
+    p.rank, p.world_size, p.spp_begin, p.spp_end = rank, world_size, spp_begin, spp_end
+    p.partition_subdiv = subdiv
+    return p

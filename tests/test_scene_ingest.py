@@ -204,3 +204,27 @@ def test_json_transformed_components(tmp_path):
     with pytest.raises(api.ArnError) as e:
         api.HostScene().load_json(p, base_dir=tmp_path)
     assert e.value.code == L.ARN_E_UNSUPPORTED
+
+
+def test_oracle_only_flattening_equals_the_product_host_layer():
+    """bench.py --impl reference assembles the Cornell scene with oracle functions only (tests/oracle_lib.OracleFlatScene);
+    it must hand the oracle the very bytes the product's host layer (FlatScene, arn_bvh_build) hands the GPU."""
+    import ctypes as C
+    from arendur_b200 import _lib as L
+    o = O.OracleFlatScene()
+    d = o.desc
+    hs, cam, film, smp, prm = scenes.cornell_scene(64, 48, 2, 2)
+    p = hs.desc()
+
+    def raw(ptr, nbytes):
+        return C.string_at(C.cast(ptr, C.c_void_p), nbytes) if nbytes else b""
+    for name in ("n_vertices", "n_triangles", "n_meshes", "n_spheres", "n_materials", "n_prims", "n_nodes", "n_lights", "n_analytic_lights"):
+        assert getattr(d, name) == getattr(p, name), name
+    for name, nbytes in (("positions", d.n_vertices * 12), ("normals", d.n_vertices * 12), ("uvs", d.n_vertices * 8), ("indices", d.n_triangles * 12),
+                         ("tri_mesh", d.n_triangles * 4), ("prims", d.n_prims * 4), ("order", d.n_prims * 4), ("nodes", d.n_nodes * 32),
+                         ("meshes", d.n_meshes * 16), ("spheres", d.n_spheres * C.sizeof(L.Sphere)), ("materials", d.n_materials * 48),
+                         ("light_prims", d.n_lights * 4), ("light_func", d.n_lights * 4), ("light_cdf", (d.n_lights + 1) * 4)):
+        assert raw(getattr(d, name), nbytes) == raw(getattr(p, name), nbytes), name
+    assert d.light_func_integral == p.light_func_integral
+    assert bytes(o.camera(64, 48)) == bytes(cam)
+    assert o.max_depth() == prm.max_depth

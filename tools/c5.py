@@ -19,6 +19,11 @@ ctx = api.Context(local); scene = ctx.upload(hs.desc())
 ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 film_dev = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
 slice_spp = SX * SX // 16
+comm = None
+if world > 1:
+    def exchange(b):
+        box = [b]; dist.broadcast_object_list(box, src=0); return box[0]
+    comm = api.FilmComm(ctx, rank, world, exchange)
 rays = samples = 0
 def sync():
     if dist is not None: dist.barrier()
@@ -27,16 +32,17 @@ with torch.cuda.stream(ext):
     scene.render_pt_dev(cam, film, smp, api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=0, spp_end=2), torch.zeros_like(film_dev).data_ptr())   # warm-up
     sync(); t0 = time.perf_counter()
     for k in range(args.spp_slices):
-        st = scene.render_pt_dev(cam, film, smp, api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=k * slice_spp, spp_end=(k + 1) * slice_spp), film_dev.data_ptr())
+        st = scene.render_pt_dev(cam, film, smp, api.make_pt_params(max_depth=prm0.max_depth, rank=rank, world_size=world, spp_begin=k * slice_spp, spp_end=(k + 1) * slice_spp, subdiv=4), film_dev.data_ptr())
         rays += st.extend_rays + st.shadow_rays + st.mis_rays; samples += st.camera_rays
-    if dist is not None: dist.reduce(film_dev, dst=0)
+    if comm is not None: comm.reduce(film_dev.data_ptr(), W * H, 0)      # arn_film_reduce: ncclReduce inside the C-ABI, once, after the last slice
+    ctx.synchronize()
     sync(); dt = time.perf_counter() - t0
 tot = torch.tensor([rays, samples], dtype=torch.float64, device="cuda")
 if dist is not None: dist.all_reduce(tot)
 if rank == 0:
     f = film_dev.cpu().numpy()
     g, _ = api.film_finalize(f)
-    print(json.dumps({"config": f"C5: Cornell {W}x{H}, {args.spp_slices * slice_spp} of {SX*SX} spp, depth 8, {world} GPU(s), (ix+iy)%N tiles, NCCL film reduce",
+    print(json.dumps({"config": f"C5: Cornell {W}x{H}, {args.spp_slices * slice_spp} of {SX*SX} spp, depth 8, {world} GPU(s), 16x16 tiles cut into 4x4 cells, cell -> rank interleave, arn_film_reduce (NCCL)",
                       "seconds": dt, "spp_per_s": tot[1].item() / dt, "mrays_per_s": tot[0].item() / dt / 1e6, "samples": tot[1].item(),
                       "image_mean_rgb": [float(v) for v in g.reshape(-1, 3).mean(0)], "finite": bool(np.isfinite(g).all())}))
 if dist is not None: dist.destroy_process_group()
