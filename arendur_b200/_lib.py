@@ -175,7 +175,12 @@ def load():
         "arn_save_png": (C.c_int, [C.c_char_p, vp, C.c_uint32, C.c_uint32]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if os.environ.get("ARN_LIB_PATH"):        # an older A/B build (tools/ab_trace.py) may lack newer entry points
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     _lib = lib

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -117,7 +118,7 @@ int ensure_wave(arn_ctx* ctx, arn_ctx::Pipe* c, size_t cap) {
     size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16), o_occ = carve(cap * 4), o_mok = carve(cap * 4);
     size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4), o_qs = carve(cap * 4), o_qm = carve(cap * 4);
     size_t o_cls[ARN_NCLS]; for (int k = 0; k < ARN_NCLS; k++) o_cls[k] = carve(cap * 4);
-    size_t o_counts = carve(64), o_stats = carve(64);
+    size_t o_counts = carve(ARN_NCOUNTS * 4), o_stats = carve(64);
     CUDA_TRY(ctx, cudaMalloc(&c->pool, off));
     char* b = (char*)c->pool;
     c->pb.ray_o = (float4*)(b + o_ray_o); c->pb.ray_d = (float4*)(b + o_ray_d); c->pb.beta = (float4*)(b + o_beta); c->pb.L = (float4*)(b + o_L);
@@ -336,6 +337,8 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
             root.offset = 0; root.len_axis = (axes << 2) | ARN_W_INNER;
         }
         std::memcpy(&s->dev.root0, &root, 16); std::memcpy(&s->dev.root1, (const char*)&root + 16, 16);
+        auto amax = [](float a, float b) { a = std::fabs(a); b = std::fabs(b); return a > b ? a : b; };
+        s->dev.absmax = make_float3(amax(root.bmin[0], root.bmax[0]), amax(root.bmin[1], root.bmax[1]), amax(root.bmin[2], root.bmax[2]));
         const size_t n_interior = ((size_t)d->n_nodes - 1) / 2;        // full binary tree; every wide node is rooted at an interior node
         if (n_interior > 0) {
             arn_node* d_wide = (arn_node*)pool_take(s, n_interior * 4 * sizeof(arn_node));
@@ -651,33 +654,28 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         arn_ctx::Pipe& P = c->pipes[wave % (unsigned long long)np];
         cudaStream_t st = P.stream;
         uint32_t n = (uint32_t)std::min<unsigned long long>(cap, total - base);
-        k_begin_wave<<<1, 1, 0, st>>>(P.q, n);
+        // k_generate empties the wave's queue counters; every k_trace empties the counter set of the other parity (wavefront.cuh, cnt_*)
         k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, base, n);
-        launches += 2;
-        int cur = 0;
-        auto trace = [&](int first, int bounce) {
-            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), st); ext_events.push_back({i0, bounce}); }
-            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
-            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
-            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, cur, first);
+        launches += 1;
+        auto trace = [&](int j) {
+            if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), st); ext_events.push_back({i0, j}); }
+            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), st);
         };
-        trace(1, 0);                                               // camera rays
+        trace(0);                                                  // camera rays
         launches += 1;
-        const uint32_t CLS_MASK = 0xF8u, NEE_MASK = (1u << 2) | (1u << 10) | (1u << 11);
         for (uint32_t b = 0; b < prm->max_depth; b++) {
-            // shade(b): consumes the class queues, fills active[cur^1] + connect / shadow / light-ray queues
+            // shade(b): consumes the class queues of trace(b), fills the next active queue + connect / shadow / light-ray queues
             // heavy classes first: the tail of the bounce is cheap Lambert work
-            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
-            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
-            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
-            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, cur); launches++; }
-            k_reset<<<1, 1, 0, st>>>(P.q, CLS_MASK | (1u << cur));
-            cur ^= 1;
-            trace(0, (int)b + 1);                                  // path rays of bounce b+1, shadow + light rays of bounce b
-            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, st>>>(P.pb, P.q);
-            k_reset<<<1, 1, 0, st>>>(P.q, NEE_MASK);
-            launches += 4;
+            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            trace((int)b + 1);                                     // path rays of bounce b+1, shadow + light rays of bounce b
+            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, st>>>(P.pb, P.q, (int)b);
+            launches += 2;
         }
         if (film->filter_radius_x <= 4.f && film->filter_radius_y <= 4.f && film->filter_radius_x >= 0.5f && film->filter_radius_y >= 0.5f) {
             unsigned long long npix = (base + n - 1) / wp.spp_count - base / wp.spp_count + 1;

@@ -20,6 +20,10 @@
 #include "dev_math.cuh"
 #include "../../../include/arn.h"
 
+#ifndef ARN_BLOCK
+#define ARN_BLOCK 256          /* threads per block of every kernel that traces rays */
+#endif
+
 namespace arn {
 
 typedef arn_sphere DevSphere;   // same POD on host and device (176 B)
@@ -46,6 +50,7 @@ struct DevScene {
     // 4-wide collapse of `nodes` (built at upload, see traverse4): 4 records of 32 B per wide node
     const float4* __restrict__ wide;
     float4 root0, root1;                     // record of the root (bounds of nodes[0] + its reference words)
+    float3 absmax;                           // max(|bmin|, |bmax|) of the root per axis: scale of the conservative slab test's slack
 };
 
 #define ARN_STACK 64           /* upload rejects trees deeper than this */
@@ -60,26 +65,41 @@ struct DevScene {
 // Ray state used by traversal: the slab cache keeps the ORIGINAL origin / 1/dir
 // (bvh.rs:101,112 refreshes only tmax), the shear cache follows the CURRENT ray
 // (ray.rs:136-139), which differs only after a transformed-sphere hit.
+// Register budget: the cache origin (read by a leaf's exact slab test only) and the current direction (read by sphere
+// slots only) live in the calling kernel's shared memory, one column per thread (`ARN_TRAV_SMEM`), not in registers.
+#define ARN_TRAV_SMEM(name) __shared__ float name[6 * ARN_BLOCK]
 struct TravRay {
-    float3 co, inv;            // cache: origin, 1/dir
-    float3 o, d;               // current ray
+    float3 inv;                // cache: 1/dir
+    float3 o;                  // current ray origin
     float tmax;
     int kz;                    // 0 = XZ perm, 1 = YZ, 2 = ZZ
     float3 shear;
+    float* sm;                 // this thread's column of the kernel's ARN_TRAV_SMEM array: co.xyz, d.xyz at stride ARN_BLOCK
+    ARN_DEV float3 co() const { return f3(sm[0], sm[ARN_BLOCK], sm[2 * ARN_BLOCK]); }
+    ARN_DEV float3 d() const { return f3(sm[3 * ARN_BLOCK], sm[4 * ARN_BLOCK], sm[5 * ARN_BLOCK]); }
+    ARN_DEV void set_d(float3 v) { sm[3 * ARN_BLOCK] = v.x; sm[4 * ARN_BLOCK] = v.y; sm[5 * ARN_BLOCK] = v.z; }
+};
+// Per-ray constants of the CONSERVATIVE slab test used on interior nodes (cull_setup / slab_cull below).
+struct CullRay {
+    float3 oi0, oi1;           // -o/d -+ slack: entry / exit distances are fma(plane, 1/d, oi0 / oi1)
+    uint32_t negbits;          // bit a = 1/d[a] < 0
 };
 
-ARN_DEV void shear_setup(TravRay& r) {                     // ShearingTransformCache::from_ray
-    float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+ARN_DEV void shear_setup(TravRay& r, float3 d) {           // ShearingTransformCache::from_ray
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     float3 dd;
-    if (ax > ay && ax > az) { r.kz = 0; dd = f3(r.d.y, r.d.z, r.d.x); }
-    else if (ay > az)       { r.kz = 1; dd = f3(r.d.z, r.d.x, r.d.y); }
-    else                    { r.kz = 2; dd = r.d; }
+    if (ax > ay && ax > az) { r.kz = 0; dd = f3(d.y, d.z, d.x); }
+    else if (ay > az)       { r.kz = 1; dd = f3(d.z, d.x, d.y); }
+    else                    { r.kz = 2; dd = d; }
     r.shear = f3(-dd.x / dd.z, -dd.y / dd.z, 1.f / dd.z);
 }
-ARN_DEV void trav_init(TravRay& r, float3 o, float3 d, float tmax) {
-    r.o = o; r.d = d; r.tmax = tmax; r.co = o;
+ARN_DEV void trav_init(TravRay& r, float* trav_sm, float3 o, float3 d, float tmax) {
+    r.sm = trav_sm + threadIdx.x;
+    r.o = o; r.tmax = tmax;
+    r.sm[0] = o.x; r.sm[ARN_BLOCK] = o.y; r.sm[2 * ARN_BLOCK] = o.z;
+    r.set_d(d);
     r.inv = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);            // construct_ray_cache (bbox.rs:583-592)
-    shear_setup(r);
+    shear_setup(r, d);
 }
 
 // Slab test without the tmax comparison: returns false on a definite miss, else t0.
@@ -90,12 +110,13 @@ ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_
     const float k = 1.f + 2.f * gamma_n(3.f);
     const bool nx = r.inv.x < 0.f, ny = r.inv.y < 0.f, nz = r.inv.z < 0.f;
     const float bminx = q0.x, bminy = q0.y, bminz = q0.z, bmaxx = q0.w, bmaxy = q1.x, bmaxz = q1.y;
-    float t0 = ((nx ? bmaxx : bminx) - r.co.x) * r.inv.x;
-    float t1 = ((nx ? bminx : bmaxx) - r.co.x) * r.inv.x;
-    float ty0 = ((ny ? bmaxy : bminy) - r.co.y) * r.inv.y;
-    float ty1 = ((ny ? bminy : bmaxy) - r.co.y) * r.inv.y;
-    float tz0 = ((nz ? bmaxz : bminz) - r.co.z) * r.inv.z;
-    float tz1 = ((nz ? bminz : bmaxz) - r.co.z) * r.inv.z;
+    const float3 co = r.co();
+    float t0 = ((nx ? bmaxx : bminx) - co.x) * r.inv.x;
+    float t1 = ((nx ? bminx : bmaxx) - co.x) * r.inv.x;
+    float ty0 = ((ny ? bmaxy : bminy) - co.y) * r.inv.y;
+    float ty1 = ((ny ? bminy : bmaxy) - co.y) * r.inv.y;
+    float tz0 = ((nz ? bmaxz : bminz) - co.z) * r.inv.z;
+    float tz1 = ((nz ? bminz : bmaxz) - co.z) * r.inv.z;
     t1 *= k; ty1 *= k; tz1 *= k;
     const bool miss_xy = (t0 > ty1) | (ty0 > t1);
     t0 = ty0 > t0 ? ty0 : t0;
@@ -105,6 +126,61 @@ ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_
     t1 = tz1 < t1 ? tz1 : t1;
     t0_out = t0;
     return !miss_xy & !miss_z & (t1 > 0.f);     // caller adds `t0 < tmax` (NaN t0 fails it, as in the reference)
+}
+
+// ---- conservative slab test for INTERIOR nodes ------------------------------------------------
+// Why interior nodes need not run the reference's slab arithmetic.  For a ray whose three 1/d are finite and non-zero
+// ("regular": no inf * 0 = NaN can arise) every f32 operation of BBox3f::intersect_ray_cached (bbox.rs:549-580) is
+// monotone in the bounds, and a child's bounds are nested in its parent's: the child's [t0, t1] interval lies inside the
+// parent's, and tmax only shrinks between the parent's pop and the child's.  So "leaf L passes its own slab test at
+// its turn" implies that every ancestor passed at its turn — the set of leaves the reference processes is
+//     { L : slab(L) passes with the tmax current when L's turn comes },   in depth-first order (near child by the
+// sign of d[split axis], a per-ray constant).  Which interior nodes were culled on the way does not enter.  Hence any
+// interior test C with  slab(N) passes => C(N) passes  visits exactly the reference's leaves in the reference's order
+// (a few extra interior nodes are expanded; their leaves then fail their own exact test, which is still run, with the
+// reference's arithmetic, before a leaf's primitives are touched).
+//
+// C(N): entry = max_a fma(near_a, 1/d_a, oi0_a), exit = min_a fma(far_a, 1/d_a, oi1_a), pass iff max(entry, 0) <= min(exit, tmax),
+// with oi0/1 = -(o/d) -+ E and E_a = 2^-19 * (|o_a/d_a| + absmax_a * |1/d_a|).  Against the reference's
+// t0 = fl(fl(near - o) * inv) (relative error <= 2.1 u, u = 2^-24) and t1 = fl(fl(fl(far - o) * inv) * (1 + 2 gamma_3))
+// (<= real value + 10 u |.|), the fma form errs by at most u (3 |o/d| + |plane/d| + 2 E): a slack of 32 u (|o/d| + |plane/d|)
+// covers both with a margin > 2.  In space the slack is ~2e-6 of the scene size: the extra interior visits are negligible.
+// Rays that are not regular (a direction component 0, denormal or infinite) take the exact walk (`traverse`).
+struct Node8 { float4 q0, q1; };
+ARN_DEV Node8 ld_node(const float4* __restrict__ p) {      // one 256-bit load per 32-byte record (LDG.E.ENL2.256.CONSTANT)
+    Node8 n;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n.q0.x), "=f"(n.q0.y), "=f"(n.q0.z), "=f"(n.q0.w), "=f"(n.q1.x), "=f"(n.q1.y), "=f"(n.q1.z), "=f"(n.q1.w) : "l"(p));
+    return n;
+}
+ARN_DEV float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }   // FMNMX3
+ARN_DEV float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+ARN_DEV bool ray_is_regular(const DevScene& sc, const TravRay& r) {
+    const float big = 1.0e15f, small = 1.0e-15f;        // products of two such magnitudes stay finite: no inf - inf, no inf * 0
+    float ax = fabsf(r.inv.x), ay = fabsf(r.inv.y), az = fabsf(r.inv.z);
+    return ax < big && ay < big && az < big && ax > small && ay > small && az > small
+        && fabsf(r.o.x) < big && fabsf(r.o.y) < big && fabsf(r.o.z) < big          // NaNs fail every comparison (o == co before any hit)
+        && sc.absmax.x < big && sc.absmax.y < big && sc.absmax.z < big;
+}
+ARN_DEV void cull_setup(const DevScene& sc, const TravRay& r, CullRay& c) {
+    const float k = 1.9073486328125e-6f;                                           // 2^-19
+    float px = r.o.x * r.inv.x, py = r.o.y * r.inv.y, pz = r.o.z * r.inv.z;       // called before any hit: o == co
+    float ex = fmaxf(k * (fabsf(px) + sc.absmax.x * fabsf(r.inv.x)), 1.0e-30f);
+    float ey = fmaxf(k * (fabsf(py) + sc.absmax.y * fabsf(r.inv.y)), 1.0e-30f);
+    float ez = fmaxf(k * (fabsf(pz) + sc.absmax.z * fabsf(r.inv.z)), 1.0e-30f);
+    c.oi0 = f3(-px - ex, -py - ey, -pz - ez);
+    c.oi1 = f3(-px + ex, -py + ey, -pz + ez);
+    c.negbits = (r.inv.x < 0.f ? 1u : 0u) | (r.inv.y < 0.f ? 2u : 0u) | (r.inv.z < 0.f ? 4u : 0u);
+}
+// true unless the box is certainly missed; lo = conservative entry distance (>= 0), re-checked against tmax at pop time
+ARN_DEV bool slab_cull(const float4 q0, const float4 q1, const TravRay& r, const CullRay& c, float& lo) {
+    const bool nx = c.negbits & 1u, ny = c.negbits & 2u, nz = c.negbits & 4u;
+    const float l = fmax3(__fmaf_rn(nx ? q0.w : q0.x, r.inv.x, c.oi0.x), __fmaf_rn(ny ? q1.x : q0.y, r.inv.y, c.oi0.y),
+                          fmaxf(__fmaf_rn(nz ? q1.y : q0.z, r.inv.z, c.oi0.z), 0.f));
+    const float h = fmin3(__fmaf_rn(nx ? q0.x : q0.w, r.inv.x, c.oi1.x), __fmaf_rn(ny ? q0.y : q1.x, r.inv.y, c.oi1.y),
+                          fminf(__fmaf_rn(nz ? q0.z : q1.y, r.inv.z, c.oi1.z), r.tmax));
+    lo = l;
+    return l <= h;
 }
 
 ARN_DEV float3 perm_point(float3 p, int kz) {
@@ -178,9 +254,8 @@ ARN_NOINL bool sphere_test(const DevSphere& sp, float3 o, float3 d, float tmax, 
     return true;
 }
 
-struct HitRec {               // what shading needs from the final hit
+struct HitRec {               // what shading needs from the final hit; its distance is the ray's final tmax
     int prim;                 // component index, -1 = miss
-    float t;
     float a, b, c;            // triangle: b0,b1,b2; sphere: refined local hit point
 };
 
@@ -190,17 +265,20 @@ struct HitRec {               // what shading needs from the final hit
 // becomes the round-tripped one.
 ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& h) {
     const DevSphere& sp = sc.spheres[sc.prims[comp] & ~ARN_PRIM_SPHERE];
-    float3 lo = r.o, ld = r.d;
-    if (sp.has_transform) { lo = xform_point(sp.parent_local, r.o); ld = xform_vector(sp.parent_local, r.d); }
+    const float3 d = r.d();
+    float3 lo = r.o, ld = d;
+    if (sp.has_transform) { lo = xform_point(sp.parent_local, r.o); ld = xform_vector(sp.parent_local, d); }
     float t; float3 p;
     if (!sphere_test(sp, lo, ld, r.tmax, t, p)) return;
     if (!(r.tmax > t)) return;
     if (sp.has_transform) {
-        r.o = xform_point(sp.local_parent, lo); r.d = xform_vector(sp.local_parent, ld);
-        shear_setup(r);
+        r.o = xform_point(sp.local_parent, lo);
+        const float3 nd = xform_vector(sp.local_parent, ld);
+        r.set_d(nd);
+        shear_setup(r, nd);
     }
     r.tmax = t;
-    h.prim = (int)comp; h.t = t; h.a = p.x; h.b = p.y; h.c = p.z;
+    h.prim = (int)comp; h.a = p.x; h.b = p.y; h.c = p.z;
 }
 
 // Closest hit (ANY = false) or any hit (ANY = true: stops at the first accepted primitive —
@@ -226,7 +304,7 @@ ARN_DEV bool trav_pop(const DevScene& sc, const TravRay& r, const uint2* stack, 
 // then test leaf primitives together, so the long triangle test runs with many lanes active.
 template <bool ANY, bool COUNT>
 ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
-    h.prim = -1; h.t = ARN_INF; h.a = h.b = h.c = 0.f;
+    h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
     int sp = 0;
     // root: tested like any popped node
@@ -270,7 +348,7 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
                 if (COUNT) ctr[1]++;
                 float t, b0, b1, b2;
                 if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
-                    r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
+                    r.tmax = t; h.prim = (int)comp; h.a = b0; h.b = b1; h.c = b2;
                 }
             }
             if (ANY && h.prim >= 0) return;
@@ -279,79 +357,150 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
     }
 }
 
-// ---- 4-wide traversal ------------------------------------------------------------------------
-// The wide tree is the binary tree with every second level removed: wide node = (children of the
-// first child, children of the second child), a leaf child occupying one slot of its pair.  The four
-// records are visited in the order the binary depth-first walk would reach them (pair order from the
-// node's split axis, order inside a pair from the child's split axis — signs of the ray direction, not
-// distances), entry distances travel on the stack and are re-checked against the shrinking tmax at pop
-// time.  Result: the same leaves are visited in the same order as in BVH::intersect_ray
-// (bvh.rs:97-128), so hits, ids and ties are bit-identical to the binary walk:
-//   * a grandchild's slab interval is contained in its parent's (same monotone f32 operations on
-//     nested bounds), so skipping the parent's test never admits a leaf the binary walk would reject
-//     — the leaf's own test, made with the same tmax as in the binary walk, decides;
-//   * only the `t0 < tmax` part of a slab test depends on when it is evaluated, and that part is
-//     re-evaluated when the record is popped.
-// tests/test_gpu_parity.py::test_wide_equals_binary checks it ray by ray against the binary kernel.
-ARN_DEV bool trav_pop4(const TravRay& r, const uint4* stack, int& sp, uint32_t& w0, uint32_t& w1) {
+// ---- fast walks: conservative culling at interior nodes, the reference's slab test at leaves -------------
+// Both walks visit the leaves BVH::intersect_ray (bvh.rs:97-128) visits, in its order (see slab_cull above), so hits,
+// ids and ties are bit-identical to `traverse`; tests/test_gpu_round2.py checks them ray by ray against the exact walk
+// and against the oracle.  A leaf's own slab test is the reference's (`slab`), evaluated when the leaf's turn comes,
+// i.e. with the reference's tmax.
+
+// leaf primitives in slot order, strict `<` acceptance (bvh.rs:104-114); returns true when an any-hit query is done
+template <bool ANY>
+ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, TravRay& r, HitRec& h) {
+    const uint32_t end = first + count;
+    for (uint32_t k = first; k < end; k++) {
+        float4 v0 = __ldg(&sc.tris[3 * k]);
+        uint32_t comp = __float_as_uint(v0.w);          // component id, sphere bit set for sphere slots
+        if (comp & ARN_PRIM_SPHERE) sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h);
+        else {
+            float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
+            float t, b0, b1, b2;
+            if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
+                r.tmax = t; h.prim = (int)comp; h.a = b0; h.b = b1; h.c = b2;
+            }
+        }
+        if (ANY && h.prim >= 0) return true;
+    }
+    return false;
+}
+
+// Binary walk over the 32-byte pre-order nodes (cache-resident trees).  Stack entry = (node, conservative entry distance).
+template <bool ANY>
+ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h) {
+    h.prim = -1; h.a = h.b = h.c = 0.f;
+    uint2 stack[ARN_STACK];
+    int sp = 0;
+    uint32_t idx = 0, offset, len_axis;
+    {
+        const Node8 n = ld_node(sc.nodes);
+        float lo;
+        if (!slab_cull(n.q0, n.q1, r, c, lo)) return;
+        offset = __float_as_uint(n.q1.z); len_axis = __float_as_uint(n.q1.w);
+    }
+    for (;;) {
+        bool alive = true;
+        // ---- interior nodes: cull both children (first child = idx+1, second = idx+offset) conservatively
+        while ((len_axis >> 2) == 0) {
+            const uint32_t ia = idx + 1, ib = idx + offset;
+            const Node8 a = ld_node(sc.nodes + 2 * ia), b = ld_node(sc.nodes + 2 * ib);
+            float la, lb;
+            const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
+            const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
+            if (ha && hb) {
+                stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
+                idx = first_b ? ib : ia;
+                offset = __float_as_uint(first_b ? b.q1.z : a.q1.z); len_axis = __float_as_uint(first_b ? b.q1.w : a.q1.w);
+            } else if (ha || hb) {
+                idx = ha ? ia : ib;
+                offset = __float_as_uint(ha ? a.q1.z : b.q1.z); len_axis = __float_as_uint(ha ? a.q1.w : b.q1.w);
+            } else if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) { alive = false; break; }
+        }
+        if (!alive) return;
+        // ---- leaf: the reference's own slab test (its bounds come back from L1), then the primitives
+        {
+            const Node8 n = ld_node(sc.nodes + 2 * idx);
+            float t0;
+            if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
+                if (leaf_prims<ANY>(sc, offset, len_axis >> 2, r, h)) return;
+            }
+        }
+        if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
+    }
+}
+
+// ---- 4-wide walk (trees that do not fit the caches) ------------------------------------------------------------
+// The wide tree is the binary tree with every second level removed: wide node = (children of the first child, children
+// of the second child), a leaf child occupying one slot of its pair; 4 records of 32 B (bounds, w0, w1) = one 128-B
+// line.  The four records are visited in the order the binary depth-first walk would reach them (pair order from the
+// node's split axis, order inside a pair from the child's split axis — signs of the ray direction, not distances).
+// Stack entry = (record index, conservative entry distance): 8 bytes, so a warp's stack level is two 128-B lines of
+// local memory instead of four; the record is fetched again when it is popped (bounds for a leaf's exact test, the
+// reference words for an interior record).  Empty slots carry inverted infinite bounds and fail every test.
+#define ARN_REC_LEAF 0x80000000u       /* stack entry: the record is a leaf (its reference words need no fetch before the leaf phase) */
+ARN_DEV bool trav_pop4(const TravRay& r, const uint2* stack, int& sp, uint32_t& rec) {
     for (;;) {
         if (sp == 0) return false;
-        uint4 e = stack[--sp];
-        if (__uint_as_float(e.z) < r.tmax) { w0 = e.x; w1 = e.y; return true; }
+        uint2 e = stack[--sp];
+        if (__uint_as_float(e.y) < r.tmax) { rec = e.x; return true; }
     }
 }
 template <bool ANY>
-ARN_DEV void traverse4(const DevScene& sc, TravRay& r, HitRec& h) {
-    h.prim = -1; h.t = ARN_INF; h.a = h.b = h.c = 0.f;
-    uint4 stack[ARN_STACK4];
+ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h) {
+    h.prim = -1; h.a = h.b = h.c = 0.f;
+    uint2 stack[ARN_STACK4];
     int sp = 0;
-    float t0;
-    if (!slab(sc.root0, sc.root1, r, t0) || !(t0 < r.tmax)) return;
-    uint32_t w0 = __float_as_uint(sc.root1.z), w1 = __float_as_uint(sc.root1.w);
-    const uint32_t negbits = (r.inv.x < 0.f ? 1u : 0u) | (r.inv.y < 0.f ? 2u : 0u) | (r.inv.z < 0.f ? 4u : 0u);
+    {
+        float lo;
+        if (!slab_cull(sc.root0, sc.root1, r, c, lo)) return;
+    }
+    // current record: its index (leaf bit set for leaves) and, for an interior record, its reference words
+    uint32_t w0 = __float_as_uint(sc.root1.z), w1 = __float_as_uint(sc.root1.w), rec = 0;
+    if ((w1 & 3u) != ARN_W_INNER) {             // a one-leaf tree: the root record is the leaf
+        float t0;
+        if (slab(sc.root0, sc.root1, r, t0) && t0 < r.tmax) leaf_prims<ANY>(sc, w0, w1 >> 8, r, h);
+        return;
+    }
     for (;;) {
         bool alive = true;
-        while ((w1 & 3u) == ARN_W_INNER) {
+        while (!(rec & ARN_REC_LEAF)) {
             const uint32_t ax = w1 >> 2;
-            const uint32_t sN = (negbits >> (ax & 3u)) & 1u, sA = (negbits >> ((ax >> 2) & 3u)) & 1u, sB = (negbits >> ((ax >> 4) & 3u)) & 1u;
+            const uint32_t sN = (c.negbits >> (ax & 3u)) & 1u, sA = (c.negbits >> ((ax >> 2) & 3u)) & 1u, sB = (c.negbits >> ((ax >> 4) & 3u)) & 1u;
             const uint32_t g1 = sN << 1, g2 = 2u - g1;                 // pair visited first / second
             const uint32_t s1 = sN ? sB : sA, s2 = sN ? sA : sB;
-            const float4* __restrict__ rec = sc.wide + (size_t)w0 * 8u;
-            const uint32_t o0 = (g1 + s1) * 2u, o1 = (g1 + (s1 ^ 1u)) * 2u, o2 = (g2 + s2) * 2u, o3 = (g2 + (s2 ^ 1u)) * 2u;
-            const float4 a0 = __ldg(rec + o0), a1 = __ldg(rec + o0 + 1);
-            const float4 b0 = __ldg(rec + o1), b1 = __ldg(rec + o1 + 1);
-            const float4 c0 = __ldg(rec + o2), c1 = __ldg(rec + o2 + 1);
-            const float4 d0 = __ldg(rec + o3), d1 = __ldg(rec + o3 + 1);
+            const uint32_t base = w0 * 4u;
+            const uint32_t r0 = base + g1 + s1, r1 = base + g1 + (s1 ^ 1u), r2 = base + g2 + s2, r3 = base + g2 + (s2 ^ 1u);
+            const Node8 na = ld_node(sc.wide + 2 * (size_t)r0), nb = ld_node(sc.wide + 2 * (size_t)r1);
+            const Node8 nc = ld_node(sc.wide + 2 * (size_t)r2), nd = ld_node(sc.wide + 2 * (size_t)r3);
             float ta, tb, tc, td;
-            const bool ha = slab(a0, a1, r, ta) && ta < r.tmax && (__float_as_uint(a1.w) & 3u);
-            const bool hb = slab(b0, b1, r, tb) && tb < r.tmax && (__float_as_uint(b1.w) & 3u);
-            const bool hc = slab(c0, c1, r, tc) && tc < r.tmax && (__float_as_uint(c1.w) & 3u);
-            const bool hd = slab(d0, d1, r, td) && td < r.tmax && (__float_as_uint(d1.w) & 3u);
-            // walk the visiting order backwards: every hit record but the first goes on the stack
-            bool have = hd;
-            uint32_t n0 = __float_as_uint(d1.z), n1 = __float_as_uint(d1.w); float nt = td;
-            if (hc) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(c1.z); n1 = __float_as_uint(c1.w); nt = tc; have = true; }
-            if (hb) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(b1.z); n1 = __float_as_uint(b1.w); nt = tb; have = true; }
-            if (ha) { if (have) stack[sp++] = make_uint4(n0, n1, __float_as_uint(nt), 0u); n0 = __float_as_uint(a1.z); n1 = __float_as_uint(a1.w); nt = ta; have = true; }
-            if (have) { w0 = n0; w1 = n1; }
-            else if (!trav_pop4(r, stack, sp, w0, w1)) { alive = false; break; }
+            const bool ha = slab_cull(na.q0, na.q1, r, c, ta), hb = slab_cull(nb.q0, nb.q1, r, c, tb);
+            const bool hc = slab_cull(nc.q0, nc.q1, r, c, tc), hd = slab_cull(nd.q0, nd.q1, r, c, td);
+            const uint32_t ka = __float_as_uint(na.q1.w), kb = __float_as_uint(nb.q1.w), kc = __float_as_uint(nc.q1.w), kd = __float_as_uint(nd.q1.w);
+            const uint32_t ea = r0 | ((ka & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u), eb = r1 | ((kb & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u);
+            const uint32_t ec = r2 | ((kc & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u), ed = r3 | ((kd & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u);
+            // every surviving record but the first in visiting order goes on the stack, last one first (branch-free)
+            const bool have = ha | hb | hc | hd;
+            if (hd & (ha | hb | hc)) stack[sp++] = make_uint2(ed, __float_as_uint(td));
+            if (hc & (ha | hb)) stack[sp++] = make_uint2(ec, __float_as_uint(tc));
+            if (hb & ha) stack[sp++] = make_uint2(eb, __float_as_uint(tb));
+            const uint32_t nr = ha ? ea : (hb ? eb : (hc ? ec : ed));
+            const uint32_t n0 = __float_as_uint(ha ? na.q1.z : (hb ? nb.q1.z : (hc ? nc.q1.z : nd.q1.z)));
+            const uint32_t n1 = ha ? ka : (hb ? kb : (hc ? kc : kd));
+            if (have) { rec = nr; w0 = n0; w1 = n1; }
+            else {
+                if (!trav_pop4(r, stack, sp, rec)) { alive = false; break; }
+                if (!(rec & ARN_REC_LEAF)) { const float4 q1 = __ldg(sc.wide + 2 * (size_t)rec + 1); w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w); }
+            }
         }
         if (!alive) return;
-        const uint32_t end = w0 + (w1 >> 8);
-        for (uint32_t k = w0; k < end; k++) {
-            float4 v0 = __ldg(&sc.tris[3 * k]);
-            uint32_t comp = __float_as_uint(v0.w);
-            if (comp & ARN_PRIM_SPHERE) sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h);
-            else {
-                float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
-                float t, b0, b1, b2;
-                if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
-                    r.tmax = t; h.prim = (int)comp; h.t = t; h.a = b0; h.b = b1; h.c = b2;
-                }
+        // ---- leaf record: the reference's own slab test on its bounds (fetched again: one line, usually still in L1), then the primitives
+        {
+            const Node8 n = ld_node(sc.wide + 2 * (size_t)(rec & ~ARN_REC_LEAF));
+            float t0;
+            if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
+                if (leaf_prims<ANY>(sc, __float_as_uint(n.q1.z), __float_as_uint(n.q1.w) >> 8, r, h)) return;
             }
-            if (ANY && h.prim >= 0) return;
         }
-        if (!trav_pop4(r, stack, sp, w0, w1)) return;
+        if (!trav_pop4(r, stack, sp, rec)) return;
+        if (!(rec & ARN_REC_LEAF)) { const float4 q1 = __ldg(sc.wide + 2 * (size_t)rec + 1); w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w); }
     }
 }
 
@@ -360,10 +509,19 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, HitRec& h) {
 #define ARN_TRAV_BINARY 0
 #define ARN_TRAV_COUNTED 1
 #define ARN_TRAV_WIDE 2
+// out-of-line exact walks for the rare rays the conservative test does not cover (one copy per kernel)
+ARN_NOINL void traverse_exact_closest(const DevScene& sc, TravRay& r, HitRec& h) { traverse<false, false>(sc, r, h, nullptr); }
+ARN_NOINL void traverse_exact_any(const DevScene& sc, TravRay& r, HitRec& h) { traverse<true, false>(sc, r, h, nullptr); }
 template <bool ANY, int MODE>
 ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
-    if (MODE == ARN_TRAV_WIDE) traverse4<ANY>(sc, r, h);
-    else traverse<ANY, MODE == ARN_TRAV_COUNTED>(sc, r, h, ctr);
+    if (MODE == ARN_TRAV_COUNTED) { traverse<ANY, true>(sc, r, h, ctr); return; }
+    if (!ray_is_regular(sc, r)) {                       // axis-parallel / degenerate directions: the reference's arithmetic at every node
+        if (ANY) traverse_exact_any(sc, r, h); else traverse_exact_closest(sc, r, h);
+        return;
+    }
+    CullRay c; cull_setup(sc, r, c);
+    if (MODE == ARN_TRAV_WIDE) traverse4<ANY>(sc, r, c, h);
+    else traverse2<ANY>(sc, r, c, h);
 }
 
 }  // namespace arn

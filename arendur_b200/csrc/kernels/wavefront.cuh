@@ -65,9 +65,21 @@ struct Queues {
     uint32_t* shadow;            // path ids with a shadow ray to trace
     uint32_t* mis;               // path ids with a BSDF-sampled light ray to trace
     uint32_t* cls[ARN_NCLS];     // hits of the current bounce, sorted by shading class (material sort)
-    uint32_t* counts;            // [0],[1] = active sizes, [2] = connect size, [3+c] = class c size, [10] = shadow rays, [11] = mis rays
+    uint32_t* counts;            // queue sizes, double-buffered by the parity of the trace launch that consumes / fills them (cnt_* below)
     unsigned long long* stats;   // [0] extend rays [1] shadow rays [2] mis rays [3] invalid samples [4] extend rays of bounces>=1 [5..7] nodes/tris/spheres tested by extend (COUNT builds)
 };
+
+// Queue counters.  Trace launch j of a wave (j = 0: camera rays; j = b + 1: after shade(b)) has parity p = j & 1:
+//   active(p)   path rays trace(j) follows      (filled by k_generate for j = 0, by shade(j - 1) otherwise)
+//   cls(p, c)   hits of trace(j) by shading class (filled by trace(j), consumed by shade(j))
+//   nee(p, k)   k = 0 connect, 1 shadow rays, 2 light rays of bounce j - 1 (filled by shade(j - 1); trace(j) reads 1 and 2,
+//               resolve(j - 1) reads 0)
+// The set with the other parity is idle while trace(j) runs — its last reader finished before trace(j) was launched and its
+// next writer starts after it — so one thread of trace(j) zeroes it: no separate reset launches between the stages.
+#define ARN_NCOUNTS 32
+ARN_DEV uint32_t* cnt_active(const uint32_t* counts, uint32_t p) { return const_cast<uint32_t*>(counts) + p; }
+ARN_DEV uint32_t* cnt_cls(const uint32_t* counts, uint32_t p, uint32_t c) { return const_cast<uint32_t*>(counts) + 2u + 5u * p + c; }
+ARN_DEV uint32_t* cnt_nee(const uint32_t* counts, uint32_t p, uint32_t k) { return const_cast<uint32_t*>(counts) + 12u + 3u * p + k; }
 
 struct WaveParams {
     float raster_view[16], view_parent[16];
@@ -128,6 +140,7 @@ ARN_DEV void stage_flush(WarpStage& st, uint32_t* __restrict__ queue, uint32_t* 
 // ---- K1 generate ------------------------------------------------------------------------
 __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q,
                                                          unsigned long long wave_base, uint32_t n) {
+    if (blockIdx.x == 0 && threadIdx.x < ARN_NCOUNTS) q.counts[threadIdx.x] = threadIdx.x == 0 ? n : 0u;     // begin the wave: every queue empty, n camera rays
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long g = wave_base + i;
         unsigned long long pl = g / p.spp_count;
@@ -184,16 +197,22 @@ ARN_DEV int shading_class(const arn_material& m) {
 template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 // the 4-wide instance serves trees that miss the caches: it trades a few spills for a fourth resident block per SM
 // (64 registers; C4 k_trace 36.3 -> 35.9 ms, whole frame +4 %); the binary instance stays at three (80 registers)
-__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB + 1 : ARN_TRAV_MINB) k_trace(DevScene sc, PathBuf pb, Queues q, int cur, int first) {
+__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB + 1 : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
-    const uint32_t n_ext = q.counts[cur], n_sh = q.counts[10], n_mis = q.counts[11];
+    const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par; const int first = j == 0;
+    const uint32_t n_ext = *cnt_active(q.counts, par), n_sh = *cnt_nee(q.counts, par, 1), n_mis = *cnt_nee(q.counts, par, 2);
+    if (blockIdx.x == 0 && threadIdx.x < 9) {          // empty the idle counter set (see cnt_* above)
+        uint32_t* z = threadIdx.x == 0 ? cnt_active(q.counts, par ^ 1u) : (threadIdx.x < 6 ? cnt_cls(q.counts, par ^ 1u, threadIdx.x - 1) : cnt_nee(q.counts, par ^ 1u, threadIdx.x - 6));
+        *z = 0u;
+    }
     const uint32_t s1 = (n_ext + 31u) & ~31u, s2 = s1 + ((n_sh + 31u) & ~31u), s3 = s2 + ((n_mis + 31u) & ~31u);
     const uint32_t* __restrict__ ids = q.active[cur];
     // staging state lives in shared memory, not in registers: the traversal below is register-bound (occupancy) and
     // would otherwise carry five row pointers and five fill counters through every walk
     __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
     __shared__ uint32_t stage_fill[ARN_NCLS][ARN_BLOCK / 32];
+    ARN_TRAV_SMEM(trav_sm);
     if ((threadIdx.x & 31u) == 0) {
 #pragma unroll
         for (int c = 0; c < ARN_NCLS; c++) stage_fill[c][threadIdx.x >> 5] = 0;
@@ -205,16 +224,17 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
             if (gi < n_ext) {
                 pid = __ldcs(&ids[gi]);
                 float4 o = __ldcs(&pb.ray_o[pid]), d = __ldcs(&pb.ray_d[pid]);     // streaming: keep L1 for nodes, slots and the stacks
-                TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
+                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
                 HitRec h;
                 trace_ray<false, MODE>(sc, r, h, ctr);
                 __stcs(&pb.hit_prim[pid], h.prim);
-                __stcs(&pb.hit[pid], make_float4(h.t, h.a, h.b, h.c));
+                __stcs(&pb.hit[pid], make_float4(h.prim >= 0 ? r.tmax : ARN_INF, h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
                     if (ref & ARN_PRIM_SPHERE) {
                         mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
-                        pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
+                        const float3 rd = r.d();
+                        pb.ray_d[pid] = make_float4(rd.x, rd.y, rd.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
                     } else mat = sc.meshes[sc.tri_mesh[ref]].material;
                     cls = shading_class(sc.materials[mat]);
                 }
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
             for (int c = 0; c < ARN_NCLS; c++) {
                 WarpStage t; t.row = stage_rows[c][threadIdx.x >> 5]; t.fill = stage_fill[c][threadIdx.x >> 5];
                 __syncwarp();
-                stage_push(t, cls == c, pid, q.cls[c], &q.counts[3 + c]);
+                stage_push(t, cls == c, pid, q.cls[c], cnt_cls(q.counts, par, c));
                 if ((threadIdx.x & 31u) == 0) stage_fill[c][threadIdx.x >> 5] = t.fill;
                 __syncwarp();
             }
@@ -232,8 +252,10 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
             if (j < n_sh) {
                 uint32_t pid = __ldcs(&q.shadow[j]);
                 float4 o = __ldcs(&pb.sh_o[pid]), d = __ldcs(&pb.sh_d[pid]);
-                TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
-                HitRec h; trace_ray<true, MODE>(sc, r, h, ctr);
+                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
+                // the counted instance runs the reference's full closest-hit query (component/mod.rs:35-38) so that its node /
+                // primitive counters are the reference traversal's; the product instances stop at the first hit: same boolean
+                HitRec h; trace_ray<MODE != ARN_TRAV_COUNTED, MODE>(sc, r, h, ctr);
                 __stcs(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
             }
         } else {
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
                 uint32_t pid = __ldcs(&q.mis[j]);
                 float4 o = __ldcs(&pb.mis_o[pid]), d = __ldcs(&pb.mis_d[pid]);
                 float3 wi = f3(d.x, d.y, d.z);
-                TravRay r; trav_init(r, f3(o.x, o.y, o.z), wi, ARN_INF);
+                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), wi, ARN_INF);
                 HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
                 uint32_t lcomp = __float_as_uint(__ldcs(&pb.a2[pid]).w);
                 uint32_t ok = 0;
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
 #pragma unroll
     for (int c = 0; c < ARN_NCLS; c++) {
         WarpStage t; t.row = stage_rows[c][threadIdx.x >> 5]; t.fill = stage_fill[c][threadIdx.x >> 5];
-        stage_flush(t, q.cls[c], &q.counts[3 + c]);
+        stage_flush(t, q.cls[c], cnt_cls(q.counts, par, c));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&q.stats[0], (unsigned long long)n_ext);
@@ -285,8 +307,9 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
 #define SHADE_PLASTIC 2
 #define SHADE_GLASS 3
 template <int KIND>
-__global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int cur) {
+__global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int j) {
     constexpr bool DIFFUSE = KIND == SHADE_DIFFUSE;
+    const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par;      // shade(j) consumes the hits of trace(j)
     constexpr uint32_t LOBES = KIND == SHADE_PLASTIC ? LOBES_PLASTIC : (KIND == SHADE_GLASS ? LOBES_GLASS : LOBES_ALL);
     // One launch over the concatenation of this instance's class queues, each padded to a multiple of 32 so that
     // every warp shades ONE material class.
@@ -294,7 +317,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
     uint32_t seg_start[ARN_NCLS + 1];
     seg_start[0] = 0;
 #pragma unroll
-    for (int k = 0; k < ARN_NCLS; k++) { uint32_t c = (ORDER >> (4 * k)) & 0xFu; seg_start[k + 1] = seg_start[k] + (c < ARN_NCLS ? ((q.counts[3 + c] + 31u) & ~31u) : 0u); }
+    for (int k = 0; k < ARN_NCLS; k++) { uint32_t c = (ORDER >> (4 * k)) & 0xFu; seg_start[k + 1] = seg_start[k] + (c < ARN_NCLS ? ((*cnt_cls(q.counts, par, c) + 31u) & ~31u) : 0u); }
     uint32_t* next = q.active[cur ^ 1];
     __shared__ uint32_t stage_rows[4][ARN_BLOCK / 32][64];
     WarpStage st_next, st_conn, st_sh, st_mis;
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
         for (int j = 1; j < ARN_NCLS; j++) if (gi >= seg_start[j]) { k = (uint32_t)j; base = seg_start[j]; }
         const uint32_t cls = (ORDER >> (4 * k)) & 0xFu;
         const uint32_t i = gi - base;
-        const uint32_t n = q.counts[3 + cls];
+        const uint32_t n = *cnt_cls(q.counts, par, cls);
         const uint32_t* __restrict__ ids = q.cls[cls];
         bool alive = false, nee = false, has_sh = false, has_mis = false;
         uint32_t pid = 0;
@@ -447,20 +470,20 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 }
             }
         }
-        stage_push(st_next, alive, pid, next, &q.counts[cur ^ 1]);
-        stage_push(st_conn, nee, pid, q.connect, &q.counts[2]);
-        stage_push(st_sh, has_sh, pid, q.shadow, &q.counts[10]);
-        stage_push(st_mis, has_mis, pid, q.mis, &q.counts[11]);
+        stage_push(st_next, alive, pid, next, cnt_active(q.counts, par ^ 1u));
+        stage_push(st_conn, nee, pid, q.connect, cnt_nee(q.counts, par ^ 1u, 0));
+        stage_push(st_sh, has_sh, pid, q.shadow, cnt_nee(q.counts, par ^ 1u, 1));
+        stage_push(st_mis, has_mis, pid, q.mis, cnt_nee(q.counts, par ^ 1u, 2));
     }
-    stage_flush(st_next, next, &q.counts[cur ^ 1]);
-    stage_flush(st_conn, q.connect, &q.counts[2]);
-    stage_flush(st_sh, q.shadow, &q.counts[10]);
-    stage_flush(st_mis, q.mis, &q.counts[11]);
+    stage_flush(st_next, next, cnt_active(q.counts, par ^ 1u));
+    stage_flush(st_conn, q.connect, cnt_nee(q.counts, par ^ 1u, 0));
+    stage_flush(st_sh, q.shadow, cnt_nee(q.counts, par ^ 1u, 1));
+    stage_flush(st_mis, q.mis, cnt_nee(q.counts, par ^ 1u, 2));
 }
 
 // ---- resolve: L += beta * (light term + BSDF term) / p_light  (evaluate_direct's sum, pt.rs:89) -----
-__global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q) {
-    const uint32_t n = q.counts[2];
+__global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q, int j) {      // resolve(j): the direct-light terms shade(j) queued, after trace(j + 1) traced their rays
+    const uint32_t n = *cnt_nee(q.counts, ((uint32_t)j + 1u) & 1u, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pid = q.connect[i];
         float4 bo = pb.beta_old[pid];
@@ -476,11 +499,6 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q) {
         pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
     }
 }
-
-// resets the queue counters between bounces (single thread)
-// single-thread counter maintenance between stages (stream order makes these race free)
-__global__ void k_reset(Queues q, uint32_t mask) { for (int i = 0; i < 16; i++) if (mask & (1u << i)) q.counts[i] = 0; }
-__global__ void k_begin_wave(Queues q, uint32_t n) { for (int i = 0; i < 16; i++) q.counts[i] = 0; q.counts[0] = n; }
 
 // ---- K6 accumulate: filtered film splat of every sample of the wave (film.rs:297-319) ---------
 // film filter weights feed sums only (no discrete decision): libdevice f32 sinf (<= 2 ulp) instead of the
@@ -622,16 +640,17 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_const
 
 // ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------
 template <int MODE>
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
                                                              unsigned long long* ctr_out) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
+    ARN_TRAV_SMEM(trav_sm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
-        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        TravRay r; trav_init(r, trav_sm, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
         uint32_t before = ctr[0];
         HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
-        arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? h.t : ARN_INF;
+        arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? r.tmax : ARN_INF;
         hits[i] = o;
         if (COUNT) {   // lane-utilisation probe: sum over warps of the longest ray's node count
             uint32_t steps = ctr[0] - before, mx = steps;
@@ -646,10 +665,11 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(DevS
     }
 }
 template <int MODE>
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+    ARN_TRAV_SMEM(trav_sm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
-        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        TravRay r; trav_init(r, trav_sm, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
         HitRec h; trace_ray<true, MODE>(sc, r, h, nullptr);
         out[i] = h.prim >= 0 ? 1 : 0;
     }

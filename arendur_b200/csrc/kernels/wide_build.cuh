@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_wide_level(const arn_node* __restrict__
         const uint32_t pair[2] = {job.x + 1, job.x + nodes[job.x].offset};
         arn_node rec[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { rec[k].bmin[0] = rec[k].bmin[1] = rec[k].bmin[2] = 0.f; rec[k].bmax[0] = rec[k].bmax[1] = rec[k].bmax[2] = 0.f; rec[k].offset = 0; rec[k].len_axis = ARN_W_EMPTY; }
+        for (int k = 0; k < 4; k++) { rec[k].bmin[0] = rec[k].bmin[1] = rec[k].bmin[2] = ARN_INF; rec[k].bmax[0] = rec[k].bmax[1] = rec[k].bmax[2] = -ARN_INF; rec[k].offset = 0; rec[k].len_axis = ARN_W_EMPTY; }   // empty slot: inverted infinite bounds fail every slab test
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t ch = pair[g];

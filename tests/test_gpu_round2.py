@@ -110,3 +110,61 @@ def test_film_reduce_over_nccl_two_ranks():
                         os.path.join(ROOT, "tests", "mp_film_reduce.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "film reduce OK" in r.stdout
+
+
+@pytest.mark.parametrize("width", [2, 4])
+def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width):
+    """Interior nodes are culled with a cheap conservative slab test, leaves with the reference's (traverse.cuh).  Rays that
+    stress the argument: axis-parallel rays whose origins sit exactly on node planes (0 * inf = NaN in the reference's slab
+    arithmetic: sticky on x, ignored on y / z), direction components of 1e-20 / 1e-38 / denormal, grazing rays along the
+    grid, tmax <= 0, huge origins.  Hit ids and t must equal the oracle's bit for bit."""
+    h = api.HostScene()
+    mat = h.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.7, 0.7, 0.7)))
+    cells = 64
+    pos, idx = scenes.heightfield(cells, -2.0, 2.0, 4.0, 0.15, 0x5EED)
+    h.add_mesh(pos, idx, mat)
+    h.add_sphere(0.4, -0.4, 0.4, 6.28, mat, transform=np.float32([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0.25, -0.5, 3.0, 1]]))
+    d = h.build()
+    rng = np.random.default_rng(width)
+    grid = (-2.0 + 4.0 * np.arange(cells + 1) / cells).astype(np.float32)      # vertex coordinates = node plane coordinates
+    parts = []
+
+    def rays_of(o, dvec, tmax=np.inf):
+        r = np.zeros(o.shape[0], api.RAY_DTYPE)
+        r["o"], r["d"], r["tmax"] = o.astype(np.float32), dvec.astype(np.float32), tmax
+        return r
+    n = 6000
+    # +z rays from grid-aligned origins (ortho-camera like): inv.x = inv.y = inf, origins on x / y planes of many nodes
+    o = np.stack([rng.choice(grid, n), rng.choice(grid, n), np.full(n, 0.5, np.float32)], 1)
+    parts.append(rays_of(o, np.tile(np.float32([0, 0, 1]), (n, 1))))
+    parts.append(rays_of(o + np.float32([0, 0, 8.0]), np.tile(np.float32([0, 0, -1]), (n, 1))))
+    # rays inside the z-range of the surface travelling along x or y, origins on planes of the other axis
+    o = np.stack([np.full(n, -3.0, np.float32), rng.choice(grid, n), rng.uniform(3.85, 4.15, n)], 1)
+    parts.append(rays_of(o, np.tile(np.float32([1, 0, 0]), (n, 1))))
+    o = np.stack([rng.choice(grid, n), np.full(n, 3.0, np.float32), rng.uniform(3.85, 4.15, n)], 1)
+    parts.append(rays_of(o, np.tile(np.float32([0, -1, 0]), (n, 1))))
+    # tiny but non-zero components (regular / irregular boundary of the fast path), -0.0 components
+    for eps in (1e-20, -1e-20, 1e-38, 1e-44, -0.0, 1e-12, -1e-16):
+        o = np.stack([rng.choice(grid, n // 4), rng.uniform(-2, 2, n // 4), np.full(n // 4, 0.5, np.float32)], 1)
+        dv = np.tile(np.float32([eps, 0.3, 1.0]), (n // 4, 1)); dv[:, 1] = rng.uniform(-0.5, 0.5, n // 4)
+        parts.append(rays_of(o, dv))
+    # random rays with finite, zero and negative tmax; huge origins; rays aimed at the sphere
+    o = rng.uniform([-2.5, -2.5, 0.0], [2.5, 2.5, 6.0], (n, 3)); v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    parts.append(rays_of(o, v, rng.choice(np.float32([np.inf, 3.0, 1.0, 0.0, -1.0]), n)))
+    parts.append(rays_of(o * np.float32(1e6), v))
+    tgt = np.float32([0.25, -0.5, 3.0]) + rng.normal(scale=0.3, size=(n, 3)); dv = tgt - o
+    parts.append(rays_of(o, dv / np.linalg.norm(dv, axis=1, keepdims=True)))
+    rays = np.concatenate(parts)
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)
+    try:
+        gh, ga = sc.intersect_closest(rays), sc.intersect_any(rays)
+    finally:
+        ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
+    oh = osc.intersect_closest(rays)
+    assert (oh["prim_id"] >= 0).sum() > rays.shape[0] // 10
+    assert (oh["prim_id"] == d.n_prims - 1).sum() > 100, "the sphere should be reached"
+    mism = np.nonzero((gh["prim_id"] != oh["prim_id"]) | (gh["t"] != oh["t"]))[0]
+    assert mism.size == 0, f"{mism.size} mismatches, first rays {mism[:5]}: o {rays['o'][mism[:3]]} d {rays['d'][mism[:3]]} gpu {gh[mism[:3]]} oracle {oh[mism[:3]]}"
+    assert np.array_equal(ga != 0, oh["prim_id"] >= 0)
+    sc.close(); osc.close()
