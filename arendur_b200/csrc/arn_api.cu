@@ -767,6 +767,47 @@ int arn_render_pt(arn_scene* s, const arn_camera* cam, const arn_film* film, con
 
 }  // extern "C"
 
+// ---------------------------------------------------------------- self test of the fast transcendentals (kernels/cr_math.cuh)
+namespace {
+// every f32 bit pattern: wrapper (short f64 kernel, library fallback) vs the library value rounded once — must be identical
+__global__ void __launch_bounds__(256) k_selftest_math(unsigned long long* out, uint32_t first, uint32_t count_log2) {
+    unsigned long long bad[5] = {0, 0, 0, 0, 0};
+    const unsigned long long n = 1ull << count_log2;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t bits = first + (uint32_t)i;
+        const float x = __uint_as_float(bits);
+        auto same = [](float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); };
+        float s, c; cr_sincosf(x, s, c);
+        double ds, dc; sincos((double)x, &ds, &dc);
+        bad[0] += !same(s, (float)ds) || !same(cr_sinf(x), (float)sin((double)x));
+        bad[1] += !same(c, (float)dc) || !same(cr_cosf(x), (float)cos((double)x));
+        bad[2] += !same(cr_expf(x), (float)exp((double)x));
+        bad[3] += !same(cr_logf(x), (float)log((double)x));
+        const uint32_t h = mix32(bits);                                         // pow: this base, a pseudo-random exponent in [-4, 4] or the Beckmann sampler's [0.4, 1.1]
+        const float b = (h & 1u) ? -4.f + 8.f * u01(h) : 0.4f + 0.7f * u01(h);
+        bad[4] += !same(cr_powf(x, b), (float)pow((double)x, (double)b));
+    }
+    for (int k = 0; k < 5; k++) {
+        unsigned long long v = bad[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&out[k], v);
+    }
+}
+}  // namespace
+
+extern "C" int arn_selftest_math(arn_ctx* c, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5) {
+    if (!c || !mismatches5 || count_log2 > 32) return set_err(c, ARN_E_INVALID, "arn_selftest_math: bad argument");
+    std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 64, c->stream));
+    k_selftest_math<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_ctr, first_bits, count_log2);
+    CUDA_TRY(c, cudaGetLastError());
+    unsigned long long h[5];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->d_ctr, 40, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 5; k++) mismatches5[k] = h[k];
+    return ARN_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU film merge (Film::merge_into across GPUs)
 // NCCL is resolved at first use with dlopen("libnccl.so.2"): a process that already loaded NCCL (torch, or the Rust
 // host's own binding) gets that same copy, a stand-alone host gets the system library, and single-GPU users never

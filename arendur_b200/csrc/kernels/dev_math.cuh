@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "cr_math.cuh"
 
 #define ARN_DEV __device__ __forceinline__
 #define ARN_INF __int_as_float(0x7f800000)
@@ -72,16 +73,17 @@ ARN_DEV bool relative_eq(float a, float b) {     // approx::relative_eq!, eps = 
 // evaluated as correctly-rounded f32 via f64, exactly like the oracle (oracle/geom.hpp): the
 // f32 libdevice versions differ from libm by an ulp, which flips ~1 % of the paths through
 // borderline shadow-ray self-intersections (the reference pulls shadow-ray ends in by only
-// 2*eps).  B200's FP64 pipe runs at half the FP32 rate, so this costs a few % of shading time.
-ARN_NOINL float cr_sinf(float x) { return (float)sin((double)x); }
-ARN_NOINL float cr_cosf(float x) { return (float)cos((double)x); }
+// 2*eps).  sin / cos / log / exp / pow take a short f64 kernel first and the library routine only
+// when the f32 rounding of that value is not certain (cr_math.cuh: same bits by construction).
+ARN_NOINL float cr_sinf(float x) { return cr_sinf_fast(x); }
+ARN_NOINL float cr_cosf(float x) { return cr_cosf_fast(x); }
 // sin and cos of one argument share the range reduction (bit-identical to the separate calls)
-ARN_NOINL void cr_sincosf(float x, float& s, float& c) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
+ARN_NOINL void cr_sincosf(float x, float& s, float& c) { cr_sincosf_fast(x, s, c); }
 ARN_NOINL float cr_acosf(float x) { return (float)acos((double)x); }
 ARN_NOINL float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-ARN_NOINL float cr_logf(float x) { return (float)log((double)x); }
-ARN_NOINL float cr_expf(float x) { return (float)exp((double)x); }
-ARN_NOINL float cr_powf(float a, float b) { return (float)pow((double)a, (double)b); }
+ARN_NOINL float cr_logf(float x) { return cr_logf_fast(x); }
+ARN_NOINL float cr_expf(float x) { return cr_expf_fast(x); }
+ARN_NOINL float cr_powf(float a, float b) { return cr_powf_fast(a, b); }
 
 // column-major 4x4 (cgmath): transform_point with homogeneous divide, transform_vector
 struct Mat4 { float m[16]; };

@@ -65,19 +65,12 @@ struct DevScene {
 // Ray state used by traversal: the slab cache keeps the ORIGINAL origin / 1/dir
 // (bvh.rs:101,112 refreshes only tmax), the shear cache follows the CURRENT ray
 // (ray.rs:136-139), which differs only after a transformed-sphere hit.
-// Register budget: the cache origin (read by a leaf's exact slab test only) and the current direction (read by sphere
-// slots only) live in the calling kernel's shared memory, one column per thread (`ARN_TRAV_SMEM`), not in registers.
-#define ARN_TRAV_SMEM(name) __shared__ float name[6 * ARN_BLOCK]
 struct TravRay {
-    float3 inv;                // cache: 1/dir
-    float3 o;                  // current ray origin
+    float3 co, inv;            // cache: origin (read by a leaf's exact slab test only), 1/dir
+    float3 o, d;               // current ray (d is read by sphere slots only)
     float tmax;
     int kz;                    // 0 = XZ perm, 1 = YZ, 2 = ZZ
     float3 shear;
-    float* sm;                 // this thread's column of the kernel's ARN_TRAV_SMEM array: co.xyz, d.xyz at stride ARN_BLOCK
-    ARN_DEV float3 co() const { return f3(sm[0], sm[ARN_BLOCK], sm[2 * ARN_BLOCK]); }
-    ARN_DEV float3 d() const { return f3(sm[3 * ARN_BLOCK], sm[4 * ARN_BLOCK], sm[5 * ARN_BLOCK]); }
-    ARN_DEV void set_d(float3 v) { sm[3 * ARN_BLOCK] = v.x; sm[4 * ARN_BLOCK] = v.y; sm[5 * ARN_BLOCK] = v.z; }
 };
 // Per-ray constants of the CONSERVATIVE slab test used on interior nodes (cull_setup / slab_cull below).
 struct CullRay {
@@ -93,11 +86,8 @@ ARN_DEV void shear_setup(TravRay& r, float3 d) {           // ShearingTransformC
     else                    { r.kz = 2; dd = d; }
     r.shear = f3(-dd.x / dd.z, -dd.y / dd.z, 1.f / dd.z);
 }
-ARN_DEV void trav_init(TravRay& r, float* trav_sm, float3 o, float3 d, float tmax) {
-    r.sm = trav_sm + threadIdx.x;
-    r.o = o; r.tmax = tmax;
-    r.sm[0] = o.x; r.sm[ARN_BLOCK] = o.y; r.sm[2 * ARN_BLOCK] = o.z;
-    r.set_d(d);
+ARN_DEV void trav_init(TravRay& r, float3 o, float3 d, float tmax) {
+    r.o = o; r.co = o; r.d = d; r.tmax = tmax;
     r.inv = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);            // construct_ray_cache (bbox.rs:583-592)
     shear_setup(r, d);
 }
@@ -110,7 +100,7 @@ ARN_DEV bool slab(const float4 q0, const float4 q1, const TravRay& r, float& t0_
     const float k = 1.f + 2.f * gamma_n(3.f);
     const bool nx = r.inv.x < 0.f, ny = r.inv.y < 0.f, nz = r.inv.z < 0.f;
     const float bminx = q0.x, bminy = q0.y, bminz = q0.z, bmaxx = q0.w, bmaxy = q1.x, bmaxz = q1.y;
-    const float3 co = r.co();
+    const float3 co = r.co;
     float t0 = ((nx ? bmaxx : bminx) - co.x) * r.inv.x;
     float t1 = ((nx ? bminx : bmaxx) - co.x) * r.inv.x;
     float ty0 = ((ny ? bmaxy : bminy) - co.y) * r.inv.y;
@@ -265,7 +255,7 @@ struct HitRec {               // what shading needs from the final hit; its dist
 // becomes the round-tripped one.
 ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& h) {
     const DevSphere& sp = sc.spheres[sc.prims[comp] & ~ARN_PRIM_SPHERE];
-    const float3 d = r.d();
+    const float3 d = r.d;
     float3 lo = r.o, ld = d;
     if (sp.has_transform) { lo = xform_point(sp.parent_local, r.o); ld = xform_vector(sp.parent_local, d); }
     float t; float3 p;
@@ -274,7 +264,7 @@ ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& 
     if (sp.has_transform) {
         r.o = xform_point(sp.local_parent, lo);
         const float3 nd = xform_vector(sp.local_parent, ld);
-        r.set_d(nd);
+        r.d = nd;
         shear_setup(r, nd);
     }
     r.tmax = t;
@@ -364,8 +354,7 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
 // i.e. with the reference's tmax.
 
 // leaf primitives in slot order, strict `<` acceptance (bvh.rs:104-114); returns true when an any-hit query is done
-template <bool ANY>
-ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, TravRay& r, HitRec& h) {
+ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, TravRay& r, HitRec& h, const bool ANY) {
     const uint32_t end = first + count;
     for (uint32_t k = first; k < end; k++) {
         float4 v0 = __ldg(&sc.tris[3 * k]);
@@ -384,8 +373,8 @@ ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, Trav
 }
 
 // Binary walk over the 32-byte pre-order nodes (cache-resident trees).  Stack entry = (node, conservative entry distance).
-template <bool ANY>
-ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h) {
+// `any` (warp-uniform at every call site): stop at the first accepted primitive
+ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
     int sp = 0;
@@ -420,7 +409,7 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const Node8 n = ld_node(sc.nodes + 2 * idx);
             float t0;
             if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
-                if (leaf_prims<ANY>(sc, offset, len_axis >> 2, r, h)) return;
+                if (leaf_prims(sc, offset, len_axis >> 2, r, h, any)) return;
             }
         }
         if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
@@ -443,8 +432,7 @@ ARN_DEV bool trav_pop4(const TravRay& r, const uint2* stack, int& sp, uint32_t& 
         if (__uint_as_float(e.y) < r.tmax) { rec = e.x; return true; }
     }
 }
-template <bool ANY>
-ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h) {
+ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK4];
     int sp = 0;
@@ -456,7 +444,7 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
     uint32_t w0 = __float_as_uint(sc.root1.z), w1 = __float_as_uint(sc.root1.w), rec = 0;
     if ((w1 & 3u) != ARN_W_INNER) {             // a one-leaf tree: the root record is the leaf
         float t0;
-        if (slab(sc.root0, sc.root1, r, t0) && t0 < r.tmax) leaf_prims<ANY>(sc, w0, w1 >> 8, r, h);
+        if (slab(sc.root0, sc.root1, r, t0) && t0 < r.tmax) leaf_prims(sc, w0, w1 >> 8, r, h, any);
         return;
     }
     for (;;) {
@@ -496,7 +484,7 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const Node8 n = ld_node(sc.wide + 2 * (size_t)(rec & ~ARN_REC_LEAF));
             float t0;
             if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
-                if (leaf_prims<ANY>(sc, __float_as_uint(n.q1.z), __float_as_uint(n.q1.w) >> 8, r, h)) return;
+                if (leaf_prims(sc, __float_as_uint(n.q1.z), __float_as_uint(n.q1.w) >> 8, r, h, any)) return;
             }
         }
         if (!trav_pop4(r, stack, sp, rec)) return;
@@ -512,16 +500,19 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
 // out-of-line exact walks for the rare rays the conservative test does not cover (one copy per kernel)
 ARN_NOINL void traverse_exact_closest(const DevScene& sc, TravRay& r, HitRec& h) { traverse<false, false>(sc, r, h, nullptr); }
 ARN_NOINL void traverse_exact_any(const DevScene& sc, TravRay& r, HitRec& h) { traverse<true, false>(sc, r, h, nullptr); }
-template <bool ANY, int MODE>
-ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) {
-    if (MODE == ARN_TRAV_COUNTED) { traverse<ANY, true>(sc, r, h, ctr); return; }
-    if (!ray_is_regular(sc, r)) {                       // axis-parallel / degenerate directions: the reference's arithmetic at every node
-        if (ANY) traverse_exact_any(sc, r, h); else traverse_exact_closest(sc, r, h);
+template <int MODE>
+ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr, const bool any) {
+    if (MODE == ARN_TRAV_COUNTED) {                 // the reference walk, every node with the reference's arithmetic; counts its tests
+        if (any) traverse<true, true>(sc, r, h, ctr); else traverse<false, true>(sc, r, h, ctr);
+        return;
+    }
+    if (!ray_is_regular(sc, r)) {                   // axis-parallel / degenerate directions: the reference's arithmetic at every node
+        if (any) traverse_exact_any(sc, r, h); else traverse_exact_closest(sc, r, h);
         return;
     }
     CullRay c; cull_setup(sc, r, c);
-    if (MODE == ARN_TRAV_WIDE) traverse4<ANY>(sc, r, c, h);
-    else traverse2<ANY>(sc, r, c, h);
+    if (MODE == ARN_TRAV_WIDE) traverse4(sc, r, c, h, any);
+    else traverse2(sc, r, c, h, any);
 }
 
 }  // namespace arn

@@ -212,33 +212,56 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
     // would otherwise carry five row pointers and five fill counters through every walk
     __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
     __shared__ uint32_t stage_fill[ARN_NCLS][ARN_BLOCK / 32];
-    ARN_TRAV_SMEM(trav_sm);
     if ((threadIdx.x & 31u) == 0) {
 #pragma unroll
         for (int c = 0; c < ARN_NCLS; c++) stage_fill[c][threadIdx.x >> 5] = 0;
     }
     __syncwarp();
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {
-        if (gi < s1) {
-            uint32_t pid = 0; int cls = -1;
-            if (gi < n_ext) {
-                pid = __ldcs(&ids[gi]);
-                float4 o = __ldcs(&pb.ray_o[pid]), d = __ldcs(&pb.ray_d[pid]);     // streaming: keep L1 for nodes, slots and the stacks
-                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ARN_INF);
-                HitRec h;
-                trace_ray<false, MODE>(sc, r, h, ctr);
+        // the three kinds of query share ONE inlined walk (instruction-cache footprint): kind and `any` are warp-uniform
+        const uint32_t kind = gi < s1 ? 0u : (gi < s2 ? 1u : 2u);                 // 0 path ray, 1 shadow ray, 2 BSDF-sampled light ray
+        const uint32_t j = gi - (kind == 0u ? 0u : (kind == 1u ? s1 : s2));
+        const uint32_t nk = kind == 0u ? n_ext : (kind == 1u ? n_sh : n_mis);
+        const uint32_t* __restrict__ qk = kind == 0u ? ids : (kind == 1u ? q.shadow : q.mis);
+        const float4* __restrict__ ok = kind == 0u ? pb.ray_o : (kind == 1u ? pb.sh_o : pb.mis_o);
+        const float4* __restrict__ dk = kind == 0u ? pb.ray_d : (kind == 1u ? pb.sh_d : pb.mis_d);
+        uint32_t pid = 0; int cls = -1;
+        if (j < nk) {
+            pid = __ldcs(&qk[j]);
+            const float4 o = __ldcs(&ok[pid]), d = __ldcs(&dk[pid]);       // streaming: keep L1 for nodes, slots and the stacks
+            TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), kind == 1u ? o.w : ARN_INF);
+            HitRec h;
+            // shadow rays: any hit (LightSample::occluded, lighting/mod.rs:125-133).  The counted instance runs the reference's full
+            // closest-hit query there (component/mod.rs:35-38) so that its counters are the reference traversal's: same boolean
+            trace_ray<MODE>(sc, r, h, ctr, kind == 1u && !COUNT);
+            if (kind == 0u) {
                 __stcs(&pb.hit_prim[pid], h.prim);
                 __stcs(&pb.hit[pid], make_float4(h.prim >= 0 ? r.tmax : ARN_INF, h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
                     if (ref & ARN_PRIM_SPHERE) {
                         mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
-                        const float3 rd = r.d();
-                        pb.ray_d[pid] = make_float4(rd.x, rd.y, rd.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
+                        pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
                     } else mat = sc.meshes[sc.tri_mesh[ref]].material;
                     cls = shading_class(sc.materials[mat]);
                 }
+            } else if (kind == 1u) {
+                __stcs(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
+            } else {
+                // `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155)
+                const float3 wi = f3(d.x, d.y, d.z);
+                uint32_t lcomp = __float_as_uint(__ldcs(&pb.a2[pid]).w);
+                uint32_t okl = 0;
+                if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
+                    const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
+                    float3 pos = f3(h.a, h.b, h.c);
+                    if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
+                    okl = is_black(light_le(sp, pos, -wi)) ? 0u : 1u;       // lsi.le(-wi)
+                }
+                __stcs(&pb.mis_ok[pid], okl);
             }
+        }
+        if (kind == 0u) {
 #pragma unroll
             for (int c = 0; c < ARN_NCLS; c++) {
                 WarpStage t; t.row = stage_rows[c][threadIdx.x >> 5]; t.fill = stage_fill[c][threadIdx.x >> 5];
@@ -246,35 +269,6 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
                 stage_push(t, cls == c, pid, q.cls[c], cnt_cls(q.counts, par, c));
                 if ((threadIdx.x & 31u) == 0) stage_fill[c][threadIdx.x >> 5] = t.fill;
                 __syncwarp();
-            }
-        } else if (gi < s2) {
-            uint32_t j = gi - s1;
-            if (j < n_sh) {
-                uint32_t pid = __ldcs(&q.shadow[j]);
-                float4 o = __ldcs(&pb.sh_o[pid]), d = __ldcs(&pb.sh_d[pid]);
-                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
-                // the counted instance runs the reference's full closest-hit query (component/mod.rs:35-38) so that its node /
-                // primitive counters are the reference traversal's; the product instances stop at the first hit: same boolean
-                HitRec h; trace_ray<MODE != ARN_TRAV_COUNTED, MODE>(sc, r, h, ctr);
-                __stcs(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
-            }
-        } else {
-            uint32_t j = gi - s2;
-            if (j < n_mis) {
-                uint32_t pid = __ldcs(&q.mis[j]);
-                float4 o = __ldcs(&pb.mis_o[pid]), d = __ldcs(&pb.mis_d[pid]);
-                float3 wi = f3(d.x, d.y, d.z);
-                TravRay r; trav_init(r, trav_sm, f3(o.x, o.y, o.z), wi, ARN_INF);
-                HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
-                uint32_t lcomp = __float_as_uint(__ldcs(&pb.a2[pid]).w);
-                uint32_t ok = 0;
-                if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
-                    const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
-                    float3 pos = f3(h.a, h.b, h.c);
-                    if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
-                    ok = is_black(light_le(sp, pos, -wi)) ? 0u : 1u;       // lsi.le(-wi)
-                }
-                __stcs(&pb.mis_ok[pid], ok);
             }
         }
     }
@@ -644,12 +638,11 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(cons
                                                              unsigned long long* ctr_out) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
-    ARN_TRAV_SMEM(trav_sm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
-        TravRay r; trav_init(r, trav_sm, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
         uint32_t before = ctr[0];
-        HitRec h; trace_ray<false, MODE>(sc, r, h, ctr);
+        HitRec h; trace_ray<MODE>(sc, r, h, ctr, false);
         arn_hit o; o.prim_id = h.prim; o.t = h.prim >= 0 ? r.tmax : ARN_INF;
         hits[i] = o;
         if (COUNT) {   // lane-utilisation probe: sum over warps of the longest ray's node count
@@ -666,11 +659,10 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(cons
 }
 template <int MODE>
 __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
-    ARN_TRAV_SMEM(trav_sm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
-        TravRay r; trav_init(r, trav_sm, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
-        HitRec h; trace_ray<true, MODE>(sc, r, h, nullptr);
+        TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
+        HitRec h; trace_ray<MODE>(sc, r, h, nullptr, true);
         out[i] = h.prim >= 0 ? 1 : 0;
     }
 }

@@ -355,6 +355,11 @@ int arn_ctx_synchronize(arn_ctx* ctx);
 /* The context's CUDA stream as a cudaStream_t cast to void* (for event timing). */
 void* arn_ctx_stream(arn_ctx* ctx);
 
+/* Diagnostic: runs the fast correctly-rounded sin / cos / exp / log / pow (kernels/cr_math.cuh) over the 2^count_log2 f32 bit
+ * patterns starting at first_bits and counts results that differ from the f64 library value rounded once — the definition
+ * both this library and the oracle use.  mismatches5 = {sin, cos, exp, log, pow}; all must be 0. */
+int arn_selftest_math(arn_ctx* ctx, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5);
+
 /* Library identification: "arendur_b200 <version> sm_100a". */
 const char* arn_version(void);
 

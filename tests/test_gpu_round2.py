@@ -168,3 +168,13 @@ def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width)
     assert mism.size == 0, f"{mism.size} mismatches, first rays {mism[:5]}: o {rays['o'][mism[:3]]} d {rays['d'][mism[:3]]} gpu {gh[mism[:3]]} oracle {oh[mism[:3]]}"
     assert np.array_equal(ga != 0, oh["prim_id"] >= 0)
     sc.close(); osc.close()
+
+
+def test_fast_transcendentals_are_the_library_values_for_every_f32(ctx):
+    """kernels/cr_math.cuh on the device, all 2^32 arguments: the short f64 kernels + rounding-certainty test return exactly
+    (float)libdevice_f64(x) for sin, cos, exp, log (and pow with a pseudo-random exponent per base)."""
+    import ctypes as C
+    out = (C.c_uint64 * 5)()
+    rc = ctx.lib.arn_selftest_math(ctx.c, 0, 32, out)
+    assert rc == 0, ctx.error()
+    assert list(out) == [0, 0, 0, 0, 0], f"mismatches (sin, cos, exp, log, pow) = {list(out)}"
