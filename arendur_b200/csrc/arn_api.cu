@@ -15,6 +15,7 @@
 #include <vector>
 #include "../../include/arn.h"
 #include "kernels/wavefront.cuh"
+#include "kernels/trace_refill.cuh"
 #include "kernels/lbvh.cuh"
 #include "kernels/wide_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -37,7 +38,8 @@ struct arn_ctx {
     // wave pipelines: each owns a stream and a set of wavefront buffers (allocated lazily, sized to the wave
     // capacity).  Consecutive waves of a render go to consecutive pipelines and run concurrently, so the thin
     // late-bounce launches of one wave overlap the wide early launches of the next.  pipes[0] runs on `stream`.
-    struct Pipe { cudaStream_t stream = nullptr; size_t wave_cap = 0; PathBuf pb{}; Queues q{}; void* pool = nullptr; cudaEvent_t done = nullptr; };
+    struct Pipe { cudaStream_t stream = nullptr; size_t wave_cap = 0; PathBuf pb{}; Queues q{}; void* pool = nullptr; cudaEvent_t done = nullptr;
+                  TraceBuf tb{}; void* tb_pool = nullptr; size_t tb_cap = 0; };     // tb: ray-stream buffers of the lane-refilling trace (allocated on first use)
     Pipe pipes[ARN_MAX_PIPES];
     int opt_pipes = 0;           // ARN_OPT_PIPELINES: 0 = auto (4, or 8 for trees large enough for the 4-wide walk)
     // tile tables
@@ -54,6 +56,8 @@ struct arn_ctx {
     int opt_width = 0;           // ARN_OPT_BVH_WIDTH: 0 auto, 2 binary, 4 wide
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
     size_t opt_wave = 0;
+    int opt_refill = 0;          // ARN_OPT_TRACE_REFILL: lane-refilling trace (kernels/trace_refill.cuh) for trees walked with the binary nodes
+    int g_setup = 0, g_refill = 0, g_classify = 0;
 };
 
 struct arn_scene {
@@ -111,26 +115,34 @@ int ensure_wave(arn_ctx* ctx, arn_ctx::Pipe* c, size_t cap) {
     // one pool, carved into 256-byte aligned SoA streams
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    size_t o_ray_o = carve(cap * 16), o_ray_d = carve(cap * 16), o_beta = carve(cap * 16), o_L = carve(cap * 16);
-    size_t o_pfilm = carve(cap * 8), o_pix = carve(cap * 4), o_smp = carve(cap * 4), o_st = carve(cap * 4);
-    size_t o_hp = carve(cap * 4), o_hit = carve(cap * 16);
-    size_t o_sho = carve(cap * 16), o_shd = carve(cap * 16), o_mo = carve(cap * 16), o_md = carve(cap * 16);
-    size_t o_a1 = carve(cap * 16), o_a2 = carve(cap * 16), o_bo = carve(cap * 16), o_occ = carve(cap * 4), o_mok = carve(cap * 4);
+    size_t o_ray = carve(cap * 32), o_beta = carve(cap * 16), o_L = carve(cap * 16);
+    size_t o_pfilm = carve(cap * 8), o_pix = carve(cap * 4), o_smp = carve(cap * 4);
+    size_t o_hit = carve(cap * 16);
+    size_t o_sh = carve(cap * 32), o_mis = carve(cap * 32), o_nee = carve(cap * 64), o_occ = carve(cap * 4), o_mok = carve(cap * 4);
     size_t o_q0 = carve(cap * 4), o_q1 = carve(cap * 4), o_qc = carve(cap * 4), o_qs = carve(cap * 4), o_qm = carve(cap * 4);
     size_t o_cls[ARN_NCLS]; for (int k = 0; k < ARN_NCLS; k++) o_cls[k] = carve(cap * 4);
     size_t o_counts = carve(ARN_NCOUNTS * 4), o_stats = carve(64);
     CUDA_TRY(ctx, cudaMalloc(&c->pool, off));
     char* b = (char*)c->pool;
-    c->pb.ray_o = (float4*)(b + o_ray_o); c->pb.ray_d = (float4*)(b + o_ray_d); c->pb.beta = (float4*)(b + o_beta); c->pb.L = (float4*)(b + o_L);
-    c->pb.pfilm = (float2*)(b + o_pfilm); c->pb.pix = (uint32_t*)(b + o_pix); c->pb.smp = (uint32_t*)(b + o_smp); c->pb.st = (uint32_t*)(b + o_st);
-    c->pb.hit_prim = (int*)(b + o_hp); c->pb.hit = (float4*)(b + o_hit);
-    c->pb.sh_o = (float4*)(b + o_sho); c->pb.sh_d = (float4*)(b + o_shd); c->pb.mis_o = (float4*)(b + o_mo); c->pb.mis_d = (float4*)(b + o_md);
-    c->pb.a1 = (float4*)(b + o_a1); c->pb.a2 = (float4*)(b + o_a2); c->pb.beta_old = (float4*)(b + o_bo);
+    c->pb.ray = (float4*)(b + o_ray); c->pb.beta = (float4*)(b + o_beta); c->pb.L = (float4*)(b + o_L);
+    c->pb.pfilm = (float2*)(b + o_pfilm); c->pb.pix = (uint32_t*)(b + o_pix); c->pb.smp = (uint32_t*)(b + o_smp);
+    c->pb.hit = (float4*)(b + o_hit);
+    c->pb.sh = (float4*)(b + o_sh); c->pb.mis = (float4*)(b + o_mis); c->pb.nee = (float4*)(b + o_nee);
     c->pb.occluded = (uint32_t*)(b + o_occ); c->pb.mis_ok = (uint32_t*)(b + o_mok);
     c->q.active[0] = (uint32_t*)(b + o_q0); c->q.active[1] = (uint32_t*)(b + o_q1); c->q.connect = (uint32_t*)(b + o_qc); c->q.shadow = (uint32_t*)(b + o_qs); c->q.mis = (uint32_t*)(b + o_qm);
     for (int k = 0; k < ARN_NCLS; k++) c->q.cls[k] = (uint32_t*)(b + o_cls[k]);
     c->q.counts = (uint32_t*)(b + o_counts); c->q.stats = (unsigned long long*)(b + o_stats);
     c->wave_cap = cap;
+    return ARN_OK;
+}
+
+int ensure_trace_buf(arn_ctx* ctx, arn_ctx::Pipe* c, size_t wave_cap) {
+    const size_t cap = 3 * wave_cap;                      // path + shadow + light rays of one bounce
+    if (c->tb_cap >= cap) return ARN_OK;
+    if (c->tb_pool) { cudaFree(c->tb_pool); c->tb_pool = nullptr; c->tb_cap = 0; }
+    CUDA_TRY(ctx, cudaMalloc(&c->tb_pool, cap * 6 * sizeof(float4)));
+    c->tb.rs = (float4*)c->tb_pool; c->tb.res = c->tb.rs + 5 * cap; c->tb.cap = (uint32_t)cap;
+    c->tb_cap = cap;
     return ARN_OK;
 }
 
@@ -182,6 +194,8 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_shade_g = grid_for(c, (const void*)k_shade<SHADE_GLASS>);
     c->g_shade_d = grid_for(c, (const void*)k_shade<SHADE_DIFFUSE>);
     c->g_resolve = grid_for(c, (const void*)k_resolve);
+    c->g_setup = grid_for(c, (const void*)k_ray_setup); c->g_refill = grid_for(c, (const void*)k_trace_refill); c->g_classify = grid_for(c, (const void*)k_classify);
+    { const char* e = std::getenv("ARN_REFILL"); if (e) c->opt_refill = std::atoi(e) != 0; }
     c->g_accum = grid_for(c, (const void*)k_accumulate);
     c->g_accum_px = grid_for(c, (const void*)k_accumulate_px);
     c->g_closest = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_BINARY>);
@@ -201,6 +215,7 @@ void arn_ctx_destroy(arn_ctx* c) {
     for (int i = 0; i < ARN_MAX_PIPES; i++) {
         if (c->pipes[i].stream) cudaStreamSynchronize(c->pipes[i].stream);
         if (c->pipes[i].pool) cudaFree(c->pipes[i].pool);
+        if (c->pipes[i].tb_pool) cudaFree(c->pipes[i].tb_pool);
         if (c->pipes[i].done) cudaEventDestroy(c->pipes[i].done);
         if (i > 0 && c->pipes[i].stream) cudaStreamDestroy(c->pipes[i].stream);
     }
@@ -221,6 +236,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
     case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2 or 4"); c->opt_width = (int)value; return ARN_OK;
     case ARN_OPT_PIPELINES: if (value < 0 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 0 (auto) ..8"); c->opt_pipes = (int)value; return ARN_OK;
+    case ARN_OPT_TRACE_REFILL: c->opt_refill = value != 0; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -619,7 +635,12 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const unsigned long long n_waves = (total + cap - 1) / cap;
     // per-kernel event timing needs serial launches: it is only taken with one pipeline (ARN_OPT_PIPELINES = 1)
     const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
-    for (int i = 0; i < np; i++) { int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc; }
+    const bool wide = use_wide(s);
+    const bool refill = c->opt_refill && !wide && !c->opt_count;
+    for (int i = 0; i < np; i++) {
+        int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;
+        if (refill) { rc = ensure_trace_buf(c, &c->pipes[i], c->pipes[i].wave_cap); if (rc != ARN_OK) return rc; }
+    }
 
     WaveParams wp;
     std::memcpy(wp.raster_view, cam->raster_view, 64); std::memcpy(wp.view_parent, cam->view_parent, 64);
@@ -648,7 +669,6 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         if (i > 0) cudaStreamWaitEvent(c->pipes[i].stream, e_begin, 0);       // after the tile tables / whatever the caller queued
         CUDA_TRY(c, cudaMemsetAsync(c->pipes[i].q.stats, 0, 64, c->pipes[i].stream));
     }
-    const bool wide = use_wide(s);
     unsigned long long wave = 0;
     for (unsigned long long base = 0; base < total; base += cap, wave++) {
         arn_ctx::Pipe& P = c->pipes[wave % (unsigned long long)np];
@@ -659,7 +679,13 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         launches += 1;
         auto trace = [&](int j) {
             if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), st); ext_events.push_back({i0, j}); }
-            if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            if (refill) {
+                k_ray_setup<<<c->g_setup, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, P.tb, j);
+                k_trace_refill<<<c->g_refill, ARN_BLOCK, 0, st>>>(s->dev, P.q, P.tb, j);
+                k_classify<<<c->g_classify, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, P.tb, j);
+                launches += 2;
+            }
+            else if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), st);

@@ -114,9 +114,13 @@ ARN_DEV uint32_t mix32(uint32_t h) {
 }
 ARN_DEV float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 struct Sampler {
-    uint32_t k1, k2, i1d, i2d;
+    uint32_t k1, k2, i1d, i2d, key;
     ARN_DEV void init(uint32_t seed, uint32_t px, uint32_t py, uint32_t s, uint32_t n1, uint32_t n2) {
-        uint32_t key = mix32(mix32(mix32(mix32(seed) + px) + py) + s);
+        init_key(mix32(mix32(mix32(mix32(seed) + px) + py) + s), n1, n2);
+    }
+    // the per-sample key travels with the path instead of (pixel, sample index): one word, no re-hashing per bounce
+    ARN_DEV void init_key(uint32_t sample_key, uint32_t n1, uint32_t n2) {
+        key = sample_key;
         k1 = mix32(key ^ 0xA511E9B3u); k2 = mix32(key ^ 0x63D83595u); i1d = n1; i2d = n2;
     }
     ARN_DEV float next() { return u01(mix32(k1 + (i1d++))); }

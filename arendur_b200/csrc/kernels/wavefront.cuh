@@ -32,25 +32,22 @@ namespace arn {
 #define ARN_SHADE_MINB_DIFFUSE 3
 #endif
 
-struct PathBuf {                 // SoA over path slots, capacity W
-    float4* ray_o;               // origin xyz
-    float4* ray_d;               // direction xyz
+// Path state of a wave, SoA over path slots (capacity W).  Streams are laid out by WRITER and in 32-byte records where one
+// stage reads or writes two float4 of the same path, so that a scattered path id costs one DRAM sector per record
+// instead of one per float4 / per 4-byte word (the matte shade instance is bound by exactly this traffic):
+struct PathBuf {
+    float4* ray;                 // 2 per slot: (origin xyz, sampler key) (direction xyz, st); st = bounces | specular << 8 | n1d << 16 | n2d << 24
     float4* beta;                // throughput rgb
     float4* L;                   // radiance rgb
     float2* pfilm;               // film position of the camera sample
-    uint32_t* pix;               // x | y << 16
-    uint32_t* smp;               // sample index
-    uint32_t* st;                // bounces | specular << 8 | n1d << 16 | n2d << 24
-    int* hit_prim;
-    float4* hit;                 // t, a, b, c
-    // next-event-estimation state between k_shade and k_connect
-    float4* sh_o;                // shadow ray origin xyz, tmax
-    float4* sh_d;                // shadow ray direction
-    float4* mis_o;               // BSDF-sampled light ray origin
-    float4* mis_d;               // ... direction (= wi)
-    float4* a1;                  // light-sampling term rgb, w = light choice pdf
-    float4* a2;                  // BSDF-sampling term rgb, w = light component id (bits)
-    float4* beta_old;            // throughput before this bounce's BSDF sample, w = flags (bits)
+    uint32_t* pix;               // x | y << 16          (film stages only: the shade stages carry the sampler key instead)
+    uint32_t* smp;               // sample index         (diagnostics only)
+    float4* hit;                 // (component index bits, -1 = miss; a, b, c): triangle b0,b1,b2 / sphere refined local hit point
+    // next-event-estimation state between k_shade, k_trace and k_resolve
+    float4* sh;                  // 2 per slot: shadow ray (origin xyz, tmax) (direction xyz, -)
+    float4* mis;                 // 2 per slot: BSDF-sampled light ray (origin xyz, -) (direction xyz = wi, light component id bits)
+    float4* nee;                 // 4 per slot: (light-sampling term rgb, light choice pdf) (BSDF-sampling term rgb, flags bits)
+                                 //             (throughput before this bounce's BSDF sample, -) (unused)
     uint32_t* occluded;          // 1 = the shadow ray was blocked (written by k_trace)
     uint32_t* mis_ok;            // 1 = the BSDF-sampled ray reached the chosen light and saw its emission
 };
@@ -168,14 +165,13 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ 
             d = normalize(pfocus - o);
         }
         o = xform_point(p.view_parent, o); d = xform_vector(p.view_parent, d);
-        pb.ray_o[i] = make_float4(o.x, o.y, o.z, 0.f);
-        pb.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+        pb.ray[2 * i] = make_float4(o.x, o.y, o.z, __uint_as_float(sm.key));
+        pb.ray[2 * i + 1] = make_float4(d.x, d.y, d.z, __uint_as_float((0u) | (0u << 8) | (0u << 16) | (2u << 24)));
         pb.beta[i] = make_float4(1.f, 1.f, 1.f, 0.f);
         pb.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         pb.pfilm[i] = pfilm;
         pb.pix[i] = px | (py << 16);
         pb.smp[i] = s;
-        pb.st[i] = (0u) | (0u << 8) | (0u << 16) | (2u << 24);
         q.active[0][i] = i;
     }
 }
@@ -223,25 +219,23 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
         const uint32_t j = gi - (kind == 0u ? 0u : (kind == 1u ? s1 : s2));
         const uint32_t nk = kind == 0u ? n_ext : (kind == 1u ? n_sh : n_mis);
         const uint32_t* __restrict__ qk = kind == 0u ? ids : (kind == 1u ? q.shadow : q.mis);
-        const float4* __restrict__ ok = kind == 0u ? pb.ray_o : (kind == 1u ? pb.sh_o : pb.mis_o);
-        const float4* __restrict__ dk = kind == 0u ? pb.ray_d : (kind == 1u ? pb.sh_d : pb.mis_d);
+        const float4* __restrict__ rk = kind == 0u ? pb.ray : (kind == 1u ? pb.sh : pb.mis);
         uint32_t pid = 0; int cls = -1;
         if (j < nk) {
             pid = __ldcs(&qk[j]);
-            const float4 o = __ldcs(&ok[pid]), d = __ldcs(&dk[pid]);       // streaming: keep L1 for nodes, slots and the stacks
+            const float4 o = __ldcs(&rk[2 * pid]), d = __ldcs(&rk[2 * pid + 1]);   // one 32-byte record; streaming: keep L1 for nodes, slots and the stacks
             TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), kind == 1u ? o.w : ARN_INF);
             HitRec h;
             // shadow rays: any hit (LightSample::occluded, lighting/mod.rs:125-133).  The counted instance runs the reference's full
             // closest-hit query there (component/mod.rs:35-38) so that its counters are the reference traversal's: same boolean
             trace_ray<MODE>(sc, r, h, ctr, kind == 1u && !COUNT);
             if (kind == 0u) {
-                __stcs(&pb.hit_prim[pid], h.prim);
-                __stcs(&pb.hit[pid], make_float4(h.prim >= 0 ? r.tmax : ARN_INF, h.a, h.b, h.c));
+                __stcs(&pb.hit[pid], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
                     if (ref & ARN_PRIM_SPHERE) {
                         mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
-                        pb.ray_d[pid] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);   // `*ray = iray`: the ray leaves traversal round-tripped
+                        pb.ray[2 * pid + 1] = make_float4(r.d.x, r.d.y, r.d.z, d.w);   // `*ray = iray`: the ray leaves traversal round-tripped
                     } else mat = sc.meshes[sc.tri_mesh[ref]].material;
                     cls = shading_class(sc.materials[mat]);
                 }
@@ -250,7 +244,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
             } else {
                 // `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155)
                 const float3 wi = f3(d.x, d.y, d.z);
-                uint32_t lcomp = __float_as_uint(__ldcs(&pb.a2[pid]).w);
+                const uint32_t lcomp = __float_as_uint(d.w);
                 uint32_t okl = 0;
                 if (h.prim >= 0 && (uint32_t)h.prim == lcomp) {            // ptr::eq(light, hit.as_light()) (scene.rs:149)
                     const DevSphere& sp = sc.spheres[sc.prims[lcomp] & ~ARN_PRIM_SPHERE];
@@ -332,15 +326,14 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
         uint32_t pid = 0;
         if (i < n) {
             pid = ids[i];
-            int prim = pb.hit_prim[pid];
+            const float4 hr = pb.hit[pid];
+            const int prim = __float_as_int(hr.x);
             if (prim >= 0) {
-                float4 hr = pb.hit[pid];
-                float4 d4 = pb.ray_d[pid];
+                const float4 o4 = pb.ray[2 * pid], d4 = pb.ray[2 * pid + 1];     // one 32-byte record: (-, sampler key) (direction, st)
                 float3 raydir = f3(d4.x, d4.y, d4.z);
-                uint32_t st = pb.st[pid];
+                uint32_t st = __float_as_uint(d4.w);
                 uint32_t bounces = st & 0xffu; bool spec = ((st >> 8) & 1u) != 0;
-                uint32_t pix = pb.pix[pid];
-                Sampler sm; sm.init(p.seed, pix & 0xffffu, pix >> 16, pb.smp[pid], (st >> 16) & 0xffu, st >> 24);
+                Sampler sm; sm.init_key(__float_as_uint(o4.w), (st >> 16) & 0xffu, st >> 24);
                 float4 b4 = pb.beta[pid]; float3 beta = f3(b4.x, b4.y, b4.z);
                 uint32_t ref = sc.prims[prim];
                 Surf s; uint32_t mat;
@@ -396,8 +389,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                             float3 v = b - a;
                             float len = length(v);
                             float3 vd = v / len;
-                            pb.sh_o[pid] = make_float4(a.x, a.y, a.z, len);
-                            pb.sh_d[pid] = make_float4(vd.x, vd.y, vd.z, 0.f);
+                            pb.sh[2 * pid] = make_float4(a.x, a.y, a.z, len);
+                            pb.sh[2 * pid + 1] = make_float4(vd.x, vd.y, vd.z, 0.f);
                             flags |= NEE_SHADOW; has_sh = true;
                         }
                     }
@@ -417,8 +410,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                         if (!skip) {
                             float3 mo = offset_towards(s, bs.wi);
                             if (!analytic) A2 = f2v * sphere_emission(light) * weight / bs.pdf;
-                            pb.mis_o[pid] = make_float4(mo.x, mo.y, mo.z, 0.f);
-                            pb.mis_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                            pb.mis[2 * pid] = make_float4(mo.x, mo.y, mo.z, 0.f);
+                            pb.mis[2 * pid + 1] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, __uint_as_float(lcomp));
                             flags |= NEE_MIS; has_mis = true;
                         }
                     }
@@ -427,12 +420,13 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                     // they do in the reference, scene.rs:65 + pt.rs:89,152-156).  NaN terms are not "black" and keep their record.
                     nee = has_mis || !is_black(A1) || !(lightpdf > 0.f && lightpdf < ARN_INF) || !(beta.x < ARN_INF && beta.y < ARN_INF && beta.z < ARN_INF);
                     if (nee) {
-                        pb.a1[pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
-                        pb.a2[pid] = make_float4(A2.x, A2.y, A2.z, __uint_as_float(lcomp));
-                        pb.beta_old[pid] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(flags));
+                        pb.nee[4 * pid] = make_float4(A1.x, A1.y, A1.z, lightpdf);
+                        pb.nee[4 * pid + 1] = make_float4(A2.x, A2.y, A2.z, __uint_as_float(flags));
+                        pb.nee[4 * pid + 2] = make_float4(beta.x, beta.y, beta.z, 0.f);
                     }
                 }
                 // sample the BSDF for the next direction (pt.rs:92-107)
+                float3 next_o = f3(0.f, 0.f, 0.f), next_d = next_o;
                 float3 wo = -raydir;
                 Sampled bs = bsdf_sample_k<DIFFUSE, LOBES>(bsdf, wo, sm.next_2d());
                 spec = (bs.type & BXDF_SPECULAR) != 0;
@@ -445,8 +439,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 }
                 if (alive) {
                     float3 no = offset_towards(s, bs.wi);
-                    pb.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f);
-                    pb.ray_d[pid] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                    next_o = no; next_d = bs.wi;
                     bounces += 1;
                     if (bounces >= p.max_depth) alive = false;
                 }
@@ -458,9 +451,10 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                         else beta = beta / (1.f - qq);
                     }
                 }
-                if (alive) {
+                if (alive) {         // the continuation ray: one 32-byte record, the sampler key travels with it
                     pb.beta[pid] = make_float4(beta.x, beta.y, beta.z, 0.f);
-                    pb.st[pid] = (bounces & 0xffu) | ((spec ? 1u : 0u) << 8) | ((sm.i1d & 0xffu) << 16) | (sm.i2d << 24);
+                    pb.ray[2 * pid] = make_float4(next_o.x, next_o.y, next_o.z, o4.w);
+                    pb.ray[2 * pid + 1] = make_float4(next_d.x, next_d.y, next_d.z, __uint_as_float((bounces & 0xffu) | ((spec ? 1u : 0u) << 8) | ((sm.i1d & 0xffu) << 16) | (sm.i2d << 24)));
                 }
             }
         }
@@ -480,12 +474,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q, int
     const uint32_t n = *cnt_nee(q.counts, ((uint32_t)j + 1u) & 1u, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pid = q.connect[i];
-        float4 bo = pb.beta_old[pid];
-        uint32_t flags = __float_as_uint(bo.w);
-        float4 a1 = pb.a1[pid];
+        const float4 a1 = pb.nee[4 * pid], a2 = pb.nee[4 * pid + 1], bo = pb.nee[4 * pid + 2];     // 48 bytes of one 64-byte record
+        uint32_t flags = __float_as_uint(a2.w);
         float3 ret = f3(a1.x, a1.y, a1.z);
         if ((flags & NEE_SHADOW) && pb.occluded[pid]) ret = grey(0.f);
-        if ((flags & NEE_MIS) && pb.mis_ok[pid]) { float4 a2 = pb.a2[pid]; ret = ret + f3(a2.x, a2.y, a2.z); }
+        if ((flags & NEE_MIS) && pb.mis_ok[pid]) ret = ret + f3(a2.x, a2.y, a2.z);
         if (is_black(ret) && a1.w > 0.f && a1.w < ARN_INF && bo.x < ARN_INF && bo.y < ARN_INF && bo.z < ARN_INF) continue;   // L + beta * (+0) = L: leave the radiance stream alone
         float3 term = ret / a1.w;                                        // evaluate_direct(..) / lightpdf
         float4 l4 = pb.L[pid];

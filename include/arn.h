@@ -348,6 +348,8 @@ int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_fil
 #define ARN_OPT_PIPELINES       4   /* 1..8 concurrent wave pipelines; 0 = auto (default): 4, or 8 for large trees (also env ARN_PIPES). Per-kernel
                                        timings in arn_stats (extend_ms, extend_bounce_ms) need serial launches and
                                        are only filled with 1                                                      */
+#define ARN_OPT_TRACE_REFILL    5   /* value != 0: lane-refilling trace (ray stream + persistent warps, kernels/trace_refill.cuh) on trees walked
+                                       with the binary nodes; same bits; also env ARN_REFILL */
 #define ARN_OPT_BVH_WIDTH       3   /* 0 auto (default), 2 binary nodes, 4 the 4-wide collapse; same bits    */
 int arn_ctx_set_option(arn_ctx* ctx, int option, long long value);
 

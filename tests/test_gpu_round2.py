@@ -178,3 +178,25 @@ def test_fast_transcendentals_are_the_library_values_for_every_f32(ctx):
     rc = ctx.lib.arn_selftest_math(ctx.c, 0, 32, out)
     assert rc == 0, ctx.error()
     assert list(out) == [0, 0, 0, 0, 0], f"mismatches (sin, cos, exp, log, pow) = {list(out)}"
+
+
+def test_lane_refilling_trace_is_bit_exact(ctx, cornell_small):
+    """ARN_OPT_TRACE_REFILL: ray stream + persistent warps that hand idle lanes new rays (kernels/trace_refill.cuh).  Same
+    per-ray arithmetic, so every camera sample's radiance, the ray counts and the oracle parity are unchanged."""
+    hs, cam, film, smp, prm = cornell_small
+    sc = ctx.upload(hs.desc()); osc = O.OracleScene(hs.desc())
+    f0, rad0, st0 = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_TRACE_REFILL, 1)
+    try:
+        f1, rad1, st1 = sc.render_pt_samples(cam, film, smp, prm)
+        # a few wave / pipeline shapes (ragged last wave, one pipeline)
+        ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 5000); ctx.set_option(L.ARN_OPT_PIPELINES, 1)
+        f2, rad2, st2 = sc.render_pt_samples(cam, film, smp, prm)
+    finally:
+        ctx.set_option(L.ARN_OPT_TRACE_REFILL, 0); ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0); ctx.set_option(L.ARN_OPT_PIPELINES, 0)
+    assert np.array_equal(rad0, rad1) and np.array_equal(rad0, rad2)
+    assert (st0.extend_rays, st0.shadow_rays, st0.mis_rays) == (st1.extend_rays, st1.shadow_rays, st1.mis_rays) == (st2.extend_rays, st2.shadow_rays, st2.mis_rays)
+    assert np.allclose(f0, f1, rtol=1e-5, atol=1e-6)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    assert np.array_equal(rad1[..., :3], orad[..., :3])
+    sc.close(); osc.close()

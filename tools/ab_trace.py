@@ -7,7 +7,7 @@ import os, sys, json, time
 sys.path.insert(0, os.environ["ARN_ROOT"])
 import numpy as np, torch
 from arendur_b200 import api, scenes, _lib as L
-out = {"lib": os.environ.get("ARN_LIB_PATH", "default")}
+out = {"lib": os.environ.get("ARN_LIB_PATH", "default") + ("+refill" if os.environ.get("ARN_REFILL") else "")}
 ctx = api.Context(0)
 def run(name, hs, cam, film, smp, prm, reps):
     sc = ctx.upload(hs.desc())
@@ -36,6 +36,8 @@ print("AB " + json.dumps(out))
 libs = [a for a in sys.argv[1:] if not a.startswith("--")]
 for lib in libs:
     env = dict(os.environ, ARN_ROOT=ROOT, AB_C4="1" if "--c4" in sys.argv else "0")
+    if lib.endswith("+refill"):                 # the lane-refilling trace of the same build
+        env["ARN_REFILL"] = "1"; lib = lib[:-7]
     if lib != "default":
         env["ARN_LIB_PATH"] = os.path.abspath(lib)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
