@@ -314,9 +314,11 @@ def main():
         return st, 2 if rank == 0 else 1          # + the memset, + the merge kernel
 
     # ---- warm-up
+    warm_rays = []
     with torch.cuda.stream(ext):
         for w in range(args.warmup):
-            device_step(w)
+            stw, _ = device_step(w)
+            warm_rays.append(int(stw.extend_rays + stw.shadow_rays + stw.mis_rays))
     barrier()
     film_acc.zero_()
     # ---- timed: device-resident film
@@ -461,6 +463,7 @@ def main():
                        "film_reduce": "per step: arn_film_reduce (ncclReduce, sum to rank 0) of the step's films + arn_film_merge into the running film, inside the timed region" if world > 1 else "none (1 GPU)"},
             "spp_per_s": samples_all / (total_ms_max * 1e-3),
             "rays_per_sample": rays_all / max(1.0, samples_all),
+            "rays_warmup_step0_rank0": warm_rays[0],     # the step profiles/roofline_traffic.json's ncu capture covers (tools/roofline_from_ncu.py)
             "e2e": {"value": e2e_rays_all / (e2e_ms_max * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_bytes,
                     "d2h_bytes_per_step": NPIX * 16, "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps},
             "gpu_launches": int(launches_all),
