@@ -193,7 +193,10 @@ ARN_DEV int shading_class(const arn_material& m) {
 template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 // the 4-wide instance serves trees that miss the caches: it trades a few spills for a fourth resident block per SM
 // (64 registers; C4 k_trace 36.3 -> 35.9 ms, whole frame +4 %); the binary instance stays at three (80 registers)
-__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB + 1 : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
+#ifndef ARN_TRAV_MINB_WIDE
+#define ARN_TRAV_MINB_WIDE (ARN_TRAV_MINB + 1)
+#endif
+__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par; const int first = j == 0;

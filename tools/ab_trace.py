@@ -29,6 +29,15 @@ def run(name, hs, cam, film, smp, prm, reps):
 hs, cam, film, smp, prm = scenes.cornell_scene(1024, 1024, 32, 32)
 run("c3_16spp", hs, cam, film, smp, api.make_pt_params(max_depth=8, spp_begin=0, spp_end=16), 3)
 if os.environ.get("AB_C4") == "1":
+    hs2, cam2, film2 = scenes.c2_heightfield_scene()
+    sc2 = ctx.upload(hs2.desc())
+    rays = scenes.pixel_center_rays(cam2, 1920, 1080); n = rays.shape[0]
+    rd = torch.from_numpy(rays.view("u1").reshape(n, 28)).cuda(); hd = torch.empty((n, 8), dtype=torch.uint8, device="cuda")
+    ms = []
+    for k in range(8):
+        st = L.Stats(); sc2.intersect_closest_dev(rd.data_ptr(), n, hd.data_ptr(), st); ms.append(st.gpu_ms)
+    out["c2_primary_ms"] = min(ms[3:]); out["c2_mrays_s"] = n / min(ms[3:]) / 1e3
+    sc2.close()
     hs, cam, film, smp, prm = scenes.c4_box_scene()
     run("c4", hs, cam, film, smp, prm, 3)
 print("AB " + json.dumps(out))
