@@ -18,6 +18,7 @@ ARN_LIGHT_POINT, ARN_LIGHT_SPOT, ARN_LIGHT_DISTANT = 0, 1, 2
 ARN_LIGHT_ANALYTIC = 0x80000000
 ARN_FILTER_LANCZOS, ARN_FILTER_BOX, ARN_FILTER_TRIANGLE, ARN_FILTER_GAUSSIAN, ARN_FILTER_MITCHELL = 0, 1, 2, 3, 4
 ARN_MAT_MATTE, ARN_MAT_PLASTIC, ARN_MAT_GLASS, ARN_MAT_TRANSLUCENT = 0, 1, 2, 3
+ARN_WRAP_REPEAT, ARN_WRAP_BLACK, ARN_WRAP_CLAMP = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)
 c_u32_p = C.POINTER(C.c_uint32)
@@ -29,7 +30,15 @@ class Node(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("sigma", C.c_float),
-                ("roughness", C.c_float), ("alpha", C.c_float), ("eta", C.c_float), ("dissolve", C.c_float)]
+                ("roughness", C.c_float), ("alpha", C.c_float), ("eta", C.c_float), ("dissolve", C.c_float),
+                ("kd_tex", C.c_uint32), ("ks_tex", C.c_uint32), ("aux_tex", C.c_uint32), ("bump_tex", C.c_uint32)]
+
+
+class Texture(C.Structure):
+    """arn_texture: an ImageTexture's mip pyramid + UVMapping (include/arn.h)."""
+    _fields_ = [("channels", C.c_uint32), ("n_levels", C.c_uint32), ("trilinear", C.c_uint32), ("wrapping", C.c_uint32), ("max_aniso", C.c_float),
+                ("scale_u", C.c_float), ("scale_v", C.c_float), ("shift_u", C.c_float), ("shift_v", C.c_float),
+                ("level_w", C.c_uint32 * 16), ("level_h", C.c_uint32 * 16), ("level_offset", C.c_uint32 * 16)]
 
 
 class Mesh(C.Structure):
@@ -59,7 +68,8 @@ class SceneDesc(C.Structure):
                 ("n_nodes", C.c_uint32), ("nodes", C.POINTER(Node)), ("order", c_u32_p),
                 ("n_lights", C.c_uint32), ("light_prims", c_u32_p), ("light_func", c_float_p), ("light_cdf", c_float_p),
                 ("light_func_integral", C.c_float),
-                ("n_analytic_lights", C.c_uint32), ("analytic_lights", C.POINTER(AnalyticLight))]
+                ("n_analytic_lights", C.c_uint32), ("analytic_lights", C.POINTER(AnalyticLight)),
+                ("n_textures", C.c_uint32), ("textures", C.POINTER(Texture)), ("n_texel_floats", C.c_uint64), ("texels", c_float_p)]
 
 
 class Camera(C.Structure):
@@ -109,7 +119,7 @@ ARN_H_SYMBOLS = [
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
-    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_spot_light_make", "arn_point_light_make",
+    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_hscene_add_texture", "arn_spot_light_make", "arn_point_light_make",
     "arn_distant_light_make", "arn_hscene_load_obj", "arn_hscene_load_json",
     "arn_hscene_build", "arn_hscene_build_gpu", "arn_hscene_desc", "arn_camera_make", "arn_ortho_camera_make", "arn_save_png",
 ]
@@ -162,6 +172,7 @@ def load():
         "arn_hscene_add_mesh": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32]),
         "arn_hscene_add_sphere": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, vp, vp]),
         "arn_hscene_add_light": (C.c_int, [vp, C.POINTER(AnalyticLight)]),
+        "arn_hscene_add_texture": (C.c_int, [vp, C.POINTER(Texture), vp, C.c_uint64]),
         "arn_spot_light_make": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.POINTER(AnalyticLight)]),
         "arn_point_light_make": (C.c_int, [vp, vp, C.POINTER(AnalyticLight)]),
         "arn_distant_light_make": (C.c_int, [vp, vp, C.c_float, C.POINTER(AnalyticLight)]),

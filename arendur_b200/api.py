@@ -84,8 +84,10 @@ def make_pt_params(max_depth=8, rank=0, world_size=1, spp_begin=0, spp_end=0, ti
     return p
 
 
-def material(kind, kd=(0, 0, 0), ks=(0, 0, 0), sigma=0.0, roughness=0.0, eta=1.0, dissolve=1.0):
+def material(kind, kd=(0, 0, 0), ks=(0, 0, 0), sigma=0.0, roughness=0.0, eta=1.0, dissolve=1.0, kd_tex=0, ks_tex=0, aux_tex=0, bump_tex=0):
+    """*_tex: ids returned by HostScene.add_texture (0 = the constant): RGB textures for kd / ks, Luma for sigma|roughness (aux) and bump."""
     m = L.Material()
+    m.kd_tex, m.ks_tex, m.aux_tex, m.bump_tex = kd_tex, ks_tex, aux_tex, bump_tex
     m.type = kind
     m.kd[:] = kd
     m.ks[:] = ks
@@ -134,6 +136,21 @@ class HostScene:
         em = _f32(emission).reshape(3) if emission is not None else None
         tr = _f32(transform).reshape(16) if transform is not None else None
         return self._check(self.lib.arn_hscene_add_sphere(self.h, radius, zmin, zmax, phimax, material_id, _ptr(em), _ptr(tr)))
+
+    def add_texture(self, levels, trilinear=True, max_aniso=8.0, wrapping=L.ARN_WRAP_REPEAT, scaling=(1.0, 1.0), shifting=(0.0, 0.0)):
+        """An ImageTexture with a ready-made pyramid: `levels` = list of float32 arrays (h, w, 3) or (h, w) (Luma), finest first.
+        Returns the id for api.material(..., kd_tex=id)."""
+        t = L.Texture()
+        lv = [_f32(a) for a in levels]
+        t.channels = 3 if lv[0].ndim == 3 else 1
+        t.n_levels, t.trilinear, t.wrapping, t.max_aniso = len(lv), int(bool(trilinear)), wrapping, max_aniso
+        t.scale_u, t.scale_v = scaling; t.shift_u, t.shift_v = shifting
+        off = 0
+        for i, a in enumerate(lv):
+            t.level_h[i], t.level_w[i], t.level_offset[i] = a.shape[0], a.shape[1], off
+            off += a.size
+        flat = np.ascontiguousarray(np.concatenate([a.reshape(-1) for a in lv]), dtype=np.float32)
+        return self._check(self.lib.arn_hscene_add_texture(self.h, C.byref(t), _ptr(flat), flat.size))
 
     def add_light(self, light):
         """`lights.push(light.to_arc())` for a Point / Spot / Distant light (examples/arencli.rs:95-98)."""

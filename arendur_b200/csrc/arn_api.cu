@@ -39,7 +39,8 @@ struct arn_ctx {
     // capacity).  Consecutive waves of a render go to consecutive pipelines and run concurrently, so the thin
     // late-bounce launches of one wave overlap the wide early launches of the next.  pipes[0] runs on `stream`.
     struct Pipe { cudaStream_t stream = nullptr; size_t wave_cap = 0; PathBuf pb{}; Queues q{}; void* pool = nullptr; cudaEvent_t done = nullptr;
-                  TraceBuf tb{}; void* tb_pool = nullptr; size_t tb_cap = 0; };     // tb: ray-stream buffers of the lane-refilling trace (allocated on first use)
+                  TraceBuf tb{}; void* tb_pool = nullptr; size_t tb_cap = 0;
+                  void* diff_pool = nullptr; size_t diff_cap = 0; };                // ray-differential stream (textured scenes)     // tb: ray-stream buffers of the lane-refilling trace (allocated on first use)
     Pipe pipes[ARN_MAX_PIPES];
     int opt_pipes = 0;           // ARN_OPT_PIPELINES: 0 = auto (4, or 8 for trees large enough for the 4-wide walk)
     // tile tables
@@ -57,7 +58,7 @@ struct arn_ctx {
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
     size_t opt_wave = 0;
     int opt_refill = 0;          // ARN_OPT_TRACE_REFILL: lane-refilling trace (kernels/trace_refill.cuh) for trees walked with the binary nodes
-    int g_setup = 0, g_refill = 0, g_classify = 0;
+    int g_setup = 0, g_refill = 0, g_classify = 0, g_shade_tex = 0;
 };
 
 struct arn_scene {
@@ -136,6 +137,16 @@ int ensure_wave(arn_ctx* ctx, arn_ctx::Pipe* c, size_t cap) {
     return ARN_OK;
 }
 
+int ensure_diff_buf(arn_ctx* ctx, arn_ctx::Pipe* c) {
+    if (c->diff_cap < c->wave_cap) {
+        if (c->diff_pool) { cudaFree(c->diff_pool); c->diff_pool = nullptr; c->diff_cap = 0; }
+        CUDA_TRY(ctx, cudaMalloc(&c->diff_pool, c->wave_cap * 4 * sizeof(float4)));
+        c->diff_cap = c->wave_cap;
+    }
+    c->pb.diff = (float4*)c->diff_pool;
+    return ARN_OK;
+}
+
 int ensure_trace_buf(arn_ctx* ctx, arn_ctx::Pipe* c, size_t wave_cap) {
     const size_t cap = 3 * wave_cap;                      // path + shadow + light rays of one bounce
     if (c->tb_cap >= cap) return ARN_OK;
@@ -190,6 +201,7 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
     c->g_shade = grid_for(c, (const void*)k_shade<SHADE_GENERIC>);
+    c->g_shade_tex = grid_for(c, (const void*)k_shade<SHADE_GENERIC, true>);
     c->g_shade_p = grid_for(c, (const void*)k_shade<SHADE_PLASTIC>);
     c->g_shade_g = grid_for(c, (const void*)k_shade<SHADE_GLASS>);
     c->g_shade_d = grid_for(c, (const void*)k_shade<SHADE_DIFFUSE>);
@@ -216,6 +228,7 @@ void arn_ctx_destroy(arn_ctx* c) {
         if (c->pipes[i].stream) cudaStreamSynchronize(c->pipes[i].stream);
         if (c->pipes[i].pool) cudaFree(c->pipes[i].pool);
         if (c->pipes[i].tb_pool) cudaFree(c->pipes[i].tb_pool);
+        if (c->pipes[i].diff_pool) cudaFree(c->pipes[i].diff_pool);
         if (c->pipes[i].done) cudaEventDestroy(c->pipes[i].done);
         if (i > 0 && c->pipes[i].stream) cudaStreamDestroy(c->pipes[i].stream);
     }
@@ -294,6 +307,21 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
         if (d->light_prims[i] >= d->n_prims || !(d->prims[d->light_prims[i]] & ARN_PRIM_SPHERE))
             return set_err(c, ARN_E_UNSUPPORTED, "lights must be emissive sphere primitives (triangle emitters do not work in arendur: surface_area() == 0, SURVEY.md Appendix A-2)");
     }
+    if (d->n_textures && (!d->textures || !d->texels)) return set_err(c, ARN_E_INVALID, "arn_scene_upload: n_textures > 0 but textures / texels is NULL");
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const arn_texture& t = d->textures[i];
+        if ((t.channels != 1 && t.channels != 3) || t.n_levels < 1 || t.n_levels > ARN_TEX_MAX_LEVELS || t.wrapping > ARN_WRAP_CLAMP) return set_err(c, ARN_E_INVALID, "texture: channels must be 1 or 3, 1..16 levels, a valid wrap mode");
+        for (uint32_t l = 0; l < t.n_levels; l++)
+            if (!t.level_w[l] || !t.level_h[l] || (uint64_t)t.level_offset[l] + (uint64_t)t.level_w[l] * t.level_h[l] * t.channels > d->n_texel_floats) return set_err(c, ARN_E_INVALID, "texture level outside the texel array");
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const arn_material& m = d->materials[i];
+        const uint32_t ids[4] = {m.kd_tex, m.ks_tex, m.aux_tex, m.bump_tex};
+        for (int k = 0; k < 4; k++) {
+            if (ids[k] > d->n_textures) return set_err(c, ARN_E_INVALID, "material references a missing texture");
+            if (ids[k] && d->textures[ids[k] - 1].channels != (k < 2 ? 3u : 1u)) return set_err(c, ARN_E_INVALID, "kd / ks take RGB textures, sigma / roughness / bump Luma textures");
+        }
+    }
     lap("reference validation");
     // tree walk: bounds of child offsets, leaf ranges, maximum stack depth
     uint32_t max_depth = 0;
@@ -326,7 +354,8 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
                      + align256((size_t)d->n_spheres * sizeof(arn_sphere)) + align256((size_t)d->n_triangles * 12) + align256((size_t)d->n_vertices * 12) * 2
                      + align256((size_t)d->n_vertices * 8) + align256((size_t)d->n_triangles * 4) + align256((size_t)d->n_meshes * sizeof(arn_mesh))
                      + align256((size_t)d->n_materials * sizeof(arn_material)) + align256((size_t)d->n_prims * 4) + align256((size_t)d->n_lights * 4) * 2
-                     + align256((size_t)d->n_analytic_lights * sizeof(arn_analytic_light)) + align256(((size_t)d->n_lights + 1) * 4) + 4096;
+                     + align256((size_t)d->n_analytic_lights * sizeof(arn_analytic_light)) + align256(((size_t)d->n_lights + 1) * 4) + 4096
+                     + align256((size_t)d->n_textures * sizeof(arn_texture)) + align256((size_t)d->n_texel_floats * 4);
         void* pool = nullptr;
         cudaError_t ce = cudaMalloc(&pool, total);
         if (ce != cudaSuccess) { set_err(c, ARN_E_OOM, std::string("scene memory: ") + cudaGetErrorString(ce)); return fail(ARN_E_OOM); }
@@ -396,6 +425,11 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if ((rc = dev_upload(s, d->analytic_lights, d->n_analytic_lights, &s->dev.analytic)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_func, d->n_lights, &s->dev.light_func)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->light_cdf, d->n_lights ? d->n_lights + 1 : 0, &s->dev.light_cdf)) != ARN_OK) return fail(rc);
+    if (d->n_textures) {
+        if ((rc = dev_upload(s, d->textures, d->n_textures, &s->dev.textures)) != ARN_OK) return fail(rc);
+        if ((rc = dev_upload(s, d->texels, (size_t)d->n_texel_floats, &s->dev.texels)) != ARN_OK) return fail(rc);
+        s->dev.n_textures = d->n_textures;
+    }
     for (uint32_t i = 0; i < d->n_materials; i++) {
         const arn_material& m = d->materials[i];
         int cls = m.type == ARN_MAT_MATTE ? (!(m.sigma >= 0.f && m.sigma != 0.f) && !(m.sigma != m.sigma) ? 0 : 1) : (m.type == ARN_MAT_PLASTIC ? 2 : (m.type == ARN_MAT_GLASS ? 3 : 4));
@@ -637,9 +671,11 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
     const bool wide = use_wide(s);
     const bool refill = c->opt_refill && !wide && !c->opt_count;
+    const bool textured = s->dev.n_textures != 0;
     for (int i = 0; i < np; i++) {
         int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;
         if (refill) { rc = ensure_trace_buf(c, &c->pipes[i], c->pipes[i].wave_cap); if (rc != ARN_OK) return rc; }
+        if (textured) { rc = ensure_diff_buf(c, &c->pipes[i]); if (rc != ARN_OK) return rc; }
     }
 
     WaveParams wp;
@@ -658,6 +694,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     wp.seed = smp->seed; wp.max_depth = prm->max_depth; wp.min_depth = prm->min_depth; wp.rr_threshold = prm->rr_threshold;
     wp.n_tiles = (uint32_t)rects.size(); wp.tile_rect = c->d_tile_rect; wp.tile_prefix = c->d_tile_prefix;
     wp.spp_begin = s0; wp.spp_count = s1 - s0;
+    wp.textured = textured ? 1u : 0u; wp.spp_total = spp;
 
     size_t ev = 0;
     cudaEvent_t e_begin = get_event(c, ev++), e_end = get_event(c, ev++);
@@ -695,10 +732,13 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         for (uint32_t b = 0; b < prm->max_depth; b++) {
             // shade(b): consumes the class queues of trace(b), fills the next active queue + connect / shadow / light-ray queues
             // heavy classes first: the tail of the bounce is cheap Lambert work
+            if (textured) { k_shade<SHADE_GENERIC, true><<<c->g_shade_tex, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            else {
             if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
             if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
             if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
             if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            }
             trace((int)b + 1);                                     // path rays of bounce b+1, shadow + light rays of bounce b
             k_resolve<<<c->g_resolve, ARN_BLOCK, 0, st>>>(P.pb, P.q, (int)b);
             launches += 2;

@@ -33,6 +33,8 @@ public:
     std::vector<uint32_t> light_list;             // Scene.lights: analytic lights, then light_prims
     std::vector<float> light_func, light_cdf;
     float light_integral = 0.f;
+    std::vector<arn_texture> textures;            // image textures (N4): finished pyramids handed in by the caller
+    std::vector<float> texels;
     bool any_normals = false, any_uvs = false, built = false;
     arn_scene_desc desc;
     std::string err;
@@ -44,6 +46,7 @@ public:
     int add_material(const arn_material& m_in) {
         arn_material m = m_in;
         if (m.type > ARN_MAT_TRANSLUCENT) return fail(ARN_E_INVALID, "unknown material type");
+        if (m.kd_tex > textures.size() || m.ks_tex > textures.size() || m.aux_tex > textures.size() || m.bump_tex > textures.size()) return fail(ARN_E_INVALID, "material references a texture that was not added");
         if (m.type == ARN_MAT_MATTE) {
             // MatteMaterial::compute_scattering clamps sigma to [0, 90] (material/matte.rs:50-54)
             if (m.sigma < 0.f) m.sigma = 0.f; else if (!(m.sigma < 90.f)) m.sigma = 90.f;
@@ -126,6 +129,20 @@ public:
         if (s.emissive && in_lights) light_prims.push_back(comp);                // `lights.push(sp.clone())`
         built = false;
         return (int)comp;
+    }
+
+    // ImageTexture::new's result, flattened: `t.level_offset` is relative to `level_texels` on entry.  Returns the id materials use (k + 1).
+    int add_texture(const arn_texture& t_in, const float* level_texels, uint64_t n_floats) {
+        arn_texture t = t_in;
+        if ((t.channels != 1 && t.channels != 3) || t.n_levels < 1 || t.n_levels > ARN_TEX_MAX_LEVELS || t.wrapping > ARN_WRAP_CLAMP || !level_texels)
+            return fail(ARN_E_INVALID, "texture: channels must be 1 or 3, 1..16 levels, a valid wrap mode");
+        for (uint32_t l = 0; l < t.n_levels; l++) {
+            if (!t.level_w[l] || !t.level_h[l] || (uint64_t)t.level_offset[l] + (uint64_t)t.level_w[l] * t.level_h[l] * t.channels > n_floats) return fail(ARN_E_INVALID, "texture level outside the texel array");
+            t.level_offset[l] += (uint32_t)texels.size();
+        }
+        texels.insert(texels.end(), level_texels, level_texels + n_floats);
+        textures.push_back(t); built = false;
+        return (int)textures.size();
     }
 
     int add_light(const arn_analytic_light& l) {
@@ -224,6 +241,8 @@ public:
         desc.n_lights = (uint32_t)light_list.size(); desc.light_prims = light_list.data();
         desc.n_analytic_lights = (uint32_t)analytic.size(); desc.analytic_lights = analytic.data();
         desc.light_func = light_func.data(); desc.light_cdf = light_cdf.data(); desc.light_func_integral = light_integral;
+        desc.n_textures = (uint32_t)textures.size(); desc.textures = textures.empty() ? nullptr : textures.data();
+        desc.n_texel_floats = texels.size(); desc.texels = texels.empty() ? nullptr : texels.data();
     }
 };
 

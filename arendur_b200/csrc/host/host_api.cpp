@@ -152,6 +152,7 @@ int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, f
     if (!h) return ARN_E_INVALID;
     return h->fs.add_sphere(radius, zmin, zmax, phimax, material, emission3, transform16);
 }
+int arn_hscene_add_texture(arn_hscene* h, const arn_texture* tex, const float* texels, uint64_t n_floats) { if (!h || !tex) return ARN_E_INVALID; return h->fs.add_texture(*tex, texels, n_floats); }
 int arn_hscene_add_light(arn_hscene* h, const arn_analytic_light* light) { if (!h || !light) return ARN_E_INVALID; return h->fs.add_light(*light); }
 
 int arn_point_light_make(const float* pos3, const float* intensity3, arn_analytic_light* out) {

@@ -58,8 +58,15 @@ ARN_DEV void get_basis_from(float3 dir, float3& u, float3& v) {         // found
     v = normalize(cross(dir, u));
 }
 
+// what the textured shade instance needs beyond Surf (kernels/shade_tex.cuh)
+struct SurfTex {
+    float2 uv;                    // si.uv
+    float3 duv_dpdu, duv_dpdv;    // si.duv: the shading frame for triangles (set_shading writes duv, quirk A-7), the (transformed) geometric one for spheres
+    float3 sh_dpdv, sh_dndu, sh_dndv;   // si.shading_duv beyond dpdu (= Surf.dpdu): geometric dpdv; dn = 0 for triangles, Weingarten for spheres
+};
+
 // triangle hit -> Surf (triangle.rs:453-484 with interaction.rs:133-182)
-ARN_DEV void surf_triangle(const DevScene& sc, uint32_t tri, float b0, float b1, float b2, float3 raydir, Surf& s) {
+ARN_DEV void surf_triangle(const DevScene& sc, uint32_t tri, float b0, float b1, float b2, float3 raydir, Surf& s, SurfTex* x = nullptr) {
     uint32_t i0 = __ldg(&sc.indices[3 * tri]), i1 = __ldg(&sc.indices[3 * tri + 1]), i2 = __ldg(&sc.indices[3 * tri + 2]);
     float3 p0 = ld3(sc.positions, i0), p1 = ld3(sc.positions, i1), p2 = ld3(sc.positions, i2);
     arn_mesh mesh = sc.meshes[__ldg(&sc.tri_mesh[tri])];
@@ -88,11 +95,17 @@ ARN_DEV void surf_triangle(const DevScene& sc, uint32_t tri, float b0, float b1,
     float3 n = normalize(cross(st, sbt));
     if (dot(s.ng, n) < 0.f) n = -n;
     s.ns = n;
+    if (x) {
+        float2 a = f2(b0 * uv0.x, b0 * uv0.y), b = f2(b1 * uv1.x, b1 * uv1.y), c = f2(b2 * uv2.x, b2 * uv2.y);
+        x->uv = f2((a.x + b.x) + c.x, (a.y + b.y) + c.y);                // uvhit (triangle.rs:465)
+        x->duv_dpdu = st; x->duv_dpdv = sbt;
+        x->sh_dpdv = dpdv; x->sh_dndu = f3(0.f, 0.f, 0.f); x->sh_dndv = f3(0.f, 0.f, 0.f);
+    }
 }
 
 // sphere hit (local refined point p) -> Surf in world space
 // (sphere.rs:250-290, interaction.rs:133-162,190-201, transformed.rs:73-83)
-ARN_DEV void surf_sphere(const DevSphere& sp, float3 p, float3 raydir_after, Surf& s) {
+ARN_DEV void surf_sphere(const DevSphere& sp, float3 p, float3 raydir_after, Surf& s, SurfTex* x = nullptr) {
     float phimax = sp.phimax;
     float thetadelta = sp.thetamax - sp.thetamin;
     float theta = cr_acosf(p.z / sp.radius);
@@ -107,6 +120,24 @@ ARN_DEV void surf_sphere(const DevSphere& sp, float3 p, float3 raydir_after, Sur
         s.ns = s.ng;
         s.dpdu = xform_vector(sp.local_parent, dpdu);
     } else { s.pos = p; s.ng = n; s.ns = n; s.dpdu = dpdu; }
+    if (x) {                                                        // uv and the Weingarten dn (sphere.rs:252-279), transformed like the rest
+        float phi = cr_atan2f(p.y, p.x);
+        if (phi < 0.f) phi += 2.f * ARN_PI;
+        x->uv = f2(phi / phimax, (theta - sp.thetamin) / thetadelta);
+        float3 dppduu = -phimax * phimax * f3(p.x, p.y, 0.f);
+        float3 dppduv = thetadelta * p.z * phimax * f3(-sin_phi, cos_phi, 0.f);
+        float3 dppdvv = -thetadelta * thetadelta * f3(p.x, p.y, p.z);
+        float e = dot(dpdu, dpdu), f = dot(dpdu, dpdv), g = dot(dpdv, dpdv);
+        float ee = dot(n, dppduu), ff = dot(n, dppduv), gg = dot(n, dppdvv);
+        float inv = 1.f / (e * g - f * f);
+        float3 dndu = (ff * f - ee * g) * inv * dpdu + (ee * f - ff * e) * inv * dpdv;
+        float3 dndv = (gg * f - ff * g) * inv * dpdu + (ff * f - gg * e) * inv * dpdv;
+        if (sp.has_transform) {                                     // DuvInfo::apply_transform (interaction.rs:92-101)
+            x->sh_dpdv = xform_vector(sp.local_parent, dpdv);
+            x->sh_dndu = normalize(xform_vector_T(sp.parent_local, dndu)); x->sh_dndv = normalize(xform_vector_T(sp.parent_local, dndv));
+        } else { x->sh_dpdv = dpdv; x->sh_dndu = dndu; x->sh_dndv = dndv; }
+        x->duv_dpdu = s.dpdu; x->duv_dpdv = x->sh_dpdv;
+    }
     s.perr = f3(0.f, 0.f, 0.f);                                     // "FIXME: wrong" (sphere.rs:281-282)
     s.wo = -raydir_after;       // local_parent * (-(parent_local * d)) == -(ray direction after the round trip)
 }

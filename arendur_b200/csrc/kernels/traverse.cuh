@@ -51,6 +51,9 @@ struct DevScene {
     const float4* __restrict__ wide;
     float4 root0, root1;                     // record of the root (bounds of nodes[0] + its reference words)
     float3 absmax;                           // max(|bmin|, |bmax|) of the root per axis: scale of the conservative slab test's slack
+    const arn_texture* __restrict__ textures;   // image textures (N4); null without
+    const float* __restrict__ texels;
+    uint32_t n_textures;
 };
 
 #define ARN_STACK 64           /* upload rejects trees deeper than this */

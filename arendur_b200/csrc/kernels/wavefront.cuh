@@ -16,6 +16,7 @@
 // FilmTile::add_sample (src/filming/film.rs:297-319).
 #pragma once
 #include "shade.cuh"
+#include "shade_tex.cuh"
 
 namespace arn {
 
@@ -50,6 +51,7 @@ struct PathBuf {
                                  //             (throughput before this bounce's BSDF sample, -) (unused)
     uint32_t* occluded;          // 1 = the shadow ray was blocked (written by k_trace)
     uint32_t* mis_ok;            // 1 = the BSDF-sampled ray reached the chosen light and saw its emission
+    float4* diff;                // textured scenes only, 4 per slot: the ray differential's offset rays (rx origin)(rx dir)(ry origin)(ry dir)
 };
 #define NEE_DONE 1u
 #define NEE_SHADOW 2u
@@ -92,6 +94,7 @@ struct WaveParams {
     const int4* tile_rect;                  // x0, y0, w, h of each of this rank's tiles
     const unsigned long long* tile_prefix;  // pixels before tile i (n_tiles + 1 entries)
     uint32_t spp_begin, spp_count;
+    uint32_t textured, spp_total;            // image textures present: carry ray differentials, scaled by 1 / spp_total (pt.rs:141-142)
 };
 
 // ---- queue append: warp ballots + per-warp shared-memory staging -------------------
@@ -163,6 +166,24 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ 
             float3 pfocus = o + d * ft;
             o = f3(pln.x, pln.y, 0.f);
             d = normalize(pfocus - o);
+        }
+        if (p.textured) {       // generate_path_differential's offset rays (perspective.rs:312-319, ortho.rs:220-227), scale_differentials (ray.rs:282-291)
+            float3 rxo, rxd, ryo, ryd;
+            if (p.ortho) {
+                float3 dx = xform_vector(p.raster_view, f3(1.f, 0.f, 0.f)), dy = xform_vector(p.raster_view, f3(0.f, 1.f, 0.f));
+                rxo = o + dx; ryo = o + dy; rxd = d; ryd = d;
+            } else {
+                float3 or2v = xform_point(p.raster_view, f3(1.f, 0.f, 0.f));                   // sic: dx = 0 (perspective.rs:68-73)
+                float3 dx = xform_point(p.raster_view, f3(1.f, 0.f, 0.f)) - or2v, dy = xform_point(p.raster_view, f3(0.f, 1.f, 0.f)) - or2v;
+                rxo = o; ryo = o; rxd = normalize(pview + dx); ryd = normalize(pview + dy);
+            }
+            float3 wo = xform_point(p.view_parent, o), wd = xform_vector(p.view_parent, d);
+            rxo = xform_point(p.view_parent, rxo); rxd = xform_vector(p.view_parent, rxd);
+            ryo = xform_point(p.view_parent, ryo); ryd = xform_vector(p.view_parent, ryd);
+            const float sc = 1.f / (float)p.spp_total;
+            rxo = wo + (rxo - wo) * sc; ryo = wo + (ryo - wo) * sc; rxd = wd + (rxd - wd) * sc; ryd = wd + (ryd - wd) * sc;
+            pb.diff[4 * i] = make_float4(rxo.x, rxo.y, rxo.z, 0.f); pb.diff[4 * i + 1] = make_float4(rxd.x, rxd.y, rxd.z, 0.f);
+            pb.diff[4 * i + 2] = make_float4(ryo.x, ryo.y, ryo.z, 0.f); pb.diff[4 * i + 3] = make_float4(ryd.x, ryd.y, ryd.z, 0.f);
         }
         o = xform_point(p.view_parent, o); d = xform_vector(p.view_parent, d);
         pb.ray[2 * i] = make_float4(o.x, o.y, o.z, __uint_as_float(sm.key));
@@ -297,14 +318,16 @@ __global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MI
 #define SHADE_DIFFUSE 1
 #define SHADE_PLASTIC 2
 #define SHADE_GLASS 3
-template <int KIND>
+// TEX (with KIND = SHADE_GENERIC only): the instance for scenes with image textures — every class in one launch, image-plane
+// differentials, textured material parameters and bump mapping (kernels/shade_tex.cuh)
+template <int KIND, bool TEX = false>
 __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int j) {
     constexpr bool DIFFUSE = KIND == SHADE_DIFFUSE;
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par;      // shade(j) consumes the hits of trace(j)
     constexpr uint32_t LOBES = KIND == SHADE_PLASTIC ? LOBES_PLASTIC : (KIND == SHADE_GLASS ? LOBES_GLASS : LOBES_ALL);
     // One launch over the concatenation of this instance's class queues, each padded to a multiple of 32 so that
     // every warp shades ONE material class.
-    const uint32_t ORDER = KIND == SHADE_DIFFUSE ? 0x55501u : (KIND == SHADE_GLASS ? 0x55553u : (KIND == SHADE_PLASTIC ? 0x55552u : 0x55554u));   // nibble k = class shaded k-th (5 = none)
+    const uint32_t ORDER = TEX ? 0x43210u : KIND == SHADE_DIFFUSE ? 0x55501u : (KIND == SHADE_GLASS ? 0x55553u : (KIND == SHADE_PLASTIC ? 0x55552u : 0x55554u));   // nibble k = class shaded k-th (5 = none)
     uint32_t seg_start[ARN_NCLS + 1];
     seg_start[0] = 0;
 #pragma unroll
@@ -339,10 +362,10 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 Sampler sm; sm.init_key(__float_as_uint(o4.w), (st >> 16) & 0xffu, st >> 24);
                 float4 b4 = pb.beta[pid]; float3 beta = f3(b4.x, b4.y, b4.z);
                 uint32_t ref = sc.prims[prim];
-                Surf s; uint32_t mat;
+                Surf s; uint32_t mat; SurfTex sx;
                 if (ref & ARN_PRIM_SPHERE) {
                     const DevSphere& sp = sc.spheres[ref & ~ARN_PRIM_SPHERE];
-                    surf_sphere(sp, f3(hr.y, hr.z, hr.w), raydir, s);
+                    surf_sphere(sp, f3(hr.y, hr.z, hr.w), raydir, s, TEX ? &sx : nullptr);
                     mat = sp.material;
                     if ((bounces == 0 || spec) && sp.emissive) {                                              // pt.rs:72-78
                         // the only place a shade launch changes L: touch the radiance stream for these hits only
@@ -351,10 +374,17 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                         pb.L[pid] = make_float4(L.x, L.y, L.z, 0.f);
                     }
                 } else {
-                    surf_triangle(sc, ref, hr.y, hr.z, hr.w, raydir, s);
+                    surf_triangle(sc, ref, hr.y, hr.z, hr.w, raydir, s, TEX ? &sx : nullptr);
                     mat = sc.meshes[sc.tri_mesh[ref]].material;
                 }
-                Bsdf bsdf; bsdf_build(sc.materials[mat], s, bsdf);
+                Bsdf bsdf;
+                DxyInfo dxy;
+                if (TEX) {          // pt.rs:80-83: dxy from the offset rays, then the material evaluates its textures (and bumps the frame)
+                    const float4 r0 = pb.diff[4 * pid], r1 = pb.diff[4 * pid + 1], r2 = pb.diff[4 * pid + 2], r3 = pb.diff[4 * pid + 3];
+                    dxy = compute_dxy(s.pos, s.ng, sx.duv_dpdu, sx.duv_dpdv, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), f3(r2.x, r2.y, r2.z), f3(r3.x, r3.y, r3.z));
+                    const arn_material m = textured_material(sc, mat, s, sx, dxy);
+                    bsdf_build(m, s, bsdf);
+                } else bsdf_build(sc.materials[mat], s, bsdf);
                 uint32_t flags = 0;
                 if (bsdf.n > 0) {                                           // pt.rs:85-91 (have_n(ALL-SPECULAR) > 0 <=> any lobe)
                     // Scene::uniform_sample_one_light (scene.rs:58-66)
@@ -456,6 +486,11 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 }
                 if (alive) {         // the continuation ray: one 32-byte record, the sampler key travels with it
                     pb.beta[pid] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    if (TEX) {      // spawn_ray_differential(wi, Some(&dxy)) (interaction.rs:236-251)
+                        const float3 xo = next_o + dxy.dpdx, yo = next_o + dxy.dpdy;
+                        pb.diff[4 * pid] = make_float4(xo.x, xo.y, xo.z, 0.f); pb.diff[4 * pid + 1] = make_float4(next_d.x, next_d.y, next_d.z, 0.f);
+                        pb.diff[4 * pid + 2] = make_float4(yo.x, yo.y, yo.z, 0.f); pb.diff[4 * pid + 3] = make_float4(next_d.x, next_d.y, next_d.z, 0.f);
+                    }
                     pb.ray[2 * pid] = make_float4(next_o.x, next_o.y, next_o.z, o4.w);
                     pb.ray[2 * pid + 1] = make_float4(next_d.x, next_d.y, next_d.z, __uint_as_float((bounces & 0xffu) | ((spec ? 1u : 0u) << 8) | ((sm.i1d & 0xffu) << 16) | (sm.i2d << 24)));
                 }

@@ -376,7 +376,7 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region
     scene_bytes = int(desc.n_nodes * 32 + desc.n_prims * 48 + desc.n_spheres * 176 + desc.n_triangles * 16 + desc.n_vertices * 32
-                      + desc.n_meshes * 16 + desc.n_materials * 48 + desc.n_prims * 4 + desc.n_lights * 12 + 4)
+                      + desc.n_meshes * 16 + desc.n_materials * 64 + desc.n_prims * 4 + desc.n_lights * 12 + 4)
     e2e_rays, e2e_ms = 0, 0.0
     host_film_t = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)      # pinned: the D2H read of the result
     host_film = host_film_t.numpy()

@@ -74,7 +74,30 @@ typedef struct arn_material {
     float    alpha;
     float    eta;         /* Glass: optical density                              */
     float    dissolve;    /* Translucent                                         */
-} arn_material;           /* 48 bytes */
+    /* image textures: 0 = the constant above, k + 1 = entry k of arn_scene_desc.textures.
+     * kd_tex / ks_tex are RGB textures replacing kd / ks (`diffuse` / `specular` of the material sources), aux_tex a Luma texture
+     * replacing sigma (Matte) or roughness (others), bump_tex the Luma displacement of add_bumping (material/mod.rs:42-86) */
+    uint32_t kd_tex, ks_tex, aux_tex, bump_tex;
+} arn_material;           /* 64 bytes */
+
+/* `ImageTexture<Float, _, UVMapping>` (texturing/textures/image.rs:26-35, texturing/mappings.rs:14-31) with its `MipMap`
+ * (image.rs:212-216) flattened.  The pyramid levels are built on the host side exactly as MipMap::new does (`image` crate
+ * decode + Lanczos3 resize per level + convert_in, image.rs:218-262: third-party code outside the reference tree) and passed
+ * as float texels, level 0 first, row-major, `channels` floats per texel. */
+#define ARN_WRAP_REPEAT 0u   /* ImageWrapMode (image.rs:573-581) */
+#define ARN_WRAP_BLACK  1u
+#define ARN_WRAP_CLAMP  2u
+#define ARN_TEX_MAX_LEVELS 16
+typedef struct arn_texture {
+    uint32_t channels;           /* 3: RGBImageTexture, 1: LumaImageTexture                                  */
+    uint32_t n_levels;           /* pyramid.len(), 1..16                                                      */
+    uint32_t trilinear;          /* ImageInfo.trilinear: trilinear look-up, else EWA                          */
+    uint32_t wrapping;           /* ARN_WRAP_*                                                                */
+    float    max_aniso;          /* ImageInfo.max_aniso                                                       */
+    float    scale_u, scale_v, shift_u, shift_v;     /* UVMapping.scaling / .shifting                         */
+    uint32_t level_w[ARN_TEX_MAX_LEVELS], level_h[ARN_TEX_MAX_LEVELS];
+    uint32_t level_offset[ARN_TEX_MAX_LEVELS];       /* index of the level's first float in arn_scene_desc.texels */
+} arn_texture;
 
 /* Mesh record: one `TriangleMesh` (shape/triangle.rs:26-36).  Vertices are already
  * in world space (from_model_transformed, triangle.rs:120-160). */
@@ -151,6 +174,12 @@ typedef struct arn_scene_desc {
     float           light_func_integral;
     uint32_t        n_analytic_lights;
     const arn_analytic_light* analytic_lights;
+    /* image textures referenced by the materials (N4); a scene with n_textures > 0 is rendered with ray differentials
+     * (geometry/interaction.rs:204-251, filming/perspective.rs:292-320) */
+    uint32_t        n_textures;
+    const arn_texture* textures;
+    uint64_t        n_texel_floats;
+    const float*    texels;
 } arn_scene_desc;
 
 /* `PerspecCam` (filming/perspective.rs:25-38) or `OrthoCam` (filming/ortho.rs:19-28) reduced to

@@ -43,6 +43,12 @@ int arn_hscene_add_mesh(arn_hscene* h, const float* positions, uint32_t n_vertic
 int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, float phimax,
                           uint32_t material, const float* emission3, const float* transform16);
 
+/* `ImageTexture::new(info, UVMapping, ..)` (texturing/textures/image.rs:104-140) with the pyramid already built by the caller
+ * (MipMap::new decodes and resizes with the `image` crate, :218-262 — outside the reference tree): `tex->level_offset[l]` indexes
+ * `texels` (n_floats floats, `channels` per texel, row-major).  Add textures BEFORE the materials that use them.  Returns the
+ * id to put into arn_material.{kd,ks,aux,bump}_tex (k + 1) or an error. */
+int arn_hscene_add_texture(arn_hscene* h, const arn_texture* tex, const float* texels, uint64_t n_floats);
+
 /* `lights.push(light.to_arc())` for the scene file's Point / Spot / Distant lights
  * (examples/arencli.rs:95-98).  These come first in `Scene.lights`, before the emissive
  * primitives.  Returns the index into analytic_lights or an error. */

@@ -231,6 +231,27 @@ int arn_oracle_bsdf_probe(const arn_material* m, const float* wo3, const float* 
     return ARN_OK;
 }
 
+// MipMap::look_up through UVMapping (texturing/textures/image.rs:447-476, mappings.rs:21-30): dxy4 = dudx, dvdx, dudy, dvdy
+int arn_oracle_texture_lookup(const arn_texture* tex, const float* texels, const float* uv2, const float* dxy4, float* out3) {
+    TexView v; v.t = tex; v.texels = texels;
+    DxyInfo d = dxy_default(); d.dudx = dxy4[0]; d.dvdx = dxy4[1]; d.dudy = dxy4[2]; d.dvdy = dxy4[3];
+    Texel t = texture_evaluate(v, v2(uv2[0], uv2[1]), d);
+    out3[0] = t.c[0]; out3[1] = t.c[1]; out3[2] = t.c[2];
+    return ARN_OK;
+}
+// SurfaceInteraction::compute_dxy on a bare plane (pos, n, dpdu, dpdv) with offset rays (rxo, rxd, ryo, ryd): out10 = dpdx, dpdy, dudx, dvdx, dudy, dvdy
+int arn_oracle_compute_dxy(const float* pos3, const float* n3, const float* dpdu3, const float* dpdv3, const float* rays12, float* out10) {
+    SurfaceInteraction si; si.basic.pos = v3(pos3[0], pos3[1], pos3[2]); si.basic.norm = v3(n3[0], n3[1], n3[2]);
+    si.duv.dpdu = v3(dpdu3[0], dpdu3[1], dpdu3[2]); si.duv.dpdv = v3(dpdv3[0], dpdv3[1], dpdv3[2]);
+    RayDifferential rd; rd.has_diffs = true;
+    rd.rx = ray_from_od(v3(rays12[0], rays12[1], rays12[2]), v3(rays12[3], rays12[4], rays12[5]));
+    rd.ry = ray_from_od(v3(rays12[6], rays12[7], rays12[8]), v3(rays12[9], rays12[10], rays12[11]));
+    DxyInfo d = compute_dxy(si, rd);
+    out10[0] = d.dpdx.x; out10[1] = d.dpdx.y; out10[2] = d.dpdx.z; out10[3] = d.dpdy.x; out10[4] = d.dpdy.y; out10[5] = d.dpdy.z;
+    out10[6] = d.dudx; out10[7] = d.dvdx; out10[8] = d.dudy; out10[9] = d.dvdy;
+    return ARN_OK;
+}
+
 const char* arn_oracle_version(void) { return "arendur oracle (CPU restatement) 0.1"; }
 
 }  // extern "C"

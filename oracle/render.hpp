@@ -70,6 +70,31 @@ inline RawRay camera_generate(const arn_camera& cam, V2 pfilm, V2 plens) {
     return ray_apply_transform(ray, vp);
 }
 
+// PerspecCam / OrthoCam::generate_path_differential with the offset rays (perspective.rs:292-320 with :68-73, ortho.rs:203-228 with :46-47)
+inline RayDifferential camera_generate_differential(const arn_camera& cam, V2 pfilm, V2 plens) {
+    M4 rv = m4_from_cols(cam.raster_view), vp = m4_from_cols(cam.view_parent);
+    V3 pview = transform_point(rv, v3(pfilm.x, pfilm.y, 0.f));
+    RawRay ray = cam.ortho ? ray_from_od(pview, v3(0.f, 0.f, 1.f)) : ray_from_od(v3(0.f, 0.f, 0.f), normalize(pview));
+    if (cam.has_lens) {
+        V2 pl = cam.lens_radius * sample_concentric_disk(plens);
+        Float ft = cam.focal_distance / ray.dir.z;
+        V3 pfocus = ray_evaluate(ray, ft);
+        V3 new_origin = v3(pl.x, pl.y, 0.f);
+        ray = ray_from_od(new_origin, normalize(pfocus - new_origin));
+    }
+    RayDifferential r; r.ray = ray; r.has_diffs = true;
+    if (cam.ortho) {
+        V3 dx = transform_vector(rv, v3(1.f, 0.f, 0.f)), dy = transform_vector(rv, v3(0.f, 1.f, 0.f));
+        r.rx = ray_from_od(ray.origin + dx, ray.dir); r.ry = ray_from_od(ray.origin + dy, ray.dir);
+    } else {
+        V3 or2v = transform_point(rv, v3(1.f, 0.f, 0.f));                        // sic: dx = T(1,0,0) - T(1,0,0) = 0 (perspective.rs:68-73)
+        V3 dx = transform_point(rv, v3(1.f, 0.f, 0.f)) - or2v, dy = transform_point(rv, v3(0.f, 1.f, 0.f)) - or2v;
+        r.rx = ray_from_od(ray.origin, normalize(pview + dx)); r.ry = ray_from_od(ray.origin, normalize(pview + dy));   // "TODO: account for lens"
+    }
+    r.ray = ray_apply_transform(r.ray, vp); r.rx = ray_apply_transform(r.rx, vp); r.ry = ray_apply_transform(r.ry, vp);   // transform_ray_differential
+    return r;
+}
+
 // ------------------------------------------------------------------ area light = emissive sphere primitive
 struct LightSample { RGB radiance; Float pdf; V3 pfrom, pto; };
 
@@ -255,8 +280,13 @@ inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 us
 }
 
 // calculate_lighting (renderer/pt.rs:55-125)
+// `rd` (scenes with image textures): the camera's ray differential; compute_dxy / textured materials / spawn_ray_differential
+// then run as in the source.  Without textures the differentials cannot reach any result and are not tracked.
 inline RGB calculate_lighting(const Scene& s, RawRay ray, ParitySampler& sampler, uint32_t max_depth,
-                              uint32_t min_depth, Float rr_threshold, RayStats* st) {
+                              uint32_t min_depth, Float rr_threshold, RayStats* st, const RayDifferential* rd_in = nullptr) {
+    const bool textured = rd_in != nullptr;
+    RayDifferential rd; if (textured) { rd = *rd_in; ray = rd.ray; }
+    TexTable tex; tex.textures = s.textures.data(); tex.texels = s.texels.data();
     RGB ret = grey(0.f);
     RGB beta = grey(1.f);
     bool specular_bounce = false;
@@ -271,7 +301,9 @@ inline RGB calculate_lighting(const Scene& s, RawRay ray, ParitySampler& sampler
             }
             uint32_t mat = s.prim_is_sphere((uint32_t)prim) ? s.spheres[s.prim_index((uint32_t)prim)].material
                                                             : s.meshes[s.tri_mesh[s.prim_index((uint32_t)prim)]].material;
-            Bsdf bsdf = compute_scattering(s.materials[mat], si);
+            DxyInfo dxy = dxy_default();
+            if (textured) { rd.ray = ray; dxy = compute_dxy(si, rd); }             // pt.rs:80 (the traversal may have rewritten `ray`)
+            Bsdf bsdf = textured ? compute_scattering(s.materials[mat], si, &dxy, &tex) : compute_scattering(s.materials[mat], si);
             if (bsdf_have_n(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0) {
                 // Scene::uniform_sample_one_light (scene.rs:58-66): next(), next_2d(), next_2d()
                 uint32_t lidx; Float lightpdf;
@@ -288,7 +320,8 @@ inline RGB calculate_lighting(const Scene& s, RawRay ray, ParitySampler& sampler
             if (is_black(bs.f) || bs.pdf == 0.f) break;
             beta = beta * (bs.f * (std::fabs(dot(bs.wi, si.shading_norm)) / bs.pdf));
             if (!rgb_valid(beta)) break;
-            ray = si_spawn_ray(si, bs.wi);
+            if (textured) { rd = spawn_ray_differential(si, bs.wi, &dxy); ray = rd.ray; }   // pt.rs:103
+            else ray = si_spawn_ray(si, bs.wi);
         } else break;
         bounces += 1;
         if (bounces >= max_depth) break;
@@ -393,7 +426,13 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
                     V2 plens = sampler.next_2d();
                     RawRay ray = camera_generate(cam, pfilm, plens);
                     tstats[tid].camera++;
-                    RGB L = calculate_lighting(s, ray, sampler, prm.max_depth, prm.min_depth, prm.rr_threshold, &tstats[tid]);
+                    RGB L;
+                    if (!s.textures.empty()) {                                   // pt.rs:141-142
+                        RayDifferential rd = camera_generate_differential(cam, pfilm, plens);
+                        scale_differentials(rd, 1.f / (Float)spp);
+                        L = calculate_lighting(s, rd.ray, sampler, prm.max_depth, prm.min_depth, prm.rr_threshold, &tstats[tid], &rd);
+                    } else
+                    L = calculate_lighting(s, ray, sampler, prm.max_depth, prm.min_depth, prm.rr_threshold, &tstats[tid]);
                     if (radiance_out) {
                         size_t ri = (((size_t)y * (size_t)(film.crop_max_x - film.crop_min_x) + (size_t)x) * (s1 - s0) + (si - s0)) * 4;
                         radiance_out[ri] = L.x; radiance_out[ri + 1] = L.y; radiance_out[ri + 2] = L.z; radiance_out[ri + 3] = 0.f;

@@ -24,6 +24,7 @@ struct Scene {
     std::vector<arn_analytic_light> analytic_lights;
     std::vector<Float> light_func, light_cdf;
     Float light_func_integral = 0.f;
+    std::vector<arn_texture> textures; std::vector<Float> texels;      // image textures (N4)
 
     void load(const arn_scene_desc& d) {
         positions.resize(d.n_vertices);
@@ -46,6 +47,7 @@ struct Scene {
         }
         light_func_integral = d.light_func_integral;
         if (d.n_analytic_lights) analytic_lights.assign(d.analytic_lights, d.analytic_lights + d.n_analytic_lights);
+        if (d.n_textures) { textures.assign(d.textures, d.textures + d.n_textures); texels.assign(d.texels, d.texels + d.n_texel_floats); }
     }
     bool prim_is_sphere(uint32_t comp) const { return (prims[comp] & ARN_PRIM_SPHERE) != 0; }
     uint32_t prim_index(uint32_t comp) const { return prims[comp] & ~ARN_PRIM_SPHERE; }

@@ -4,6 +4,7 @@
 //   microfacet}.rs, src/material/{bsdf,matte,plastic,glass,translucent}.rs, src/spectrum/mod.rs
 #pragma once
 #include "geom.hpp"
+#include "texture.hpp"
 #include "../include/arn.h"
 
 namespace orc {
@@ -526,7 +527,22 @@ inline Sampled bsdf_evaluate_sampled(const Bsdf& b, V3 wow, V2 u, uint32_t types
 
 // ------------------------------------------------------------------ materials (material/*.rs), constant textures
 inline Bxdf mk_bxdf(BxdfKind k) { Bxdf x; std::memset(&x, 0, sizeof x); x.kind = k; return x; }
-inline Bsdf compute_scattering(const arn_material& m, const SurfaceInteraction& si) {
+// Textured form (material/{matte,plastic,glass,translucent}.rs with ImageTexture parameters): bump first, then every texture is
+// evaluated on the (bumped) interaction; `tex` = the scene's texture table (null: constants only).
+struct TexTable { const arn_texture* textures; const Float* texels; };
+inline Bsdf compute_scattering(const arn_material& m_in, SurfaceInteraction& si, const DxyInfo* dxy = nullptr, const TexTable* tex = nullptr) {
+    arn_material m = m_in;
+    if (tex && dxy) {
+        auto view = [&](uint32_t id) { TexView v; v.t = &tex->textures[id - 1]; v.texels = tex->texels; return v; };
+        if (m.bump_tex) add_bumping(si, *dxy, view(m.bump_tex));                    // matte.rs:46-48 and alike
+        // evaluation order as in the sources: Matte kd, sigma; Plastic diffuse, specular, roughness; Glass specular, diffuse, roughness
+        if (m.kd_tex) { Texel t = texture_evaluate(view(m.kd_tex), si.uv, *dxy); m.kd[0] = t.c[0]; m.kd[1] = t.c[1]; m.kd[2] = t.c[2]; }
+        if (m.ks_tex) { Texel t = texture_evaluate(view(m.ks_tex), si.uv, *dxy); m.ks[0] = t.c[0]; m.ks[1] = t.c[1]; m.ks[2] = t.c[2]; }
+        if (m.aux_tex) {
+            Float a = texture_evaluate(view(m.aux_tex), si.uv, *dxy).c[0];
+            if (m.type == ARN_MAT_MATTE) m.sigma = a; else { m.roughness = a; m.alpha = roughness_to_alpha(a); }
+        }
+    }
     Bsdf b = bsdf_new(si, 1.f);
     RGB kd = rgb(m.kd[0], m.kd[1], m.kd[2]), ks = rgb(m.ks[0], m.ks[1], m.ks[2]);
     switch (m.type) {

@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.Node) == 32
-    assert ctypes.sizeof(L.Material) == 48
+    assert ctypes.sizeof(L.Material) == 64
+    assert ctypes.sizeof(L.Texture) == 36 + 3 * 64
     assert ctypes.sizeof(L.Sphere) == 176
     assert ctypes.sizeof(L.Ray) == 28
     assert ctypes.sizeof(L.Hit) == 8

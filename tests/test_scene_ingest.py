@@ -24,7 +24,7 @@ def _desc_arrays(d):
         indices=np.ctypeslib.as_array(d.indices, shape=(d.n_triangles, 3)).copy(),
         tri_mesh=np.ctypeslib.as_array(d.tri_mesh, shape=(d.n_triangles,)).copy(),
         prims=np.ctypeslib.as_array(d.prims, shape=(d.n_prims,)).copy(),
-        materials=bytes(C.string_at(d.materials, d.n_materials * 48)),
+        materials=bytes(C.string_at(d.materials, d.n_materials * C.sizeof(L.Material))),
         spheres=bytes(C.string_at(d.spheres, d.n_spheres * 176)),
         meshes=bytes(C.string_at(d.meshes, d.n_meshes * 16)),
     )
@@ -37,7 +37,7 @@ def test_cornell_fixture_scene_shape():
     a = _desc_arrays(d)
     # component order of BASELINE.md C1: OBJ triangles, light_sphere, blue_sphere
     assert np.array_equal(a["prims"][:1112], np.arange(1112)) and a["prims"][1112] == L.ARN_PRIM_SPHERE and a["prims"][1113] == L.ARN_PRIM_SPHERE | 1
-    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 12)
+    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 16)
     # sphere Plastic, shortBox Glass, floor Plastic, ceiling/backWall/leftWall/rightWall/light Matte, fallback Matte, sphere light Matte
     assert mats[:, 0].tolist() == [1, 2, 1, 0, 0, 0, 0, 0, 0, 0]
     # Scene::new power distribution (Y-power 994.6 / 685.1 -> pdf 0.592 / 0.408)
@@ -118,8 +118,8 @@ def test_obj_loader_small(tmp_path):
     d = hs.build()
     a = _desc_arrays(d)
     assert d.n_meshes == 5 and d.n_triangles == 6
-    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 12)
-    fm = np.frombuffer(a["materials"], dtype=np.float32).reshape(-1, 12)
+    mats = np.frombuffer(a["materials"], dtype=np.uint32).reshape(-1, 16)
+    fm = np.frombuffer(a["materials"], dtype=np.float32).reshape(-1, 16)
     assert mats[:, 0].tolist() == [L.ARN_MAT_GLASS, L.ARN_MAT_PLASTIC, L.ARN_MAT_MATTE, L.ARN_MAT_TRANSLUCENT, L.ARN_MAT_MATTE]
     assert fm[0, 10] == np.float32(1.5) and fm[3, 11] == np.float32(0.25) and fm[1, 8] == np.float32(0.8)      # eta, dissolve, roughness (1000-200)/1000
     assert np.allclose(fm[4, 1:4], (0.5, 0.6, 0.7))                       # fallback material
@@ -144,7 +144,7 @@ def test_json_and_obj_loader_match_fixture():
         assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
     assert a["meshes"] == b["meshes"] and a["spheres"] == b["spheres"]
     # material tables: same entries; the fixture scene appends the sphere material after the OBJ ones as well
-    ma, mb = np.frombuffer(a["materials"], np.uint32).reshape(-1, 12), np.frombuffer(b["materials"], np.uint32).reshape(-1, 12)
+    ma, mb = np.frombuffer(a["materials"], np.uint32).reshape(-1, 16), np.frombuffer(b["materials"], np.uint32).reshape(-1, 16)
     assert ma.shape == mb.shape
     assert np.array_equal(ma[:, :10], mb[:, :10])                      # type, kd, ks, sigma, roughness, alpha
     glass = ma[:, 0] == L.ARN_MAT_GLASS
@@ -222,7 +222,7 @@ def test_oracle_only_flattening_equals_the_product_host_layer():
         assert getattr(d, name) == getattr(p, name), name
     for name, nbytes in (("positions", d.n_vertices * 12), ("normals", d.n_vertices * 12), ("uvs", d.n_vertices * 8), ("indices", d.n_triangles * 12),
                          ("tri_mesh", d.n_triangles * 4), ("prims", d.n_prims * 4), ("order", d.n_prims * 4), ("nodes", d.n_nodes * 32),
-                         ("meshes", d.n_meshes * 16), ("spheres", d.n_spheres * C.sizeof(L.Sphere)), ("materials", d.n_materials * 48),
+                         ("meshes", d.n_meshes * 16), ("spheres", d.n_spheres * C.sizeof(L.Sphere)), ("materials", d.n_materials * C.sizeof(L.Material)),
                          ("light_prims", d.n_lights * 4), ("light_func", d.n_lights * 4), ("light_cdf", (d.n_lights + 1) * 4)):
         assert raw(getattr(d, name), nbytes) == raw(getattr(p, name), nbytes), name
     assert d.light_func_integral == p.light_func_integral
