@@ -18,6 +18,8 @@
 #include "kernels/trace_refill.cuh"
 #include "kernels/lbvh.cuh"
 #include "kernels/wide_build.cuh"
+#include "kernels/cw8_build.cuh"
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace arn;
@@ -56,6 +58,7 @@ struct arn_ctx {
     bool opt_count = false;
     int opt_width = 0;           // ARN_OPT_BVH_WIDTH: 0 auto, 2 binary, 4 wide
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
+    int g_trace_8 = 0, g_closest_8 = 0, g_any_8 = 0;      // compressed 8-wide walk
     size_t opt_wave = 0;
     int opt_refill = 0;          // ARN_OPT_TRACE_REFILL: lane-refilling trace (kernels/trace_refill.cuh) for trees walked with the binary nodes
     int g_setup = 0, g_refill = 0, g_classify = 0, g_shade_tex = 0;
@@ -200,6 +203,9 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
+    c->g_trace_8 = grid_for(c, (const void*)k_trace<ARN_TRAV_CW8>);
+    c->g_closest_8 = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_CW8>);
+    c->g_any_8 = grid_for(c, (const void*)k_any_batch<ARN_TRAV_CW8>);
     c->g_shade = grid_for(c, (const void*)k_shade<SHADE_GENERIC>);
     c->g_shade_tex = grid_for(c, (const void*)k_shade<SHADE_GENERIC, true>);
     c->g_shade_p = grid_for(c, (const void*)k_shade<SHADE_PLASTIC>);
@@ -247,7 +253,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     if (!c) return ARN_E_INVALID;
     switch (option) {
     case ARN_OPT_COUNT_TRAVERSAL: c->opt_count = value != 0; return ARN_OK;
-    case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2 or 4"); c->opt_width = (int)value; return ARN_OK;
+    case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4 && value != 8) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2, 4 or 8"); c->opt_width = (int)value; return ARN_OK;
     case ARN_OPT_PIPELINES: if (value < 0 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 0 (auto) ..8"); c->opt_pipes = (int)value; return ARN_OK;
     case ARN_OPT_TRACE_REFILL: c->opt_refill = value != 0; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
@@ -416,6 +422,46 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
         s->dev.tris = d_slots;
     }
     lap("slots (device gather)");
+    // compressed 8-wide nodes + leaf blob (kernels/cw8_build.cuh) for trees the 4-wide records no longer keep in the caches
+    // — only on request (ARN_OPT_BVH_WIDTH = 8 before the upload): on C4 the 8-wide walk moves 21 % fewer DRAM bytes but issues 63 % more
+    // instructions and is 20 % slower than the 4-wide walk (profiles/r02_c4_cw8.txt), so `auto` never picks it
+    if (d->n_nodes >= 3 && (d->nodes[0].len_axis >> 2) == 0 && c->opt_width == 8) {
+        const size_t n_nodes = d->n_nodes, n_leaves = (n_nodes + 1) / 2;
+        uint32_t* d_sizes = nullptr; uint32_t* d_off = nullptr; void* d_tmp = nullptr; uint2 *f0 = nullptr, *f1 = nullptr; uint32_t* d_cnt = nullptr;
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_sizes, d_off, (int)n_nodes, c->stream);
+        auto salloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; scratch.push_back(p); return p; };
+        d_sizes = (uint32_t*)salloc(n_nodes * 4); d_off = (uint32_t*)salloc(n_nodes * 4); d_tmp = salloc(tmp_bytes);
+        f0 = (uint2*)salloc(n_interior_all * sizeof(uint2)); f1 = (uint2*)salloc(n_interior_all * sizeof(uint2)); d_cnt = (uint32_t*)salloc((ARN_STACK + 4) * 4);
+        if (!d_sizes || !d_off || !d_tmp || !f0 || !f1 || !d_cnt) { cudaGetLastError(); set_err(c, ARN_E_OOM, "8-wide collapse scratch: out of device memory"); return fail(ARN_E_OOM); }
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const int grid = (int)std::min<size_t>((size_t)sms * 8, (n_nodes + 255) / 256);
+        k_cw8_leaf_sizes<<<grid, 256, 0, c->stream>>>(dn, (uint32_t)n_nodes, d_sizes);
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_sizes, d_off, (int)n_nodes, c->stream);
+        const size_t blob_f4 = 2 * n_leaves + 3 * (size_t)d->n_prims;
+        const int levels = (int)(max_depth + 2) / 3 + 2;
+        uint32_t* d_node_count = d_cnt + ARN_STACK + 2;
+        // counting pass, then the exact allocation
+        k_cw8_begin<<<1, 1, 0, c->stream>>>(f0, d_cnt, d_node_count);
+        for (int level = 0; level < levels; level++)
+            k_cw8_level<<<grid, 256, 0, c->stream>>>(dn, d_off, nullptr, (level & 1) ? f1 : f0, (level & 1) ? f0 : f1, d_cnt, level, d_node_count);
+        uint32_t n_cw8 = 0;
+        cudaMemcpyAsync(&n_cw8, d_node_count, 4, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_err(c, ARN_E_CUDA, "8-wide collapse (count) failed"); return fail(ARN_E_CUDA); }
+        if (n_cw8 < (1u << 24) && blob_f4 < 0xffffffffull) {          // node index + leaf mask share a word; leaf references are 32-bit float4 indices
+            void* extra = nullptr;
+            if (cudaMalloc(&extra, (size_t)n_cw8 * 128 + blob_f4 * 16) != cudaSuccess) { cudaGetLastError(); set_err(c, ARN_E_OOM, "8-wide nodes: out of device memory"); return fail(ARN_E_OOM); }
+            s->allocs.push_back(extra);
+            uint4* d_cw8 = (uint4*)extra; float4* d_blob = (float4*)((char*)extra + (size_t)n_cw8 * 128);
+            k_cw8_leaf_blob<<<grid, 256, 0, c->stream>>>(dn, (uint32_t)n_nodes, d_off, s->dev.tris, d_blob);
+            k_cw8_begin<<<1, 1, 0, c->stream>>>(f0, d_cnt, d_node_count);
+            for (int level = 0; level < levels; level++)
+                k_cw8_level<<<grid, 256, 0, c->stream>>>(dn, d_off, d_cw8, (level & 1) ? f1 : f0, (level & 1) ? f0 : f1, d_cnt, level, d_node_count);
+            s->dev.cw8 = d_cw8; s->dev.blob = d_blob;
+            s->bytes += (size_t)n_cw8 * 128 + blob_f4 * 16;
+        }
+        lap("8-wide collapse + leaf blob");
+    }
     if ((rc = dev_upload(s, d->normals, d->normals ? (size_t)d->n_vertices * 3 : 0, &s->dev.normals)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->uvs, d->uvs ? (size_t)d->n_vertices * 2 : 0, &s->dev.uvs)) != ARN_OK) return fail(rc);
     if ((rc = dev_upload(s, d->tri_mesh, d->n_triangles, &s->dev.tri_mesh)) != ARN_OK) return fail(rc);
@@ -452,9 +498,14 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
 // the chain of dependent node fetches and wins once the tree no longer sits in L1 (C4: +10 %), the
 // binary walk issues fewer instructions per node and wins on cache-resident trees (Cornell: +15 %).
 #define ARN_WIDE_MIN_NODES (1u << 16)
+static bool use_cw8(const arn_scene* s) {        // compressed 8-wide walk: trees far larger than the caches (needs the 8-wide nodes, built at upload)
+    int w = s->ctx->opt_width;
+    return s->dev.cw8 != nullptr && w == 8;
+}
 static bool use_wide(const arn_scene* s) {
     int w = s->ctx->opt_width;
-    return w == 4 || (w == 0 && s->dev.n_nodes >= ARN_WIDE_MIN_NODES);
+    if (use_cw8(s)) return false;
+    return w == 4 || ((w == 0 || w == 8) && s->dev.n_nodes >= ARN_WIDE_MIN_NODES);
 }
 
 // ---------------------------------------------------------------- batched queries
@@ -462,11 +513,12 @@ int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void
     if (!s || (n && (!rays_dev || !hits_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_closest_dev: NULL argument");
     arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
-    const bool wide = use_wide(s);
-    int grid = (int)std::min<size_t>((size_t)(wide ? c->g_closest_w : c->g_closest), (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    const bool wide = use_wide(s), cw8 = use_cw8(s);
+    int grid = (int)std::min<size_t>((size_t)(cw8 ? c->g_closest_8 : wide ? c->g_closest_w : c->g_closest), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    if (wide) k_closest_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    if (cw8) k_closest_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    else if (wide) k_closest_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     else k_closest_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     CUDA_TRY(c, cudaGetLastError());
     if (stats) {
@@ -482,11 +534,12 @@ int arn_intersect_any_dev(arn_scene* s, const void* rays_dev, size_t n, void* ou
     if (!s || (n && (!rays_dev || !out_dev))) return set_err(s ? s->ctx : nullptr, ARN_E_INVALID, "arn_intersect_any_dev: NULL argument");
     arn_ctx* c = s->ctx; std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     if (n == 0) return ARN_OK;
-    const bool wide = use_wide(s);
-    int grid = (int)std::min<size_t>((size_t)(wide ? c->g_any_w : c->g_any), (n + ARN_BLOCK - 1) / ARN_BLOCK);
+    const bool wide = use_wide(s), cw8 = use_cw8(s);
+    int grid = (int)std::min<size_t>((size_t)(cw8 ? c->g_any_8 : wide ? c->g_any_w : c->g_any), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    if (wide) k_any_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    if (cw8) k_any_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    else if (wide) k_any_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     else k_any_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     CUDA_TRY(c, cudaGetLastError());
     if (stats) {
@@ -669,8 +722,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const unsigned long long n_waves = (total + cap - 1) / cap;
     // per-kernel event timing needs serial launches: it is only taken with one pipeline (ARN_OPT_PIPELINES = 1)
     const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
-    const bool wide = use_wide(s);
-    const bool refill = c->opt_refill && !wide && !c->opt_count;
+    const bool wide = use_wide(s), cw8 = use_cw8(s);
+    const bool refill = c->opt_refill && !wide && !cw8 && !c->opt_count;
     const bool textured = s->dev.n_textures != 0;
     for (int i = 0; i < np; i++) {
         int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;
@@ -723,6 +776,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
                 launches += 2;
             }
             else if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            else if (cw8) k_trace<ARN_TRAV_CW8><<<c->g_trace_8, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), st);

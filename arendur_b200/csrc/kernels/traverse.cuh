@@ -51,6 +51,8 @@ struct DevScene {
     const float4* __restrict__ wide;
     float4 root0, root1;                     // record of the root (bounds of nodes[0] + its reference words)
     float3 absmax;                           // max(|bmin|, |bmax|) of the root per axis: scale of the conservative slab test's slack
+    const uint4* __restrict__ cw8;           // compressed 8-wide nodes, 8 uint4 each (kernels/cw8_build.cuh); null unless built
+    const float4* __restrict__ blob;         // leaf blob of the 8-wide walk: [exact bounds, count] + primitive records per leaf
     const arn_texture* __restrict__ textures;   // image textures (N4); null without
     const float* __restrict__ texels;
     uint32_t n_textures;
@@ -357,14 +359,14 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
 // i.e. with the reference's tmax.
 
 // leaf primitives in slot order, strict `<` acceptance (bvh.rs:104-114); returns true when an any-hit query is done
-ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, TravRay& r, HitRec& h, const bool ANY) {
-    const uint32_t end = first + count;
-    for (uint32_t k = first; k < end; k++) {
-        float4 v0 = __ldg(&sc.tris[3 * k]);
+ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, TravRay& r, HitRec& h, const bool ANY, const float4* __restrict__ recs = nullptr) {
+    const float4* __restrict__ base = recs ? recs : sc.tris + 3 * (size_t)first;        // `recs`: the leaf's records in the 8-wide walk's leaf blob
+    for (uint32_t k = 0; k < count; k++) {
+        float4 v0 = __ldg(&base[3 * k]);
         uint32_t comp = __float_as_uint(v0.w);          // component id, sphere bit set for sphere slots
         if (comp & ARN_PRIM_SPHERE) sphere_slot(sc, comp & ~ARN_PRIM_SPHERE, r, h);
         else {
-            float4 v1 = __ldg(&sc.tris[3 * k + 1]), v2 = __ldg(&sc.tris[3 * k + 2]);
+            float4 v1 = __ldg(&base[3 * k + 1]), v2 = __ldg(&base[3 * k + 2]);
             float t, b0, b1, b2;
             if (tri_test(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), r, t, b0, b1, b2) && r.tmax > t) {
                 r.tmax = t; h.prim = (int)comp; h.a = b0; h.b = b1; h.c = b2;
@@ -510,11 +512,94 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
     }
 }
 
+// ---- compressed 8-wide walk (trees far larger than the caches) --------------------------------------------------
+// Node layout and the argument for quantised, outward-rounded child boxes: kernels/cw8_build.cuh.  A node's eight child boxes
+// are tested with t = q * (2^e / d) + ((origin - o) / d -+ slack): one byte-permute, one FADD and one FFMA per plane.  The
+// children that survive are kept as ONE stack entry per node — (node | leaf mask, pending list in the reference's visiting
+// order for this ray's sign octant) — and the next child's reference is read from the node when its turn comes.  Nothing
+// but leaves decides a hit: a leaf's exact bounds sit in front of its primitives in the leaf blob and take the reference's
+// slab test with the tmax current at its turn.
+#define ARN_STACK8 32
+ARN_DEV float cw8_qf(uint32_t word, uint32_t sel) { return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.f; }   // byte -> float, exact
+struct Cw8Axis { float a, b0, b1; uint32_t n_lo, n_hi, f_lo, f_hi; };      // scale / d, near / far offsets, near / far plane bytes of slots 0-3 / 4-7
+ARN_DEV void cw8_expand(const DevScene& sc, const TravRay& r, const CullRay& c, uint32_t w, uint32_t perm_off, uint32_t& gnode, uint32_t& gpend) {
+    const uint4* __restrict__ nd = sc.cw8 + 8 * (size_t)w;
+    const uint4 q0 = __ldg(nd), p0 = __ldg(nd + 2), p1 = __ldg(nd + 3), p2 = __ldg(nd + 4);
+    const uint32_t order = __ldg(reinterpret_cast<const uint32_t*>(nd) + perm_off);
+    const uint32_t meta = q0.w;
+    Cw8Axis X, Y, Z;
+    {
+        const float ox = __uint_as_float(q0.x), oy = __uint_as_float(q0.y), oz = __uint_as_float(q0.z);
+        X.a = __uint_as_float((meta & 0xffu) << 23) * r.inv.x; Y.a = __uint_as_float(((meta >> 8) & 0xffu) << 23) * r.inv.y; Z.a = __uint_as_float(((meta >> 16) & 0xffu) << 23) * r.inv.z;
+        X.b0 = __fmaf_rn(ox, r.inv.x, c.oi0.x); X.b1 = __fmaf_rn(ox, r.inv.x, c.oi1.x);
+        Y.b0 = __fmaf_rn(oy, r.inv.y, c.oi0.y); Y.b1 = __fmaf_rn(oy, r.inv.y, c.oi1.y);
+        Z.b0 = __fmaf_rn(oz, r.inv.z, c.oi0.z); Z.b1 = __fmaf_rn(oz, r.inv.z, c.oi1.z);
+        const bool nx = c.negbits & 1u, ny = c.negbits & 2u, nz = c.negbits & 4u;
+        // planes: p0 = (lo.x[0-3], lo.x[4-7], lo.y[0-3], lo.y[4-7]), p1 = (lo.z, lo.z, hi.x, hi.x), p2 = (hi.y, hi.y, hi.z, hi.z)
+        X.n_lo = nx ? p1.z : p0.x; X.n_hi = nx ? p1.w : p0.y; X.f_lo = nx ? p0.x : p1.z; X.f_hi = nx ? p0.y : p1.w;
+        Y.n_lo = ny ? p2.x : p0.z; Y.n_hi = ny ? p2.y : p0.w; Y.f_lo = ny ? p0.z : p2.x; Y.f_hi = ny ? p0.w : p2.y;
+        Z.n_lo = nz ? p2.z : p1.x; Z.n_hi = nz ? p2.w : p1.y; Z.f_lo = nz ? p1.x : p2.z; Z.f_hi = nz ? p1.y : p2.w;
+    }
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t sel = 0x7440u | (uint32_t)(k & 3);
+        const float tnx = __fmaf_rn(cw8_qf(k < 4 ? X.n_lo : X.n_hi, sel), X.a, X.b0), tfx = __fmaf_rn(cw8_qf(k < 4 ? X.f_lo : X.f_hi, sel), X.a, X.b1);
+        const float tny = __fmaf_rn(cw8_qf(k < 4 ? Y.n_lo : Y.n_hi, sel), Y.a, Y.b0), tfy = __fmaf_rn(cw8_qf(k < 4 ? Y.f_lo : Y.f_hi, sel), Y.a, Y.b1);
+        const float tnz = __fmaf_rn(cw8_qf(k < 4 ? Z.n_lo : Z.n_hi, sel), Z.a, Z.b0), tfz = __fmaf_rn(cw8_qf(k < 4 ? Z.f_lo : Z.f_hi, sel), Z.a, Z.b1);
+        const float lo = fmax3(tnx, tny, fmaxf(tnz, 0.f)), hi = fmin3(tfx, tfy, fminf(tfz, r.tmax));
+        hitmask |= (lo <= hi ? 1u : 0u) << k;
+    }
+    // pending list: the node's visiting order for this sign octant, a valid bit on the slots that survived
+    uint32_t pend = order;
+#pragma unroll
+    for (int q = 0; q < 8; q++) pend |= ((hitmask >> ((order >> (4 * q)) & 7u)) & 1u) << (4 * q + 3);
+    gnode = w | (meta & 0xff000000u); gpend = pend;
+}
+ARN_DEV void traverse8(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
+    h.prim = -1; h.a = h.b = h.c = 0.f;
+    uint2 stack[ARN_STACK8];
+    int sp = 0;
+    const uint32_t perm_off = 4u + c.negbits + ((c.negbits & 4u) ? 12u : 0u);      // word offset of this octant's visiting order inside a node
+    uint32_t gnode, gpend;
+    cw8_expand(sc, r, c, 0u, perm_off, gnode, gpend);
+    for (;;) {
+        // ---- interior: take children in order, expand interior ones, until a leaf's turn comes
+        uint32_t leaf_ref = 0; bool have_leaf = false;
+        while (!have_leaf) {
+            const uint32_t valid = gpend & 0x88888888u;
+            if (!valid) {
+                if (sp == 0) return;
+                const uint2 e = stack[--sp]; gnode = e.x; gpend = e.y;
+                continue;
+            }
+            const uint32_t k4 = (uint32_t)__ffs((int)valid) - 4u;                    // bit position of the first pending nibble
+            const uint32_t slot = (gpend >> k4) & 7u;
+            gpend &= ~(8u << k4);
+            const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(sc.cw8 + 8 * (size_t)(gnode & 0xffffffu)) + 24u + slot);
+            if ((gnode >> (24u + slot)) & 1u) { leaf_ref = ref; have_leaf = true; }
+            else {
+                if (gpend & 0x88888888u) stack[sp++] = make_uint2(gnode, gpend);
+                cw8_expand(sc, r, c, ref, perm_off, gnode, gpend);
+            }
+        }
+        // ---- leaf: the reference's slab test on its exact bounds, then its primitives
+        {
+            const float4 b0 = __ldg(sc.blob + leaf_ref), b1 = __ldg(sc.blob + leaf_ref + 1);      // 16-byte aligned only: leaves are 2 + 3 * count float4 long
+            float t0;
+            if (slab(b0, b1, r, t0) && t0 < r.tmax) {
+                if (leaf_prims(sc, 0u, __float_as_uint(b1.z), r, h, any, sc.blob + leaf_ref + 2)) return;
+            }
+        }
+    }
+}
+
 // What the kernels call.  The counted mode always walks the binary nodes: its counters report the
 // reference algorithm's node / primitive tests.
 #define ARN_TRAV_BINARY 0
 #define ARN_TRAV_COUNTED 1
 #define ARN_TRAV_WIDE 2
+#define ARN_TRAV_CW8 3
 // out-of-line exact walks for the rare rays the conservative test does not cover (one copy per kernel)
 ARN_NOINL void traverse_exact_closest(const DevScene& sc, TravRay& r, HitRec& h) { traverse<false, false>(sc, r, h, nullptr); }
 ARN_NOINL void traverse_exact_any(const DevScene& sc, TravRay& r, HitRec& h) { traverse<true, false>(sc, r, h, nullptr); }
@@ -528,12 +613,13 @@ ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr,
         if (any) traverse_exact_any(sc, r, h); else traverse_exact_closest(sc, r, h);
         return;
     }
-    if (MODE == ARN_TRAV_WIDE) {                    // large scenes are often seen from outside: rays that miss the root (the reference's own
+    if (MODE == ARN_TRAV_WIDE || MODE == ARN_TRAV_CW8) {                    // large scenes are often seen from outside: rays that miss the root (the reference's own
         float t0;                                   // first test, bvh.rs:100-102) leave before the conservative-test constants are computed
         if (!slab(sc.root0, sc.root1, r, t0) || !(t0 < r.tmax)) { h.prim = -1; h.a = h.b = h.c = 0.f; return; }
     }
     CullRay c; cull_setup(sc, r, c);
-    if (MODE == ARN_TRAV_WIDE) traverse4(sc, r, c, h, any);
+    if (MODE == ARN_TRAV_CW8) traverse8(sc, r, c, h, any);
+    else if (MODE == ARN_TRAV_WIDE) traverse4(sc, r, c, h, any);
     else traverse2(sc, r, c, h, any);
 }
 

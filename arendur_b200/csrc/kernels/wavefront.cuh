@@ -217,7 +217,7 @@ template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 #ifndef ARN_TRAV_MINB_WIDE
 #define ARN_TRAV_MINB_WIDE (ARN_TRAV_MINB + 1)
 #endif
-__global__ void __launch_bounds__(ARN_BLOCK, MODE == ARN_TRAV_WIDE ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
+__global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == ARN_TRAV_CW8) ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par; const int first = j == 0;

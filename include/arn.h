@@ -379,7 +379,8 @@ int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_fil
                                        are only filled with 1                                                      */
 #define ARN_OPT_TRACE_REFILL    5   /* value != 0: lane-refilling trace (ray stream + persistent warps, kernels/trace_refill.cuh) on trees walked
                                        with the binary nodes; same bits; also env ARN_REFILL */
-#define ARN_OPT_BVH_WIDTH       3   /* 0 auto (default), 2 binary nodes, 4 the 4-wide collapse; same bits    */
+#define ARN_OPT_BVH_WIDTH       3   /* 0 auto (default), 2 binary nodes, 4 the 4-wide collapse, 8 the compressed 8-wide collapse (set BEFORE the
+                                       upload for trees below 2^20 nodes: the 8-wide nodes are built at upload); same bits */
 int arn_ctx_set_option(arn_ctx* ctx, int option, long long value);
 
 int arn_ctx_synchronize(arn_ctx* ctx);

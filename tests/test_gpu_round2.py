@@ -112,7 +112,7 @@ def test_film_reduce_over_nccl_two_ranks():
     assert "film reduce OK" in r.stdout
 
 
-@pytest.mark.parametrize("width", [2, 4])
+@pytest.mark.parametrize("width", [2, 4, 8])
 def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width):
     """Interior nodes are culled with a cheap conservative slab test, leaves with the reference's (traverse.cuh).  Rays that
     stress the argument: axis-parallel rays whose origins sit exactly on node planes (0 * inf = NaN in the reference's slab
@@ -155,9 +155,10 @@ def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width)
     tgt = np.float32([0.25, -0.5, 3.0]) + rng.normal(scale=0.3, size=(n, 3)); dv = tgt - o
     parts.append(rays_of(o, dv / np.linalg.norm(dv, axis=1, keepdims=True)))
     rays = np.concatenate(parts)
-    sc = ctx.upload(d); osc = O.OracleScene(d)
-    ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)
+    osc = O.OracleScene(d)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)          # before the upload: the compressed 8-wide nodes are built there
     try:
+        sc = ctx.upload(d)
         gh, ga = sc.intersect_closest(rays), sc.intersect_any(rays)
     finally:
         ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
@@ -199,4 +200,41 @@ def test_lane_refilling_trace_is_bit_exact(ctx, cornell_small):
     assert np.allclose(f0, f1, rtol=1e-5, atol=1e-6)
     _, orad = osc.render_pt_samples(cam, film, smp, prm)
     assert np.array_equal(rad1[..., :3], orad[..., :3])
+    sc.close(); osc.close()
+
+
+def test_compressed_8_wide_walk_renders_bit_exact(ctx, cornell_small):
+    """ARN_OPT_BVH_WIDTH = 8: quantised 8-wide nodes + leaf blob (kernels/cw8_build.cuh, traverse8).  Every camera sample of the
+    Cornell render (spheres, any-hit shadow rays, light rays) equals the oracle's; closest hits on 100 K random rays equal the
+    exact binary walk's."""
+    import torch
+    hs, cam, film, smp, prm = cornell_small
+    d = hs.desc()
+    osc = O.OracleScene(d)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, 8)
+    try:
+        sc = ctx.upload(d)
+        f8, rad8, st8 = sc.render_pt_samples(cam, film, smp, prm)
+        rng = np.random.default_rng(21)
+        n = 100_000
+        rays = np.zeros(n, api.RAY_DTYPE)
+        rays["o"] = rng.uniform([-1.8, -1.3, 2.2], [1.8, 2.2, 5.8], (n, 3)).astype(np.float32)
+        v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+        rays["d"] = v.astype(np.float32)
+        rays["tmax"] = np.where(rng.random(n) < 0.3, rng.uniform(0.1, 4.0, n), np.inf).astype(np.float32)
+        rd, hd = _dev(rays)
+        sc.intersect_closest_dev(rd.data_ptr(), n, hd.data_ptr())
+        ctx.synchronize()                                   # the *_dev queries are asynchronous on the context's stream
+        h8 = hd.cpu().numpy().copy()
+        hb = torch.empty_like(hd)
+        sc.intersect_closest_counted_dev(rd.data_ptr(), n, hb.data_ptr())           # the exact binary walk
+        a8 = sc.intersect_any(rays)
+    finally:
+        ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert np.array_equal(rad8[..., :3], orad[..., :3])
+    assert (st8.extend_rays, st8.shadow_rays, st8.mis_rays) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays)
+    assert np.array_equal(h8, hb.cpu().numpy())
+    assert np.array_equal(a8 != 0, hb.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)["prim_id"] >= 0)
     sc.close(); osc.close()

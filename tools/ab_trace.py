@@ -7,8 +7,9 @@ import os, sys, json, time
 sys.path.insert(0, os.environ["ARN_ROOT"])
 import numpy as np, torch
 from arendur_b200 import api, scenes, _lib as L
-out = {"lib": os.environ.get("ARN_LIB_PATH", "default") + ("+refill" if os.environ.get("ARN_REFILL") else "")}
+out = {"lib": os.environ.get("ARN_LIB_PATH", "default") + ("+refill" if os.environ.get("ARN_REFILL") else "") + ("+w" + os.environ["AB_WIDTH"] if os.environ.get("AB_WIDTH") else "")}
 ctx = api.Context(0)
+if os.environ.get('AB_WIDTH'): ctx.set_option(L.ARN_OPT_BVH_WIDTH, int(os.environ['AB_WIDTH']))
 def run(name, hs, cam, film, smp, prm, reps):
     sc = ctx.upload(hs.desc())
     res = {}
@@ -45,6 +46,8 @@ print("AB " + json.dumps(out))
 libs = [a for a in sys.argv[1:] if not a.startswith("--")]
 for lib in libs:
     env = dict(os.environ, ARN_ROOT=ROOT, AB_C4="1" if "--c4" in sys.argv else "0")
+    if lib.endswith("+w4"):                     # force the 4-wide walk (large trees default to the compressed 8-wide walk)
+        env["AB_WIDTH"] = "4"; lib = lib[:-3]
     if lib.endswith("+refill"):                 # the lane-refilling trace of the same build
         env["ARN_REFILL"] = "1"; lib = lib[:-7]
     if lib != "default":
