@@ -59,6 +59,14 @@ struct DevScene {
 };
 
 #define ARN_STACK 64           /* upload rejects trees deeper than this */
+// -DARN_DEBUG_STACK: device-side assertions on every push (the stacks are sized from the depth the upload measures; a build with
+// this flag traps instead of corrupting local memory if that reasoning were ever wrong).  Off in the product build.
+#ifdef ARN_DEBUG_STACK
+#include <cassert>
+#define ARN_STACK_CHECK(sp, cap) assert((sp) < (cap))
+#else
+#define ARN_STACK_CHECK(sp, cap) ((void)0)
+#endif
 #define ARN_STACK4 96          /* wide traversal: <= 3 pushes per wide level, ARN_STACK/2 wide levels */
 // reference words of a wide record: w0 = q1.z, w1 = q1.w
 //   w1 & 3 : 0 empty slot, 1 interior (w0 = wide node index, (w1 >> 2) & 63 = split axes of that node:
@@ -323,6 +331,7 @@ ARN_DEV void traverse(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr) 
             bool neg = axis_of(r.inv, (int)(len_axis & 3u)) < 0.f;     // dir_is_neg[split_axis]: second child first
             if (ha && hb) {
                 bool first_b = neg;
+                ARN_STACK_CHECK(sp, ARN_STACK);
                 stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(ta)) : make_uint2(ib, __float_as_uint(tb));
                 idx = first_b ? ib : ia;
                 offset = __float_as_uint(first_b ? b1.z : a1.z); len_axis = __float_as_uint(first_b ? b1.w : a1.w);
@@ -400,6 +409,7 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
             const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
             if (ha && hb) {
+                ARN_STACK_CHECK(sp, ARN_STACK);
                 stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
                 idx = first_b ? ib : ia;
                 offset = __float_as_uint(first_b ? b.q1.z : a.q1.z); len_axis = __float_as_uint(first_b ? b.q1.w : a.q1.w);
@@ -490,6 +500,7 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const uint32_t ec = r2 | ((kc & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u), ed = r3 | ((kd & 3u) == ARN_W_LEAF ? ARN_REC_LEAF : 0u);
             // every surviving record but the first in visiting order goes on the stack, last one first (branch-free)
             const bool have = ha | hb | hc | hd;
+            ARN_STACK_CHECK(sp + 2, ARN_STACK4);
             if (hd & (ha | hb | hc)) stack[sp++] = wide_entry(ed, td, __float_as_uint(nd.q1.z), kd);
             if (hc & (ha | hb)) stack[sp++] = wide_entry(ec, tc, __float_as_uint(nc.q1.z), kc);
             if (hb & ha) stack[sp++] = wide_entry(eb, tb, __float_as_uint(nb.q1.z), kb);
@@ -579,6 +590,7 @@ ARN_DEV void traverse8(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(sc.cw8 + 8 * (size_t)(gnode & 0xffffffu)) + 24u + slot);
             if ((gnode >> (24u + slot)) & 1u) { leaf_ref = ref; have_leaf = true; }
             else {
+                ARN_STACK_CHECK(sp, ARN_STACK8);
                 if (gpend & 0x88888888u) stack[sp++] = make_uint2(gnode, gpend);
                 cw8_expand(sc, r, c, ref, perm_off, gnode, gpend);
             }

@@ -3,6 +3,7 @@
 these values are derived by hand from the cited lines), host construction, JSON ingest."""
 import ctypes as C
 import json
+import os
 import math
 
 import numpy as np
@@ -142,7 +143,7 @@ def test_oracle_distant_light_uses_the_mis_weight():
 
 
 def test_json_lights(tmp_path):
-    src = json.load(open("tests/golden/mini_scene/scene.json"))
+    src = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mini_scene", "scene.json")))
     ident = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
     spot = api.spot_light((0.5, 2.5, 1.0), (0, -1, 0.2), (6, 6, 5), 0.9, 0.5)
     pl = np.array(spot.parent_local, f32).reshape(4, 4)
@@ -154,7 +155,7 @@ def test_json_lights(tmp_path):
     ]
     import shutil
     for f in ("room.obj", "room.mtl"):
-        shutil.copy(f"tests/golden/mini_scene/{f}", tmp_path / f)
+        shutil.copy(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mini_scene", f), tmp_path / f)
     p = tmp_path / "scene.json"
     p.write_text(json.dumps(src))
     hs = api.HostScene()

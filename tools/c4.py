@@ -38,8 +38,9 @@ print(f"c4 render {res}^2 x {sx*sx} spp: {st.gpu_ms:.1f} ms, all rays {rays/st.g
 ctx.set_option(L.ARN_OPT_COUNT_TRAVERSAL, 1)
 p1 = api.make_pt_params(max_depth=8, spp_begin=0, spp_end=1)
 f, stc = sc.render_pt(cam, film, smp, p1)
-bpr = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_spheres) / stc.extend_rays + 36
-print(f"Nn/ray {stc.extend_nodes/stc.extend_rays:.1f} Nt/ray {stc.extend_tris/stc.extend_rays:.2f} bytes/ray {bpr:.0f} -> extend algorithmic {bpr*st.extend_rays/st.extend_ms/1e6:.0f} GB/s of 6457 measured")
+rays_c = stc.extend_rays + stc.shadow_rays + stc.mis_rays        # the counters cover ALL traversals (path, shadow and light rays): divide by all of them, as bench.py does
+bpr = (32.0 * stc.extend_nodes + 36.0 * stc.extend_tris + 152.0 * stc.extend_spheres) / rays_c + 36
+print(f"Nn/ray {stc.extend_nodes/rays_c:.1f} Nt/ray {stc.extend_tris/rays_c:.2f} bytes/ray {bpr:.0f} (per traversal, all kinds) -> k_trace algorithmic {bpr*rays/st.extend_ms/1e6:.0f} GB/s of 6457 measured")
 g, _ = api.film_finalize(f)
 print("image mean", g.reshape(-1, 3).mean(0), "finite", np.isfinite(g).all())
 if os.environ.get("C4_CPU") == "1":        # CPU restatement on a bounded sample: the same view at 256 x 256, 1 spp
