@@ -59,11 +59,10 @@ struct DevScene {
 };
 
 #define ARN_STACK 64           /* upload rejects trees deeper than this */
-// -DARN_DEBUG_STACK: device-side assertions on every push (the stacks are sized from the depth the upload measures; a build with
+// -DARN_DEBUG_STACK: a device-side check on every push (the stacks are sized from the depth the upload measures; a build with
 // this flag traps instead of corrupting local memory if that reasoning were ever wrong).  Off in the product build.
 #ifdef ARN_DEBUG_STACK
-#include <cassert>
-#define ARN_STACK_CHECK(sp, cap) assert((sp) < (cap))
+#define ARN_STACK_CHECK(sp, cap) do { if ((sp) >= (cap)) __trap(); } while (0)
 #else
 #define ARN_STACK_CHECK(sp, cap) ((void)0)
 #endif
