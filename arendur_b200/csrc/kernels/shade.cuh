@@ -482,47 +482,51 @@ template <bool BECK> ARN_DEV void as_eval_pdf(const Lobe& x, float3 wo, float3 w
     }
 }
 template <uint32_t M> ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, float3 wi, bool want_f, float3& f, float& pdf) {
-    switch (known_kind<M>(x.kind)) {
-    case LOBE_TS_R: {
-        float3 wh = normalize(wo + wi);
-        const bool need_pdf = !(wo.z * wi.z <= 0.f);
-        const bool need_f = want_f && !any_nan(wh);
+    const int kind = known_kind<M>(x.kind);
+    if (kind == LOBE_TS_R || kind == LOBE_TS_T) {
+        // Both Torrance–Sparrow lobes in ONE code path: a glass BSDF samples one of them per path, so lanes of a warp hold
+        // either; the distribution terms D(wh), Lambda(wo), Lambda(wi) — most of the arithmetic — then run converged.  Every
+        // lane evaluates exactly the expressions of its own lobe (microfacet.rs:372-430 / :433-533), in the same order.
+        const bool is_t = kind == LOBE_TS_T;
         pdf = 0.f; f = grey(0.f);
-        if (!(need_pdf || need_f)) return;
-        float D = dist_D<false>(x.alpha, x.alpha, wh);
-        float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
-        if (need_pdf) pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) / (4.f * dot(wo, wh));
-        if (need_f) {
-            float li = dist_lambda<false>(x.alpha, x.alpha, wi);
-            f = x.a * D * (1.f / (1.f + lo + li)) * grey(fresnel_dielectric(dot(wi, wh), x.c0, x.c1)) / (4.f * fabsf(wo.z) * fabsf(wi.z));
+        float eta = 1.f; float3 wh; bool need_pdf = true, need_f = want_f;
+        if (is_t) {
+            if (wo.z * wi.z > 0.f) return;
+            eta = wo.z > 0.f ? x.c1 / x.c0 : x.c0 / x.c1;
+            wh = normalize(wo + wi * eta);
+            if (any_inf(wh) || any_nan(wh)) { pdf = 1.f; if (want_f) f = grey(1.f); return; }
+        } else {
+            wh = normalize(wo + wi);
+            need_pdf = !(wo.z * wi.z <= 0.f);
+            need_f = want_f && !any_nan(wh);
+            if (!(need_pdf || need_f)) return;
+        }
+        const float D = dist_D<false>(x.alpha, x.alpha, wh);
+        const float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
+        float li = 0.f;
+        if (need_f) li = dist_lambda<false>(x.alpha, x.alpha, wi);
+        if (is_t) {
+            {
+                float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+                float dhdi = eta * eta * fabsf(dot(wi, wh)) / (sqrt_denom * sqrt_denom);
+                pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) * dhdi;
+            }
+            if (want_f) {
+                if (wh.z < 0.f) wh = -wh;
+                float cosoh = dot(wo, wh);
+                float3 fr = grey(fresnel_dielectric(cosoh, x.c0, x.c1));
+                float cosih = dot(wi, wh);
+                float sqrt_denom = cosoh + eta * cosih;
+                f = x.a * D * (1.f / (1.f + lo + li)) * (grey(1.f) - fr) * fabsf(cosih) * fabsf(cosoh)
+                  / (fabsf(cos_theta(wo)) * fabsf(cos_theta(wi)) * sqrt_denom * sqrt_denom);
+            }
+        } else {
+            if (need_pdf) pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) / (4.f * dot(wo, wh));
+            if (need_f) f = x.a * D * (1.f / (1.f + lo + li)) * grey(fresnel_dielectric(dot(wi, wh), x.c0, x.c1)) / (4.f * fabsf(wo.z) * fabsf(wi.z));
         }
         return;
     }
-    case LOBE_TS_T: {
-        pdf = 0.f; f = grey(0.f);
-        if (wo.z * wi.z > 0.f) return;
-        float eta = wo.z > 0.f ? x.c1 / x.c0 : x.c0 / x.c1;
-        float3 wh = normalize(wo + wi * eta);
-        if (any_inf(wh) || any_nan(wh)) { pdf = 1.f; if (want_f) f = grey(1.f); return; }
-        float D = dist_D<false>(x.alpha, x.alpha, wh);
-        float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
-        {
-            float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
-            float dhdi = eta * eta * fabsf(dot(wi, wh)) / (sqrt_denom * sqrt_denom);
-            pdf = (D * (1.f / (1.f + lo)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) * dhdi;
-        }
-        if (want_f) {
-            if (wh.z < 0.f) wh = -wh;
-            float cosoh = dot(wo, wh);
-            float3 fr = grey(fresnel_dielectric(cosoh, x.c0, x.c1));
-            float cosih = dot(wi, wh);
-            float sqrt_denom = cosoh + eta * cosih;
-            float li = dist_lambda<false>(x.alpha, x.alpha, wi);
-            f = x.a * D * (1.f / (1.f + lo + li)) * (grey(1.f) - fr) * fabsf(cosih) * fabsf(cosoh)
-              / (fabsf(cos_theta(wo)) * fabsf(cos_theta(wi)) * sqrt_denom * sqrt_denom);
-        }
-        return;
-    }
+    switch (kind) {
     case LOBE_AS_BECK: as_eval_pdf<true>(x, wo, wi, want_f, f, pdf); return;
     case LOBE_AS_TROW: as_eval_pdf<false>(x, wo, wi, want_f, f, pdf); return;
     case LOBE_FRESNEL: pdf = 0.f; f = grey(0.f); return;                 // specular: no value, no density (fresnel.rs:150-161)
@@ -550,7 +554,31 @@ template <bool BECK> ARN_DEV Sampled as_sample(const Lobe& x, float3 wo, float2 
 }
 template <uint32_t M> ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, float2 u) {
     Sampled r; r.type = lobe_type(known_kind<M>(x.kind));
-    switch (known_kind<M>(x.kind)) {
+    const int kind = known_kind<M>(x.kind);
+    if (kind == LOBE_TS_R || kind == LOBE_TS_T) {
+        // one code path for both Torrance–Sparrow lobes (microfacet.rs:408-421 / :493-511): the half-vector sample and the
+        // value + density evaluation run converged for lanes that drew either lobe; per lane the expressions are the lobe's own
+        const float3 wh = dist_sample_wh<false>(x.alpha, x.alpha, wo, u);
+        float3 wi; bool ok;
+        if (kind == LOBE_TS_R) {
+            r.pdf = dist_pdf<false>(x.alpha, x.alpha, wo, wh) / (4.f * dot(wo, wh));
+            wi = normalize(2.f * wh * dot(wo, wh) - wo);
+            r.wi = wi; r.f = grey(0.f);
+            ok = !(wo.z * wi.z <= 0.f);
+        } else {
+            const float eta = wo.z > 0.f ? x.c0 / x.c1 : x.c1 / x.c0;
+            ok = refract(wo, wh, eta, wi);
+            if (ok) r.wi = wi; else { r.f = grey(0.f); r.wi = f3(0.f, 0.f, 0.f); r.pdf = 0.f; }
+        }
+        if (ok) {
+            float3 fv; float pv;
+            lobe_eval_pdf<M>(x, wo, wi, true, fv, pv);
+            r.f = fv;
+            if (kind == LOBE_TS_T) r.pdf = pv;
+        }
+        return r;
+    }
+    switch (kind) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
         float3 wi = sample_cosw_hemisphere(u);
         if (wo.z < 0.f) wi.z = -wi.z;
@@ -577,23 +605,6 @@ template <uint32_t M> ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, fl
         r.type = BXDF_TRANSMISSION | BXDF_SPECULAR; r.pdf = pdf;
         if (refract(wo, n, eta, wt)) { r.f = x.b * eta * eta * pdf / fabsf(wt.z); r.wi = wt; }
         else { r.f = grey(0.f); r.wi = f3(0.f, 0.f, 0.f); }
-        return r;
-    }
-    case LOBE_TS_R: {                                                        // microfacet.rs:408-421
-        float3 wh = dist_sample_wh<false>(x.alpha, x.alpha, wo, u);
-        r.pdf = dist_pdf<false>(x.alpha, x.alpha, wo, wh) / (4.f * dot(wo, wh));
-        float3 wi = normalize(2.f * wh * dot(wo, wh) - wo);
-        r.wi = wi;
-        r.f = grey(0.f);
-        if (!(wo.z * wi.z <= 0.f)) { float unused; lobe_eval_pdf<M>(x, wo, wi, true, r.f, unused); }
-        return r;
-    }
-    case LOBE_TS_T: {                                                        // :493-511
-        float3 wh = dist_sample_wh<false>(x.alpha, x.alpha, wo, u);
-        float eta = wo.z > 0.f ? x.c0 / x.c1 : x.c1 / x.c0;
-        float3 wi;
-        if (refract(wo, wh, eta, wi)) { lobe_eval_pdf<M>(x, wo, wi, true, r.f, r.pdf); r.wi = wi; }
-        else { r.f = grey(0.f); r.wi = f3(0.f, 0.f, 0.f); r.pdf = 0.f; }
         return r;
     }
     case LOBE_AS_BECK: return as_sample<true>(x, wo, u);
