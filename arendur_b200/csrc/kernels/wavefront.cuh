@@ -246,15 +246,15 @@ __global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == A
         const float4* __restrict__ rk = kind == 0u ? pb.ray : (kind == 1u ? pb.sh : pb.mis);
         uint32_t pid = 0; int cls = -1;
         if (j < nk) {
-            pid = __ldcs(&qk[j]);
-            const float4 o = __ldcs(&rk[2 * pid]), d = __ldcs(&rk[2 * pid + 1]);   // one 32-byte record; streaming: keep L1 for nodes, slots and the stacks
+            pid = __ldcg(&qk[j]);
+            const float4 o = __ldcg(&rk[2 * pid]), d = __ldcg(&rk[2 * pid + 1]);   // one 32-byte record; streaming: keep L1 for nodes, slots and the stacks
             TravRay r; trav_init(r, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), kind == 1u ? o.w : ARN_INF);
             HitRec h;
             // shadow rays: any hit (LightSample::occluded, lighting/mod.rs:125-133).  The counted instance runs the reference's full
             // closest-hit query there (component/mod.rs:35-38) so that its counters are the reference traversal's: same boolean
             trace_ray<MODE>(sc, r, h, ctr, kind == 1u && !COUNT);
             if (kind == 0u) {
-                __stcs(&pb.hit[pid], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
+                __stcg(&pb.hit[pid], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
                     if (ref & ARN_PRIM_SPHERE) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == A
                     cls = shading_class(sc.materials[mat]);
                 }
             } else if (kind == 1u) {
-                __stcs(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
+                __stcg(&pb.occluded[pid], h.prim >= 0 ? 1u : 0u);
             } else {
                 // `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155)
                 const float3 wi = f3(d.x, d.y, d.z);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == A
                     if (sp.has_transform) pos = xform_point(sp.local_parent, pos);
                     okl = is_black(light_le(sp, pos, -wi)) ? 0u : 1u;       // lsi.le(-wi)
                 }
-                __stcs(&pb.mis_ok[pid], okl);
+                __stcg(&pb.mis_ok[pid], okl);
             }
         }
         if (kind == 0u) {
