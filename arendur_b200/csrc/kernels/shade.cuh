@@ -347,7 +347,7 @@ ARN_DEV float fresnel_dielectric(float cti, float etai, float etat) {       // f
 
 // ---------------------------------------------------------------- BxDF lobes
 enum LobeKind { LOBE_LAMBERT_R = 0, LOBE_LAMBERT_T, LOBE_OREN_NAYAR, LOBE_FRESNEL, LOBE_TS_R, LOBE_TS_T, LOBE_AS_BECK, LOBE_AS_TROW };
-struct Lobe { int kind; float3 a, b; float c0, c1, alpha; };
+struct Lobe { int kind; float3 a, b; float c0, c1, alpha; float lam; };   // lam: Lambda(wo) of the lobe's microfacet distribution for THIS hit's outgoing direction (bsdf_prepare)
 struct Sampled { float3 f, wi; float pdf; uint32_t type; };
 
 ARN_DEV uint32_t lobe_type(int k) {
@@ -468,7 +468,7 @@ template <bool BECK> ARN_DEV void as_eval_pdf(const Lobe& x, float3 wo, float3 w
     if (need_pdf || need_f) D = dist_D<BECK>(x.alpha, x.alpha, wh);
     pdf = 0.f; f = grey(0.f);
     if (need_pdf) {
-        float dp = D * dist_visible<BECK>(x.alpha, x.alpha, wo) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo));
+        float dp = D * (1.f / (1.f + x.lam)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo));      // dist_visible(wo) = 1 / (1 + Lambda(wo)), Lambda(wo) once per hit
         pdf = 0.5f * (dp / (4.f * dot(wo, wh)) + fabsf(cos_theta(wi)) * ARN_INV_PI);
     }
     if (need_f) {
@@ -502,7 +502,7 @@ template <uint32_t M> ARN_NOINL void lobe_eval_pdf(const Lobe& x, float3 wo, flo
             if (!(need_pdf || need_f)) return;
         }
         const float D = dist_D<false>(x.alpha, x.alpha, wh);
-        const float lo = dist_lambda<false>(x.alpha, x.alpha, wo);
+        const float lo = x.lam;                                           // Lambda(wo): once per hit (bsdf_prepare), not once per lobe evaluation
         float li = 0.f;
         if (need_f) li = dist_lambda<false>(x.alpha, x.alpha, wi);
         if (is_t) {
@@ -561,7 +561,7 @@ template <uint32_t M> ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, fl
         const float3 wh = dist_sample_wh<false>(x.alpha, x.alpha, wo, u);
         float3 wi; bool ok;
         if (kind == LOBE_TS_R) {
-            r.pdf = dist_pdf<false>(x.alpha, x.alpha, wo, wh) / (4.f * dot(wo, wh));
+            r.pdf = (dist_D<false>(x.alpha, x.alpha, wh) * (1.f / (1.f + x.lam)) * fabsf(dot(wo, wh)) / fabsf(cos_theta(wo))) / (4.f * dot(wo, wh));   // dist_pdf(wo, wh) / (4 wo.wh)
             wi = normalize(2.f * wh * dot(wo, wh) - wo);
             r.wi = wi; r.f = grey(0.f);
             ok = !(wo.z * wi.z <= 0.f);
@@ -613,7 +613,7 @@ template <uint32_t M> ARN_NOINL Sampled lobe_sample(const Lobe& x, float3 wo, fl
 }
 
 // ---------------------------------------------------------------- Bsdf (material/bsdf.rs)
-struct Bsdf { float3 ns, ng, ts, bs; Lobe lobe[3]; int n; };
+struct Bsdf { float3 ns, ng, ts, bs; Lobe lobe[3]; int n; float3 wo_l; };   // wo_l: the hit's outgoing direction in the local frame (bsdf_prepare)
 
 ARN_DEV float3 to_local(const Bsdf& b, float3 v) { return f3(dot(v, b.ts), dot(v, b.bs), dot(v, b.ns)); }
 ARN_DEV float3 to_parent(const Bsdf& b, float3 v) {
@@ -623,7 +623,7 @@ ARN_DEV float3 to_parent(const Bsdf& b, float3 v) {
 ARN_DEV void bsdf_build(const arn_material& m, const Surf& s, Bsdf& b) {
     b.ts = normalize(s.dpdu); b.ns = s.ns; b.bs = normalize(cross(b.ns, b.ts)); b.ng = s.ng; b.n = 0;
     float3 kd = f3(m.kd[0], m.kd[1], m.kd[2]), ks = f3(m.ks[0], m.ks[1], m.ks[2]);
-    Lobe z; z.kind = 0; z.a = grey(0.f); z.b = grey(0.f); z.c0 = 0.f; z.c1 = 0.f; z.alpha = m.alpha;
+    Lobe z; z.kind = 0; z.a = grey(0.f); z.b = grey(0.f); z.c0 = 0.f; z.c1 = 0.f; z.alpha = m.alpha; z.lam = 0.f;
     switch (m.type) {
     case ARN_MAT_MATTE: {
         float sig = clampf(m.sigma, 0.f, 90.f);
@@ -684,8 +684,24 @@ ARN_DEV float bsdf_pdf(const Bsdf& b, float3 wow, float3 wiw) {
     return b.n == 0 ? pdfsum : pdfsum / (float)b.n;
 }
 // Bsdf::evaluate + Bsdf::pdf for the same pair of directions (the NEE light sample needs both, scene.rs:98-101)
+// The microfacet lobes of one Bsdf share (alpha, distribution), and every evaluation / sampling call of a hit uses the same
+// outgoing direction: Lambda(wo) and the local wo are computed ONCE per hit instead of once per lobe evaluation (up to eight
+// times for glass).  Same function of the same arguments: the bits do not change.
+template <uint32_t M> ARN_DEV void bsdf_prepare(Bsdf& b, float3 wow) {
+    b.wo_l = normalize(to_local(b, wow));
+    bool need = false, beck = false;
+    for (int i = 0; i < b.n; i++) {
+        const int k = known_kind<M>(b.lobe[i].kind);
+        if (k == LOBE_TS_R || k == LOBE_TS_T || k == LOBE_AS_TROW) need = true;
+        if (k == LOBE_AS_BECK) { need = true; beck = true; }
+    }
+    float lam = 0.f;
+    if (need) lam = beck ? dist_lambda<true>(b.lobe[0].alpha, b.lobe[0].alpha, b.wo_l) : dist_lambda<false>(b.lobe[0].alpha, b.lobe[0].alpha, b.wo_l);
+    for (int i = 0; i < b.n; i++) b.lobe[i].lam = lam;
+}
+// `wow` must be the direction bsdf_prepare was given (the hit's wo)
 template <uint32_t M> ARN_DEV void bsdf_eval_pdf(const Bsdf& b, float3 wow, float3 wiw, float3& f, float& pdf) {
-    float3 wo = normalize(to_local(b, wow)), wi = normalize(to_local(b, wiw));
+    float3 wo = b.wo_l, wi = normalize(to_local(b, wiw));
     bool is_reflection = dot(wow, b.ng) * dot(wiw, b.ng) > 0.f;
     f = grey(0.f);
     float pdfsum = 0.f;
@@ -704,7 +720,7 @@ template <uint32_t M> ARN_NOINL Sampled bsdf_sample(const Bsdf& b, float3 wow, f
     Sampled ret; ret.f = grey(0.f); ret.wi = f3(0.f, 1.f, 0.f); ret.pdf = 0.f; ret.type = 0;
     int match_count = b.n;
     if (match_count == 0) return ret;
-    float3 wo = normalize(to_local(b, wow));
+    float3 wo = b.wo_l;                                    // = normalize(to_local(b, wow)), see bsdf_prepare
     int idx = (int)floorf(u.x * (float)match_count); if (idx > match_count - 1) idx = match_count - 1;
     Sampled s = lobe_sample<M>(b.lobe[idx], wo, u);
     if (s.pdf == 0.f) return ret;

@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                     const arn_material m = textured_material(sc, mat, s, sx, dxy);
                     bsdf_build(m, s, bsdf);
                 } else bsdf_build(sc.materials[mat], s, bsdf);
+                if (!DIFFUSE) bsdf_prepare<LOBES>(bsdf, s.wo);
                 uint32_t flags = 0;
                 if (bsdf.n > 0) {                                           // pt.rs:85-91 (have_n(ALL-SPECULAR) > 0 <=> any lobe)
                     // Scene::uniform_sample_one_light (scene.rs:58-66)
