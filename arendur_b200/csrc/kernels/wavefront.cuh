@@ -591,17 +591,27 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant_
     if ((threadIdx.x & 31) == 0 && invalid) atomicAdd(&q.stats[3], invalid);
 }
 
-// ---- K6 accumulate, warp-per-pixel form (filter radius <= 4): a warp walks the samples of ONE
-// pixel of the wave (they are consecutive path slots), keeps the 9x9 window of affected film pixels in
-// registers (3 targets per lane), and issues one vector atomic per target per pixel instead of 64 per
-// sample.  Every (L*w, w) term is the scatter kernel's; only the order of the additions differs.
+// ---- K6 accumulate, warp-per-pixel form (filter radius <= 4): a warp owns ONE pixel of the wave (its samples are
+// consecutive path slots) and keeps the 9x9 window of affected film pixels in registers (3 targets per lane): one vector
+// atomic per target per pixel instead of 64 per sample.  Two phases per chunk of 32 samples: (1) lane k validates sample k,
+// clips its splat box and evaluates its 9 + 9 separable filter factors (zero outside the box: adding L * 0 and 0 is exact)
+// into shared memory; (2) the warp walks the chunk in sample order, every lane adding w = wx * wy and L * w to its three
+// targets.  Every (L*w, w) term is the scatter kernel's; only the order of the additions across pixels differs.
+#define ARN_ACC_STRIDE 19            // 18 factors per sample, odd stride: conflict-free stores
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film,
                                                               unsigned long long wave_base, uint32_t n) {
-    const unsigned lane = threadIdx.x & 31u;
+    __shared__ float s_w[ARN_BLOCK / 32][32 * ARN_ACC_STRIDE];
+    __shared__ float4 s_L[ARN_BLOCK / 32][32];
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    float* __restrict__ wrow = s_w[wib];
+    float4* __restrict__ lrow = s_L[wib];
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long first_pl = wave_base / p.spp_count, last_pl = (wave_base + n - 1) / p.spp_count;
     unsigned long long invalid = 0;
+    int tx[3], ty[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { const int t = min((int)lane + 32 * j, 80); tx[j] = t % 9; ty[j] = 9 + t / 9; }
     for (unsigned long long pl = first_pl + warp; pl <= last_pl; pl += nwarps) {
         unsigned long long g0 = pl * p.spp_count, g1 = g0 + p.spp_count;
         uint32_t s_begin = (uint32_t)((g0 > wave_base ? g0 : wave_base) - wave_base);
@@ -613,34 +623,41 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
         float4 acc[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t s = s_begin; s < s_end; s++) {
-            float4 l4 = pb.L[s];
-            float3 L = f3(l4.x, l4.y, l4.z);
-            bool valid = !(isnan(L.x) || isnan(L.y) || isnan(L.z)) && !(isinf(L.x) || isinf(L.y) || isinf(L.z)) && L.x >= 0.f && L.y >= 0.f && L.z >= 0.f;
-            if (!valid) { L = grey(0.f); if (lane == 0) invalid++; }     // pt.rs:152-156
-            float2 pos = pb.pfilm[s];
-            float cx = pos.x - p.fr_x + 0.5f, cy = pos.y - p.fr_y + 0.5f;
-            float fx = pos.x + p.fr_x - 0.5f, fy = pos.y + p.fr_y - 0.5f;
-            int x0 = (int)cx, y0 = (int)cy, x1 = (int)fx + 1, y1 = (int)fy + 1;   // truncation toward zero
-            if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
-            if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
-            x0 = max(x0, sx0); y0 = max(y0, sy0); x1 = min(x1, sx1); y1 = min(y1, sy1);
-            float wv = 0.f;
-            if (lane < 9) wv = filter1(p, ((float)(px - 4 + (int)lane) + 0.5f) - pos.x, p.fr_x);
-            else if (lane < 18) wv = filter1(p, ((float)(py - 4 + (int)lane - 9) + 0.5f) - pos.y, p.fr_y);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                int t = (int)lane + 32 * j;
-                int tx = t % 9, ty = t / 9;
-                float wx = __shfl_sync(0xffffffffu, wv, tx);
-                float wy = __shfl_sync(0xffffffffu, wv, 9 + (ty < 9 ? ty : 8));
-                int X = px - 4 + tx, Y = py - 4 + ty;
-                if (t < 81 && X >= x0 && X < x1 && Y >= y0 && Y < y1) {
-                    float w = wx * wy;
-                    float3 c = L * w;
-                    acc[j].x += c.x; acc[j].y += c.y; acc[j].z += c.z; acc[j].w += w;
+        for (uint32_t base = s_begin; base < s_end; base += 32u) {
+            const uint32_t cnt = min(32u, s_end - base);
+            if (lane < cnt) {
+                const uint32_t s = base + lane;
+                float4 l4 = pb.L[s];
+                bool valid = !(isnan(l4.x) || isnan(l4.y) || isnan(l4.z)) && !(isinf(l4.x) || isinf(l4.y) || isinf(l4.z)) && l4.x >= 0.f && l4.y >= 0.f && l4.z >= 0.f;
+                if (!valid) { l4 = make_float4(0.f, 0.f, 0.f, 0.f); invalid++; }     // pt.rs:152-156
+                lrow[lane] = l4;
+                float2 pos = pb.pfilm[s];
+                float cx = pos.x - p.fr_x + 0.5f, cy = pos.y - p.fr_y + 0.5f;
+                float fx = pos.x + p.fr_x - 0.5f, fy = pos.y + p.fr_y - 0.5f;
+                int x0 = (int)cx, y0 = (int)cy, x1 = (int)fx + 1, y1 = (int)fy + 1;   // truncation toward zero
+                if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
+                if (y0 > y1) { int t = y0; y0 = y1; y1 = t; }
+                x0 = max(x0, sx0); y0 = max(y0, sy0); x1 = min(x1, sx1); y1 = min(y1, sy1);
+                float* __restrict__ w = wrow + lane * ARN_ACC_STRIDE;
+#pragma unroll 1
+                for (int i = 0; i < 9; i++) {
+                    const int X = px - 4 + i, Y = py - 4 + i;
+                    const float wx = filter1(p, ((float)X + 0.5f) - pos.x, p.fr_x), wy = filter1(p, ((float)Y + 0.5f) - pos.y, p.fr_y);
+                    w[i] = (X >= x0 && X < x1) ? wx : 0.f;
+                    w[9 + i] = (Y >= y0 && Y < y1) ? wy : 0.f;
                 }
             }
+            __syncwarp();
+            for (uint32_t k = 0; k < cnt; k++) {
+                const float4 l4 = lrow[k];
+                const float* __restrict__ w = wrow + k * ARN_ACC_STRIDE;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float wv = w[tx[j]] * w[ty[j]];
+                    acc[j].x += l4.x * wv; acc[j].y += l4.y * wv; acc[j].z += l4.z * wv; acc[j].w += wv;
+                }
+            }
+            __syncwarp();
         }
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -651,6 +668,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
                 atomicAdd(&film[(size_t)(Y - p.crop_y0) * (size_t)p.crop_w + (size_t)(X - p.crop_x0)], acc[j]);
         }
     }
+    for (int off = 16; off > 0; off >>= 1) invalid += __shfl_down_sync(0xffffffffu, invalid, off);
     if (lane == 0 && invalid) atomicAdd(&q.stats[3], invalid);
 }
 
