@@ -387,6 +387,70 @@ ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, Trav
 
 // Binary walk over the 32-byte pre-order nodes (cache-resident trees).  Stack entry = (node, conservative entry distance).
 // `any` (warp-uniform at every call site): stop at the first accepted primitive
+#ifndef ARN_SPEC_LEAF
+#define ARN_SPEC_LEAF 0                /* 1 (measured, slower: DESIGN.md §4): a lane that reaches a leaf postpones it and keeps walking until it holds a second one */
+#endif
+#if ARN_SPEC_LEAF
+// Speculative while-while (Aila & Laine): the first leaf a lane reaches is POSTPONED and the lane goes on through interior nodes
+// until it stands on a second leaf (or its stack is empty); the leaf phase then runs the postponed leaf, then the second one —
+// the reference's order.  What the walk does between the two with a tmax the postponed leaf might have shortened is interior
+// culling only, which merely has to be conservative (a larger tmax culls less); every leaf still takes the exact test with the
+// tmax current at ITS turn.  The warp switches phases half as often and both phases run with more lanes.
+ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
+    h.prim = -1; h.a = h.b = h.c = 0.f;
+    uint2 stack[ARN_STACK];
+    int sp = 0;
+    uint32_t idx = 0, offset, len_axis;
+    {
+        const Node8 n = ld_node(sc.nodes);
+        float lo;
+        if (!slab_cull(n.q0, n.q1, r, c, lo)) return;
+        offset = __float_as_uint(n.q1.z); len_axis = __float_as_uint(n.q1.w);
+    }
+    const uint32_t NONE = 0xffffffffu;
+    uint32_t pleaf = NONE;
+    bool more = true;                                       // (idx, offset, len_axis) is a node still to be visited
+    for (;;) {
+        while (more) {
+            if ((len_axis >> 2) != 0) {
+                if (pleaf != NONE) break;                   // second leaf: leaf phase
+                pleaf = idx;
+                more = trav_pop(sc, r, stack, sp, idx, offset, len_axis);
+                continue;
+            }
+            const uint32_t ia = idx + 1, ib = idx + offset;
+            const Node8 a = ld_node(sc.nodes + 2 * ia), b = ld_node(sc.nodes + 2 * ib);
+            float la, lb;
+            const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
+            const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
+            if (ha && hb) {
+                ARN_STACK_CHECK(sp, ARN_STACK);
+                stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
+                idx = first_b ? ib : ia;
+                offset = __float_as_uint(first_b ? b.q1.z : a.q1.z); len_axis = __float_as_uint(first_b ? b.q1.w : a.q1.w);
+            } else if (ha || hb) {
+                idx = ha ? ia : ib;
+                offset = __float_as_uint(ha ? a.q1.z : b.q1.z); len_axis = __float_as_uint(ha ? a.q1.w : b.q1.w);
+            } else more = trav_pop(sc, r, stack, sp, idx, offset, len_axis);
+        }
+        // ---- leaf phase: the postponed leaf, then the one the lane stands on; each takes the reference's own slab test on its bounds
+        // (they come back from L1) with the tmax current at its turn, then its primitives
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            uint32_t li;
+            if (k == 0) { li = pleaf; pleaf = NONE; if (li == NONE) continue; }
+            else { if (!more) return; li = idx; }
+            const Node8 n = ld_node(sc.nodes + 2 * li);
+            float t0;
+            if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
+                if (leaf_prims(sc, __float_as_uint(n.q1.z), __float_as_uint(n.q1.w) >> 2, r, h, any)) return;
+            }
+        }
+        more = trav_pop(sc, r, stack, sp, idx, offset, len_axis);
+        if (!more) return;
+    }
+}
+#else
 ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
@@ -429,6 +493,7 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
         if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
     }
 }
+#endif
 
 // ---- 4-wide walk (trees that do not fit the caches) ------------------------------------------------------------
 // The wide tree is the binary tree with every second level removed: wide node = (children of the first child, children
