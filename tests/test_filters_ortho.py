@@ -105,7 +105,7 @@ def test_ortho_camera_bit_exact(ctx, lens):
     _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
     _, orad = osc.render_pt_samples(cam, film, smp, prm)
     same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
-    assert same.mean() >= 1.0 - 1e-4, f"{(~same).sum()} of {same.size} samples differ"
+    assert same.all(), f"{(~same).sum()} of {same.size} samples differ"
     assert (orad[..., :3].max(-1) > 0).mean() > 0.1
     sc.close(); osc.close()
 

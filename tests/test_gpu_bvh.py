@@ -70,7 +70,7 @@ def test_gpu_build_structure_and_same_tree_parity(ctx):
     _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
     _, orad = osc.render_pt_samples(cam, film, smp, prm)
     same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
-    assert same.mean() >= 1.0 - 1e-4
+    assert same.all()
     sc.close(); osc.close()
 
 

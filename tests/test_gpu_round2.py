@@ -171,6 +171,69 @@ def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width)
     sc.close(); osc.close()
 
 
+@pytest.mark.parametrize("width", [2, 4, 8])
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 3e4])
+def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
+    """Fuzz of the walk on geometry the regular fixtures do not have: triangle soups at three coordinate scales with axis-aligned
+    (zero-thickness boxes), degenerate (collinear / repeated vertices) and duplicated triangles (exact ties: the first in slot order
+    wins on both sides), clipped and transformed spheres; rays from random points, from vertex coordinates and along the axes."""
+    rng = np.random.default_rng(1000 * width + int(math.log10(scale) * 7) + 77)
+    S = np.float32(scale)
+    h = api.HostScene()
+    mat = h.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+    n_tri = 2500
+    c = rng.uniform(-1, 1, (n_tri, 1, 3)); e = rng.normal(scale=0.08, size=(n_tri, 3, 3))
+    tri = (c + e).astype(np.float32)
+    k = n_tri // 5
+    for ax in range(3):                                  # flat in one axis: zero-thickness bounds
+        sel = slice(ax * k // 3, (ax + 1) * k // 3)
+        tri[sel, :, ax] = np.round(tri[sel, :1, ax] * 8) / 8
+    tri[k:k + 60, 2] = tri[k:k + 60, 1]                  # repeated vertex
+    tri[k + 60:k + 120, 2] = (tri[k + 60:k + 120, 0] + tri[k + 60:k + 120, 1]) * np.float32(0.5)   # collinear
+    tri[k + 120:k + 220] = tri[k + 220:k + 320]          # exact duplicates
+    tri *= S
+    pos = tri.reshape(-1, 3); idx = np.arange(pos.shape[0], dtype=np.uint32).reshape(-1, 3)
+    h.add_mesh(pos, idx, mat)
+    for _ in range(6):
+        rad = float(rng.uniform(0.05, 0.3)) * float(S)
+        t = np.eye(4, dtype=np.float32); t[3, :3] = rng.uniform(-1, 1, 3) * S
+        if rng.random() < 0.5:
+            a = rng.uniform(0, 6.28); t[0, 0], t[0, 1], t[1, 0], t[1, 1] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+        h.add_sphere(rad, -rad * float(rng.uniform(0.3, 1)), rad * float(rng.uniform(0.3, 1)), float(rng.uniform(2, 6.2832)), mat, transform=t)
+    d = h.build()
+
+    def rays_of(o, dvec, tmax=np.inf):
+        r = np.zeros(o.shape[0], api.RAY_DTYPE)
+        r["o"], r["d"], r["tmax"] = o.astype(np.float32), dvec.astype(np.float32), tmax
+        return r
+    n = 8000
+    parts = []
+    o = rng.uniform(-1.5, 1.5, (n, 3)) * S; v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    parts.append(rays_of(o, v))
+    parts.append(rays_of(o, v * S))                      # unnormalised directions
+    verts = pos[rng.integers(0, pos.shape[0], n)]
+    parts.append(rays_of(verts, v))                      # origins on vertices = on box planes
+    axes = np.eye(3, dtype=np.float32)[rng.integers(0, 3, n)] * rng.choice(np.float32([-1, 1]), (n, 1))
+    o2 = verts.copy(); o2 -= axes * np.float32(3.0) * S
+    parts.append(rays_of(o2, axes))                      # axis-parallel rays through vertex coordinates
+    tgt = pos[rng.integers(0, pos.shape[0], n)]; dv = tgt - o
+    parts.append(rays_of(o, dv, rng.choice(np.float32([np.inf, 1.0, 1.0000001, 0.9999999]), n)))   # aimed at vertices, tmax at the hit
+    rays = np.concatenate(parts)
+    osc = O.OracleScene(d)
+    ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)
+    try:
+        sc = ctx.upload(d)
+        gh, ga = sc.intersect_closest(rays), sc.intersect_any(rays)
+    finally:
+        ctx.set_option(L.ARN_OPT_BVH_WIDTH, 0)
+    oh = osc.intersect_closest(rays)
+    assert (oh["prim_id"] >= 0).sum() > rays.shape[0] // 8
+    mism = np.nonzero((gh["prim_id"] != oh["prim_id"]) | (gh["t"] != oh["t"]))[0]
+    assert mism.size == 0, f"{mism.size} mismatches, first rays {mism[:5]}: o {rays['o'][mism[:3]]} d {rays['d'][mism[:3]]} gpu {gh[mism[:3]]} oracle {oh[mism[:3]]}"
+    assert np.array_equal(ga != 0, oh["prim_id"] >= 0)
+    sc.close(); osc.close()
+
+
 def test_fast_transcendentals_are_the_library_values_for_every_f32(ctx):
     """kernels/cr_math.cuh on the device, all 2^32 arguments: the short f64 kernels + rounding-certainty test return exactly
     (float)libdevice_f64(x) for sin, cos, exp, log (and pow with a pseudo-random exponent per base)."""
