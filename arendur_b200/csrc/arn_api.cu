@@ -928,6 +928,43 @@ extern "C" int arn_selftest_math(arn_ctx* c, uint32_t first_bits, uint32_t count
     return ARN_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(128) k_selftest_bsdf(const arn_material m, uint32_t n, const float* __restrict__ wo3, const float* __restrict__ u2,
+                                                       const float* __restrict__ wi3, const float* __restrict__ fr, float* __restrict__ out12) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float3 wo = f3(wo3[3 * i], wo3[3 * i + 1], wo3[3 * i + 2]), wi = f3(wi3[3 * i], wi3[3 * i + 1], wi3[3 * i + 2]);
+        Surf s; s.pos = f3(0.f, 0.f, 0.f); s.perr = s.pos; s.wo = wo; s.ng = f3(0.f, 0.f, 1.f); s.ns = s.ng; s.dpdu = f3(1.f, 0.f, 0.f);
+        if (fr) { const float* q = fr + 9 * (size_t)i; s.dpdu = f3(q[0], q[1], q[2]); s.ns = f3(q[3], q[4], q[5]); s.ng = f3(q[6], q[7], q[8]); }
+        Bsdf b; bsdf_build(m, s, b);
+        bsdf_prepare<LOBES_ALL>(b, wo);
+        const Sampled sm = bsdf_sample<LOBES_ALL>(b, wo, f2(u2[2 * i], u2[2 * i + 1]));
+        float3 f; float pdf; bsdf_eval_pdf<LOBES_ALL>(b, wo, wi, f, pdf);
+        float* o = out12 + 12 * (size_t)i;
+        o[0] = sm.f.x; o[1] = sm.f.y; o[2] = sm.f.z; o[3] = sm.wi.x; o[4] = sm.wi.y; o[5] = sm.wi.z; o[6] = sm.pdf; o[7] = (float)sm.type;
+        o[8] = f.x; o[9] = f.y; o[10] = f.z; o[11] = pdf;
+    }
+}
+}  // namespace
+
+extern "C" int arn_selftest_bsdf(arn_ctx* c, const arn_material* m, size_t n, const float* wo3, const float* u2, const float* wi3, const float* frame9, float* out12) {
+    if (!c || !m || !wo3 || !u2 || !wi3 || !out12 || n == 0 || n > (1u << 24)) return set_err(c, ARN_E_INVALID, "arn_selftest_bsdf: bad argument");
+    if (m->type > ARN_MAT_TRANSLUCENT || m->kd_tex || m->ks_tex || m->aux_tex || m->bump_tex) return set_err(c, ARN_E_INVALID, "arn_selftest_bsdf: constant materials only");
+    std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
+    float* d = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d, n * 29 * sizeof(float)));
+    float *dwo = d, *du = d + 3 * n, *dwi = d + 5 * n, *dout = d + 8 * n, *dfr = d + 20 * n;
+    cudaError_t e = cudaMemcpyAsync(dwo, wo3, n * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(du, u2, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dwi, wi3, n * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && frame9) e = cudaMemcpyAsync(dfr, frame9, n * 36, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) { k_selftest_bsdf<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(*m, (uint32_t)n, dwo, du, dwi, frame9 ? dfr : nullptr, dout); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out12, dout, n * 48, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(c, ARN_E_CUDA, cudaGetErrorString(e));
+    return ARN_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU film merge (Film::merge_into across GPUs)
 // NCCL is resolved at first use with dlopen("libnccl.so.2"): a process that already loaded NCCL (torch, or the Rust
 // host's own binding) gets that same copy, a stand-alone host gets the system library, and single-GPU users never

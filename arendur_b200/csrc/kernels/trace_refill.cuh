@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace_refill(const
                         float lo;
                         if (slab_cull(nd.q0, nd.q1, r, c, lo)) { idx = 0; offset = __float_as_uint(nd.q1.z); len_axis = __float_as_uint(nd.q1.w); busy = true; }
                     }
-                    if (!busy) __stcs(&tb.res[slot], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));      // ended at the root
+                    if (!busy) { __stcs(&tb.res[slot], make_float4(__int_as_float(h.prim), h.a, h.b, h.c)); __stcs(&tb.rs[slot], make_float4(r.d.x, r.d.y, r.d.z, 0.f)); }      // ended at the root
                 }
             }
             exhausted_mask = __ballot_sync(0xffffffffu, exhausted);
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace_refill(const
                 } else if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) {
                     busy = false;
                     __stcs(&tb.res[slot], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
+                    __stcs(&tb.rs[slot], make_float4(r.d.x, r.d.y, r.d.z, 0.f));       // the direction the ray leaves the traversal with (plane 0 of its set-up record is consumed)
                 }
             }
         } else {
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_trace_refill(const
                 if (done || !trav_pop(sc, r, stack, sp, idx, offset, len_axis)) {
                     busy = false;
                     __stcs(&tb.res[slot], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
+                    __stcs(&tb.rs[slot], make_float4(r.d.x, r.d.y, r.d.z, 0.f));       // the direction the ray leaves the traversal with (plane 0 of its set-up record is consumed)
                 }
             }
         }
@@ -176,15 +178,12 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_classify(const __grid_constant__ 
                 __stcs(&pb.hit[pid], res);
                 if (prim >= 0) {
                     uint32_t ref = sc.prims[prim], mat;
-                    if (ref & ARN_PRIM_SPHERE) {
-                        const DevSphere& sp = sc.spheres[ref & ~ARN_PRIM_SPHERE];
-                        mat = sp.material;
-                        if (sp.has_transform) {       // `*ray = iray`: the ray leaves traversal round-tripped (sphere_slot's arithmetic)
-                            const float4 d4 = pb.ray[2 * pid + 1];
-                            const float3 nd = xform_vector(sp.local_parent, xform_vector(sp.parent_local, f3(d4.x, d4.y, d4.z)));
-                            pb.ray[2 * pid + 1] = make_float4(nd.x, nd.y, nd.z, d4.w);
-                        }
-                    } else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                    if (ref & ARN_PRIM_SPHERE) mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
+                    else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                    {   // `*ray = iray`: accepted hits on transformed spheres leave the ray round-tripped (sphere_slot), see k_trace
+                        const float4 d4 = pb.ray[2 * pid + 1], nd = __ldcs(&tb.rs[gi]);
+                        if (nd.x != d4.x || nd.y != d4.y || nd.z != d4.z) pb.ray[2 * pid + 1] = make_float4(nd.x, nd.y, nd.z, d4.w);
+                    }
                     cls = shading_class(sc.materials[mat]);
                 }
             } else if (rr.kind == 1u) {

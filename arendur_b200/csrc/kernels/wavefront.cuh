@@ -257,10 +257,12 @@ __global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == A
                 __stcg(&pb.hit[pid], make_float4(__int_as_float(h.prim), h.a, h.b, h.c));
                 if (h.prim >= 0) {
                     uint32_t ref = sc.prims[h.prim], mat;
-                    if (ref & ARN_PRIM_SPHERE) {
-                        mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
-                        pb.ray[2 * pid + 1] = make_float4(r.d.x, r.d.y, r.d.z, d.w);   // `*ray = iray`: the ray leaves traversal round-tripped
-                    } else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                    if (ref & ARN_PRIM_SPHERE) mat = sc.spheres[ref & ~ARN_PRIM_SPHERE].material;
+                    else mat = sc.meshes[sc.tri_mesh[ref]].material;
+                    // `*ray = iray` (bvh.rs:108-113): every accepted hit on a transformed sphere leaves the traversal ray round-tripped
+                    // through that sphere's frame — also when a nearer primitive is accepted afterwards.  Shading's wo is the ray that
+                    // left the traversal, so a changed direction goes back into the ray record.
+                    if (r.d.x != d.x || r.d.y != d.y || r.d.z != d.z) pb.ray[2 * pid + 1] = make_float4(r.d.x, r.d.y, r.d.z, d.w);
                     cls = shading_class(sc.materials[mat]);
                 }
             } else if (kind == 1u) {
@@ -441,6 +443,12 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                             float lpdf = analytic ? 0.f : light_pdf(light, s.pos, bs.wi);
                             if (lpdf == 0.f) skip = true; else weight = power_heuristic(bs.pdf, lpdf);
                         }
+#ifdef ARN_DBG_PIX
+                        if (pb.pix[pid] == (uint32_t)(ARN_DBG_PIX) && pb.smp[pid] == (uint32_t)(ARN_DBG_SMP))
+                            printf("[dbg] pos %.9g %.9g %.9g ns %.9g %.9g %.9g wo %.9g %.9g %.9g uscatter %.9g %.9g\n      bs.f %.9g %.9g %.9g wi %.9g %.9g %.9g pdf %.9g type %u f2v %.9g %.9g %.9g lpdf %.9g weight %.9g skip %d\n",
+                                   s.pos.x, s.pos.y, s.pos.z, s.ns.x, s.ns.y, s.ns.z, s.wo.x, s.wo.y, s.wo.z, uscatter.x, uscatter.y, bs.f.x, bs.f.y, bs.f.z, bs.wi.x, bs.wi.y, bs.wi.z, bs.pdf, bs.type, f2v.x, f2v.y, f2v.z,
+                                   (bs.type & BXDF_SPECULAR) ? -1.f : light_pdf(light, s.pos, bs.wi), weight, (int)skip);
+#endif
                         if (!skip) {
                             float3 mo = offset_towards(s, bs.wi);
                             if (!analytic) A2 = f2v * sphere_emission(light) * weight / bs.pdf;

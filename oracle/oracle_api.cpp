@@ -218,9 +218,15 @@ float arn_oracle_roughness_to_alpha(float r) { return roughness_to_alpha(r); }
 
 // BSDF probe for kernel-level parity: evaluate_sampled / evaluate / pdf of a material at a fixed
 // local frame (ts, bs, ns = x, y, z; ng = z).  out: f(3), wi(3), pdf, type, feval(3), pdfeval
+int arn_oracle_bsdf_probe2(const arn_material* m, const float* wo3, const float* u2, const float* wi_eval3, const float* frame9, float* out12);
 int arn_oracle_bsdf_probe(const arn_material* m, const float* wo3, const float* u2, const float* wi_eval3, float* out12) {
+    return arn_oracle_bsdf_probe2(m, wo3, u2, wi_eval3, nullptr, out12);
+}
+// frame9 (optional): dpdu, shading normal, geometric normal
+int arn_oracle_bsdf_probe2(const arn_material* m, const float* wo3, const float* u2, const float* wi_eval3, const float* frame9, float* out12) {
     SurfaceInteraction si; std::memset(&si, 0, sizeof si);
     si.shading_duv.dpdu = v3(1, 0, 0); si.shading_norm = v3(0, 0, 1); si.basic.norm = v3(0, 0, 1);
+    if (frame9) { si.shading_duv.dpdu = v3(frame9[0], frame9[1], frame9[2]); si.shading_norm = v3(frame9[3], frame9[4], frame9[5]); si.basic.norm = v3(frame9[6], frame9[7], frame9[8]); }
     Bsdf b = compute_scattering(*m, si);
     Sampled s = bsdf_evaluate_sampled(b, v3(wo3[0], wo3[1], wo3[2]), v2(u2[0], u2[1]), BXDF_ALL);
     out12[0] = s.f.x; out12[1] = s.f.y; out12[2] = s.f.z; out12[3] = s.wi.x; out12[4] = s.wi.y; out12[5] = s.wi.z;

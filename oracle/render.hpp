@@ -3,6 +3,8 @@
 //   src/filming/{projective,perspective,film}.rs, src/component/{shape,transformed}.rs (Light impls),
 //   src/lighting/mod.rs, src/renderer/{pt,scene}.rs
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -209,6 +211,10 @@ inline bool ls_occluded(const Scene& s, const LightSample& ls, RayStats* st) {
 }
 
 // Scene::evaluate_direct (renderer/scene.rs:83-167)
+// Debugging aid of the test infrastructure: ARN_ORACLE_TRACE="x,y,s" makes the render print what that camera sample does, bounce by bounce.
+inline thread_local bool g_trace = false;
+#define ORC_TRACE(...) do { if (g_trace) std::fprintf(stderr, __VA_ARGS__); } while (0)
+
 inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 uscattering,
                            const SurfaceInteraction& si, const Bsdf& bsdf, RayStats* st) {
     if (light_comp & ARN_LIGHT_ANALYTIC) {
@@ -252,6 +258,7 @@ inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 us
         if (!is_black(f) && ls_occluded(s, ls, st)) f = grey(0.f);
         Float weight = power_heuristic(ls.pdf, spdf);                       // area lights are never delta
         RGB addition = ls.radiance * f * weight / ls.pdf;
+        ORC_TRACE("    light sample: radiance %.9g %.9g %.9g pdf %.9g wi %.9g %.9g %.9g f %.9g %.9g %.9g spdf %.9g weight %.9g add %.9g %.9g %.9g\n", ls.radiance.x, ls.radiance.y, ls.radiance.z, ls.pdf, wi.x, wi.y, wi.z, f.x, f.y, f.z, spdf, weight, addition.x, addition.y, addition.z);
         ret = ret + addition;
     }
     // sample BSDF with multiple importance sampling
@@ -261,6 +268,7 @@ inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 us
         Float weight = 1.f;
         if (!(bs.type & BXDF_SPECULAR)) {
             Float lpdf = light_pdf(light, si.basic.pos, bs.wi);
+            ORC_TRACE("    light_pdf %.9g\n", lpdf);
             if (lpdf == 0.f) return ret;
             weight = power_heuristic(bs.pdf, lpdf);
         }
@@ -271,6 +279,7 @@ inline RGB evaluate_direct(const Scene& s, uint32_t light_comp, V2 ulight, V2 us
         if (bvh_intersect(s, ray, &lsi, &lprim, st ? &st->trav : nullptr, true)) {
             if ((uint32_t)lprim == light_comp) li = si_le(s, lsi, -bs.wi);  // ptr::eq(light, primitive.as_light())
         }
+        ORC_TRACE("    bsdf sample: wi %.9g %.9g %.9g f*cos %.9g %.9g %.9g pdf %.9g type %u weight %.9g hit %d li %.9g %.9g %.9g\n", bs.wi.x, bs.wi.y, bs.wi.z, f.x, f.y, f.z, bs.pdf, (unsigned)bs.type, weight, lprim, li.x, li.y, li.z);
         if (!is_black(li)) {
             RGB addition = f * li * weight / bs.pdf;
             ret = ret + addition;
@@ -311,7 +320,10 @@ inline RGB calculate_lighting(const Scene& s, RawRay ray, ParitySampler& sampler
                                 sampler.next(), &lidx, &lightpdf);
                 V2 ulight = sampler.next_2d();
                 V2 uscattering = sampler.next_2d();
+                ORC_TRACE("  si: wo %.9g %.9g %.9g ng %.9g %.9g %.9g ns %.9g %.9g %.9g dpdu %.9g %.9g %.9g ulight %.9g %.9g uscatter %.9g %.9g\n", si.basic.wo.x, si.basic.wo.y, si.basic.wo.z, si.basic.norm.x, si.basic.norm.y, si.basic.norm.z,
+                          si.shading_norm.x, si.shading_norm.y, si.shading_norm.z, si.shading_duv.dpdu.x, si.shading_duv.dpdu.y, si.shading_duv.dpdu.z, ulight.x, ulight.y, uscattering.x, uscattering.y);
                 RGB term = evaluate_direct(s, s.light_prims[lidx], ulight, uscattering, si, bsdf, st) / lightpdf;
+                ORC_TRACE("  bounce %u prim %d material %u (type %u) pos %.9g %.9g %.9g light %u (comp 0x%x) lightpdf %.9g direct %.9g %.9g %.9g beta %.9g %.9g %.9g\n", bounces, prim, mat, (unsigned)s.materials[mat].type, si.basic.pos.x, si.basic.pos.y, si.basic.pos.z, lidx, s.light_prims[lidx], lightpdf, term.x, term.y, term.z, beta.x, beta.y, beta.z);
                 ret = ret + beta * term;
             }
             V3 wo = -ray.dir;
@@ -402,6 +414,8 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
     std::atomic<size_t> next_tile(0);
     if (nthreads < 1) nthreads = 1;
     std::vector<RayStats> tstats((size_t)nthreads);
+    long trace_x = -1, trace_y = -1, trace_s = -1;
+    const bool trace_on = std::getenv("ARN_ORACLE_TRACE") && std::sscanf(std::getenv("ARN_ORACLE_TRACE"), "%ld,%ld,%ld", &trace_x, &trace_y, &trace_s) == 3;
     auto worker = [&](int tid) {
         for (;;) {
             size_t ti = next_tile.fetch_add(1);
@@ -427,6 +441,7 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
                     RawRay ray = camera_generate(cam, pfilm, plens);
                     tstats[tid].camera++;
                     RGB L;
+                    g_trace = trace_on && x == trace_x && y == trace_y && (long)si == trace_s;
                     if (!s.textures.empty()) {                                   // pt.rs:141-142
                         RayDifferential rd = camera_generate_differential(cam, pfilm, plens);
                         scale_differentials(rd, 1.f / (Float)spp);

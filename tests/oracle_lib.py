@@ -72,6 +72,7 @@ def load():
     lib.arn_oracle_roughness_to_alpha.restype = C.c_float
     lib.arn_oracle_roughness_to_alpha.argtypes = [C.c_float]
     lib.arn_oracle_bsdf_probe.argtypes = [C.POINTER(L.Material), vp, vp, vp, vp]
+    lib.arn_oracle_bsdf_probe2.argtypes = [C.POINTER(L.Material), vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

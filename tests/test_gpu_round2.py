@@ -301,3 +301,149 @@ def test_compressed_8_wide_walk_renders_bit_exact(ctx, cornell_small):
     assert np.array_equal(h8, hb.cpu().numpy())
     assert np.array_equal(a8 != 0, hb.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)["prim_id"] >= 0)
     sc.close(); osc.close()
+
+
+def _random_scene(seed):
+    """A random scene for the shading fuzz: a closed room of random quads, a soup of triangles with and without shading normals,
+    random materials of all four families with parameters out to the clamps, sphere emitters (clipped / transformed) and a random
+    set of delta / distant lights, a random camera (perspective with or without lens, or orthographic)."""
+    rng = np.random.default_rng(seed)
+    hs = api.HostScene()
+    mats = []
+    for _ in range(10):
+        kind = int(rng.integers(0, 4))
+        col = lambda lo=0.0, hi=1.0: tuple(float(x) for x in rng.uniform(lo, hi, 3))
+        rough = float(rng.choice([0.001, 0.01, 0.08, 0.3, 0.7, 1.0, 2.5]))
+        if kind == 0:
+            m = api.material(L.ARN_MAT_MATTE, kd=col(), sigma=float(rng.choice([0.0, 0.0, 0.3, 20.0, 90.0, 140.0])))
+        elif kind == 1:
+            m = api.material(L.ARN_MAT_PLASTIC, kd=col(), ks=col(), roughness=rough)
+        elif kind == 2:
+            m = api.material(L.ARN_MAT_GLASS, kd=col() if rng.random() < 0.7 else (0, 0, 0), ks=col() if rng.random() < 0.7 else (0, 0, 0), roughness=rough,
+                             eta=float(rng.choice([1.0001, 1.2, 1.5, 2.4, 0.75])))
+        else:
+            m = api.material(L.ARN_MAT_TRANSLUCENT, kd=col(), ks=col(), roughness=rough, dissolve=float(rng.choice([0.0, 0.3, 0.8, 1.0])))
+        mats.append(hs.add_material(m))
+    pick = lambda: mats[int(rng.integers(0, len(mats)))]
+    # room [-3, 3]^3, each wall one quad
+    B = 3.0
+    walls = [([-B, -B, -B], [B, -B, -B], [B, -B, B], [-B, -B, B]), ([-B, B, -B], [-B, B, B], [B, B, B], [B, B, -B]),
+             ([-B, -B, -B], [-B, B, -B], [B, B, -B], [B, -B, -B]), ([-B, -B, B], [B, -B, B], [B, B, B], [-B, B, B]),
+             ([-B, -B, -B], [-B, -B, B], [-B, B, B], [-B, B, -B]), ([B, -B, -B], [B, B, -B], [B, B, B], [B, -B, B])]
+    for q in walls:
+        hs.add_mesh(np.float32(q), np.uint32([0, 1, 2, 0, 2, 3]), pick())
+    for _ in range(14):                                   # objects: small random meshes, half of them with shading normals / uvs
+        c = rng.uniform(-2.2, 2.2, 3); nt = int(rng.integers(1, 12))
+        pos = (c + rng.normal(scale=0.5, size=(nt * 3, 3))).astype(np.float32)
+        idx = np.arange(nt * 3, dtype=np.uint32)
+        nrm = uv = None
+        if rng.random() < 0.5:
+            nrm = rng.normal(size=(nt * 3, 3)).astype(np.float32); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        if rng.random() < 0.5:
+            uv = rng.uniform(0, 1, (nt * 3, 2)).astype(np.float32)
+        hs.add_mesh(pos, idx, pick(), normals=nrm, uvs=uv)
+    for k in range(int(rng.integers(1, 4))):              # sphere emitters
+        rad = float(rng.uniform(0.15, 0.6))
+        t = np.eye(4, dtype=np.float32); t[3, :3] = rng.uniform(-2.3, 2.3, 3)
+        if rng.random() < 0.5:
+            a = rng.uniform(0, 6.28); t[1, 1], t[1, 2], t[2, 1], t[2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+        full = rng.random() < 0.5
+        hs.add_sphere(rad, -rad if full else -rad * float(rng.uniform(0.2, 0.9)), rad if full else rad * float(rng.uniform(0.2, 0.9)),
+                      6.2831855 if full else float(rng.uniform(2.0, 6.0)), pick(), emission=tuple(float(x) for x in rng.uniform(2, 30, 3)), transform=t)
+    for k in range(2):                                    # non-emissive spheres
+        rad = float(rng.uniform(0.3, 0.8)); t = np.eye(4, dtype=np.float32); t[3, :3] = rng.uniform(-2, 2, 3)
+        hs.add_sphere(rad, -rad, rad, 6.2831855, pick(), transform=t)
+    if rng.random() < 0.7:
+        hs.add_light(api.point_light(rng.uniform(-2, 2, 3), rng.uniform(1, 20, 3)))
+    if rng.random() < 0.7:
+        hs.add_light(api.spot_light(rng.uniform(-2, 2, 3), rng.uniform(-1, 1, 3), rng.uniform(5, 40, 3), float(rng.uniform(0.4, 1.2)), float(rng.uniform(0.1, 0.35))))
+    if rng.random() < 0.5:
+        dv = rng.normal(size=3); hs.add_light(api.distant_light(rng.uniform(0.2, 2, 3), dv / np.linalg.norm(dv), 6.0))
+    hs.build()
+    eye = rng.uniform(-2.0, 2.0, 3); eye[2] = 2.6
+    view_parent = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, -1, 0], [eye[0], eye[1], eye[2], 1]], np.float32)      # looking along -z
+    w, h = 56, 40
+    lens = (float(rng.uniform(0.02, 0.2)), float(rng.uniform(2, 5))) if rng.random() < 0.4 else None
+    if rng.random() < 0.25:
+        cam = api.make_ortho_camera(view_parent.reshape(-1), (-2.5, -1.8, 2.5, 1.8), 0.1, 100.0, w, h, lens=lens)
+    else:
+        parent_view = np.linalg.inv(view_parent.T).T.astype(np.float32)
+        cam = api.make_camera(parent_view.reshape(-1), (-1.3, -0.95, 1.3, 0.95), 0.1, 100.0, float(rng.uniform(0.7, 1.4)), w, h, lens=lens)
+    depth = int(rng.choice([1, 2, 5, 8, 12]))
+    prm = api.make_pt_params(max_depth=depth, rr_threshold=float(rng.choice([0.05, 0.5, 0.0])))
+    return hs, cam, api.make_film(w, h), api.make_sampler(2, 2, int(rng.choice([2, 8])), int(rng.integers(0, 1 << 30))), prm
+
+
+@pytest.mark.parametrize("seed", [0, 2, 3, 4, 5, 6, 7, 9, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 24, 25, 26, 27])
+def test_random_scenes_per_sample_radiance_is_bit_exact(ctx, seed):
+    """Shading fuzz: every camera sample's radiance through the whole bounce loop equals the oracle's bit for bit on random scenes
+    (materials of all four families out to their parameter clamps, partial / transformed sphere emitters, Point / Spot / Distant
+    lights, thin lens / orthographic cameras, depths 1 .. 12, three Russian-roulette thresholds); so do the traced-ray counters."""
+    hs, cam, film, smp, prm = _random_scene(seed)
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.all(), f"seed {seed}: {(~same).sum()} of {same.size} samples differ, first {np.argwhere(~same)[:3].tolist()}: gpu {grad[~same][:2]} oracle {orad[~same][:2]}"
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
+    assert (orad[..., :3].max(-1) > 0).mean() > 0.08
+    sc.close(); osc.close()
+
+
+def _probe_material(rng, kind):
+    col = lambda: tuple(float(x) for x in rng.uniform(0, 1, 3))
+    rough = float(rng.choice([0.0005, 0.001, 0.01, 0.08, 0.3, 0.7, 1.0, 2.5]))
+    if kind == 0:
+        m = api.material(L.ARN_MAT_MATTE, kd=col(), sigma=float(rng.choice([0.0, 0.3, 20.0, 90.0, 140.0])))
+    elif kind == 1:
+        m = api.material(L.ARN_MAT_PLASTIC, kd=col(), ks=col(), roughness=rough)
+    elif kind == 2:
+        m = api.material(L.ARN_MAT_GLASS, kd=col() if rng.random() < 0.8 else (0, 0, 0), ks=col() if rng.random() < 0.6 else (0, 0, 0), roughness=rough,
+                         eta=float(rng.choice([1.0001, 1.2, 1.5, 2.4, 0.75])))
+    else:
+        m = api.material(L.ARN_MAT_TRANSLUCENT, kd=col(), ks=col(), roughness=rough, dissolve=float(rng.choice([0.0, 0.3, 0.8, 1.0])))
+    m.alpha = O.load().arn_oracle_roughness_to_alpha(m.roughness)
+    return m
+
+
+@pytest.mark.parametrize("general_frame", [False, True])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_bsdf_probe_is_bit_exact(ctx, kind, general_frame):
+    """Kernel-level parity of Bsdf::{evaluate_sampled, evaluate, pdf} (material/bsdf.rs) for every material family: 12 random
+    materials x 4096 (wo, u, wi) triples incl. grazing, axis-aligned and below-horizon directions, in the canonical frame and in
+    random frames (dpdu not orthogonal to the shading normal, shading normal != geometric normal) — the device probe
+    (arn_selftest_bsdf) returns the oracle's twelve floats bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(4242 + kind + 10 * int(general_frame))
+    n = 4096
+    olib = O.load()
+    for rep in range(12):
+        m = _probe_material(rng, kind)
+        def dirs():
+            v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+            v[: n // 8, 2] *= 1e-3                                     # grazing (renormalised below)
+            v[n // 8: n // 8 + 16] = np.float32([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0]] * 4)
+            v /= np.linalg.norm(v, axis=1, keepdims=True)
+            return np.ascontiguousarray(v, np.float32)
+        wo, wi = dirs(), dirs()
+        wi[n // 2: n // 2 + 512] = wo[n // 2: n // 2 + 512] * np.float32([-1, -1, 1])      # mirror directions: the microfacet peak
+        u = np.ascontiguousarray(rng.uniform(0, 1, (n, 2)), np.float32); u[:8] = np.float32([[0, 0], [0.5, 0.5], [0.999999, 0.999999], [0.5, 0], [0, 0.5], [0.25, 0.75], [0.49999997, 0.1], [0.75, 1e-7]])
+        fr = None
+        if general_frame:
+            ns = rng.normal(size=(n, 3)); ns /= np.linalg.norm(ns, axis=1, keepdims=True)
+            ng = ns + rng.normal(scale=0.2, size=(n, 3)); ng /= np.linalg.norm(ng, axis=1, keepdims=True)
+            dpdu = np.cross(ng, rng.normal(size=(n, 3))) * rng.uniform(0.1, 5, (n, 1))
+            fr = np.ascontiguousarray(np.concatenate([dpdu, ns, ng], 1), np.float32)
+        gout = np.zeros((n, 12), np.float32)
+        rc = ctx.lib.arn_selftest_bsdf(ctx.c, C.byref(m), n, wo.ctypes.data, u.ctypes.data, wi.ctypes.data, fr.ctypes.data if fr is not None else None, gout.ctypes.data)
+        assert rc == 0, ctx.error()
+        oout = np.zeros((n, 12), np.float32)
+        for i in range(n):
+            olib.arn_oracle_bsdf_probe2(C.byref(m), wo[i].ctypes.data, u[i].ctypes.data, wi[i].ctypes.data, fr[i].ctypes.data if fr is not None else None, oout[i].ctypes.data)
+        gb, ob = gout.view(np.uint32), oout.view(np.uint32)
+        same = (gb == ob) | (np.isnan(gout) & np.isnan(oout))
+        bad = np.argwhere(~same.all(axis=1))[:, 0]
+        assert bad.size == 0, (f"material {rep} (type {m.type} rough {m.roughness} eta {m.eta} dissolve {m.dissolve} sigma {m.sigma} kd {list(m.kd)} ks {list(m.ks)}): {bad.size} of {n} probes differ; "
+                               f"first {bad[0]}: wo {wo[bad[0]]} u {u[bad[0]]} wi {wi[bad[0]]}\n gpu    {gout[bad[0]]}\n oracle {oout[bad[0]]}")
