@@ -303,12 +303,34 @@ def test_compressed_8_wide_walk_renders_bit_exact(ctx, cornell_small):
     sc.close(); osc.close()
 
 
-def _random_scene(seed):
+def _random_pyramid(rng, channels, scale):
+    h, w = int(rng.choice([1, 2, 8, 16, 32])), int(rng.choice([2, 4, 16, 32]))
+    lv = []
+    while True:
+        shape = (h, w, 3) if channels == 3 else (h, w)
+        lv.append((scale * rng.random(shape)).astype(np.float32))
+        if h == 1 and w == 1:
+            break
+        h, w = max(h // 2, 1), max(w // 2, 1)
+    return lv
+
+
+def _random_scene(seed, textured=False):
     """A random scene for the shading fuzz: a closed room of random quads, a soup of triangles with and without shading normals,
     random materials of all four families with parameters out to the clamps, sphere emitters (clipped / transformed) and a random
-    set of delta / distant lights, a random camera (perspective with or without lens, or orthographic)."""
+    set of delta / distant lights, a random camera (perspective with or without lens, or orthographic).  `textured`: random image
+    textures (RGB on kd / ks, Luma on sigma | roughness and as bump maps; trilinear and EWA, all wrap modes) on most materials."""
     rng = np.random.default_rng(seed)
     hs = api.HostScene()
+    rgb_tex, luma_tex, bump_tex = [0], [0], [0]
+    if textured:
+        wraps = [L.ARN_WRAP_REPEAT, L.ARN_WRAP_CLAMP, L.ARN_WRAP_BLACK]
+        def tex(channels, scale):
+            return hs.add_texture(_random_pyramid(rng, channels, scale), trilinear=bool(rng.random() < 0.5), max_aniso=float(rng.choice([1.0, 4.0, 8.0, 16.0])),
+                                  wrapping=wraps[int(rng.integers(0, 3))], scaling=tuple(float(x) for x in rng.uniform(0.3, 6, 2)), shifting=tuple(float(x) for x in rng.uniform(-1, 1, 2)))
+        rgb_tex += [tex(3, 1.0) for _ in range(3)]
+        luma_tex += [tex(1, float(rng.choice([0.6, 30.0]))) for _ in range(2)]
+        bump_tex += [tex(1, float(rng.choice([0.01, 0.2]))) for _ in range(2)]
     mats = []
     for _ in range(10):
         kind = int(rng.integers(0, 4))
@@ -323,6 +345,9 @@ def _random_scene(seed):
                              eta=float(rng.choice([1.0001, 1.2, 1.5, 2.4, 0.75])))
         else:
             m = api.material(L.ARN_MAT_TRANSLUCENT, kd=col(), ks=col(), roughness=rough, dissolve=float(rng.choice([0.0, 0.3, 0.8, 1.0])))
+        if textured:
+            m.kd_tex, m.ks_tex = int(rng.choice(rgb_tex)), int(rng.choice(rgb_tex))
+            m.aux_tex, m.bump_tex = int(rng.choice(luma_tex)), int(rng.choice(bump_tex))
         mats.append(hs.add_material(m))
     pick = lambda: mats[int(rng.integers(0, len(mats)))]
     # room [-3, 3]^3, each wall one quad
@@ -447,3 +472,21 @@ def test_bsdf_probe_is_bit_exact(ctx, kind, general_frame):
         bad = np.argwhere(~same.all(axis=1))[:, 0]
         assert bad.size == 0, (f"material {rep} (type {m.type} rough {m.roughness} eta {m.eta} dissolve {m.dissolve} sigma {m.sigma} kd {list(m.kd)} ks {list(m.ks)}): {bad.size} of {n} probes differ; "
                                f"first {bad[0]}: wo {wo[bad[0]]} u {u[bad[0]]} wi {wi[bad[0]]}\n gpu    {gout[bad[0]]}\n oracle {oout[bad[0]]}")
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_textured_scenes_per_sample_radiance_is_bit_exact(ctx, seed):
+    """The shading fuzz with image textures: MipMap look-ups (trilinear / EWA, three wrap modes, pyramids from 1 x 2 to 32 x 32 texels),
+    UV mappings, ray differentials through up to 12 bounces, bump mapping on meshes with and without shading normals / uvs and on
+    rotated, clipped spheres — through the textured shade instance, every camera sample equals the oracle's."""
+    hs, cam, film, smp, prm = _random_scene(seed, textured=True)
+    d = hs.desc()
+    assert d.n_textures == 7
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1) | np.all(np.isnan(grad) == np.isnan(orad), axis=-1) & np.all((grad == orad) | np.isnan(grad), axis=-1)
+    assert same.all(), f"seed {seed}: {(~same).sum()} of {same.size} samples differ, first {np.argwhere(~same)[:3].tolist()}: gpu {grad[~same][:2]} oracle {orad[~same][:2]}"
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
+    sc.close(); osc.close()
