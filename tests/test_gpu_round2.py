@@ -490,3 +490,47 @@ def test_random_textured_scenes_per_sample_radiance_is_bit_exact(ctx, seed):
     _, ost, _ = osc.render_pt(cam, film, smp, prm)
     assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
     sc.close(); osc.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_film_configurations_match_the_oracle(ctx, seed):
+    """Film fuzz (k_accumulate_px / k_accumulate): random resolution, crop window, filter kind and radius (<= 4: warp-per-pixel
+    gather, > 4: scatter), tile grid, samples per pixel (chunks of 32 per warp: counts around that), wave capacity (pixels whose
+    samples straddle waves), rank / world / cell subdivision — the film equals the oracle's up to the order of the float additions."""
+    rng = np.random.default_rng(900 + seed)
+    w, h = int(rng.integers(20, 70)), int(rng.integers(16, 50))
+    sx, sy = [(1, 1), (3, 1), (2, 2), (5, 7), (6, 6), (8, 4), (11, 3)][int(rng.integers(0, 7))]
+    hs, cam, _, _, _ = scenes.cornell_scene(w, h, sx, sy)
+    x0, y0 = int(rng.integers(0, w // 3)), int(rng.integers(0, h // 3))
+    crop = (0, 0, w, h) if rng.random() < 0.4 else (x0, y0, int(rng.integers(x0 + 8, w + 1)), int(rng.integers(y0 + 8, h + 1)))
+    kinds = [(0, 0.0, 0.0), (L.ARN_FILTER_BOX, 0.0, 0.0), (L.ARN_FILTER_TRIANGLE, 0.0, 0.0), (L.ARN_FILTER_GAUSSIAN, 0.7, 0.0), (L.ARN_FILTER_MITCHELL, 1.0 / 3, 1.0 / 3)]
+    kind, fa, fb = kinds[int(rng.integers(0, 5))]
+    radius = [(4.0, 4.0), (2.0, 2.0), (0.5, 0.5), (2.7, 1.3), (1.0, 3.9), (6.0, 5.0), (4.5, 2.0)][int(rng.integers(0, 7))]
+    film = api.make_film(w, h, crop=crop, filter_radius=radius, filter_kind=kind, filter_a=fa, filter_b=fb)
+    smp = api.make_sampler(sx, sy, 8, int(rng.integers(0, 1 << 30)))
+    cw, ch = crop[2] - crop[0], crop[3] - crop[1]
+    tiles = (int(rng.integers(1, min(cw, 9))), int(rng.integers(1, min(ch, 9))))
+    world = int(rng.choice([1, 1, 2, 3])); rank = int(rng.integers(0, world)); subdiv = int(rng.choice([0, 0, 2, 4]))
+    prm = api.make_pt_params(max_depth=3, tiles=tiles, rank=rank, world_size=world, subdiv=subdiv)
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    cfg = f"res {w}x{h} crop {crop} spp {sx}x{sy} filter {kind} r {radius} tiles {tiles} rank {rank}/{world} subdiv {subdiv}"
+    wave = int(rng.choice([0, 1024, 4096]))
+    try:
+        of, ost, _ = osc.render_pt(cam, film, smp, prm)
+    except Exception:
+        # the reference panics here (film.rs:129: a tile of the grid laid out from (0, 0) misses the crop window): both sides refuse
+        with pytest.raises(api.ArnError):
+            sc.render_pt(cam, film, smp, prm)
+        sc.close(); osc.close()
+        return
+    ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, wave)
+    try:
+        gf, st = sc.render_pt(cam, film, smp, prm)
+    finally:
+        ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
+    assert st.camera_rays == ost.camera_rays > 0, cfg
+    assert gf.shape == of.shape and np.isfinite(gf).all(), cfg
+    scale = max(float(np.abs(of).max()), 1e-6)
+    assert np.abs(gf - of).max() <= 1e-5 * scale, f"{cfg}: max diff {np.abs(gf - of).max()} of {scale}"
+    sc.close(); osc.close()
