@@ -19,6 +19,7 @@ ARN_LIGHT_ANALYTIC = 0x80000000
 ARN_FILTER_LANCZOS, ARN_FILTER_BOX, ARN_FILTER_TRIANGLE, ARN_FILTER_GAUSSIAN, ARN_FILTER_MITCHELL = 0, 1, 2, 3, 4
 ARN_MAT_MATTE, ARN_MAT_PLASTIC, ARN_MAT_GLASS, ARN_MAT_TRANSLUCENT = 0, 1, 2, 3
 ARN_WRAP_REPEAT, ARN_WRAP_BLACK, ARN_WRAP_CLAMP = 0, 1, 2
+ARN_SAMPLER_PARITY, ARN_SAMPLER_STRATIFIED = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
 c_u32_p = C.POINTER(C.c_uint32)
@@ -84,7 +85,7 @@ class Film(C.Structure):
 
 
 class Sampler(C.Structure):
-    _fields_ = [("sampledx", C.c_uint32), ("sampledy", C.c_uint32), ("ndim", C.c_uint32), ("seed", C.c_uint32)]
+    _fields_ = [("sampledx", C.c_uint32), ("sampledy", C.c_uint32), ("ndim", C.c_uint32), ("seed", C.c_uint32), ("mode", C.c_uint32)]
 
 
 class PTParams(C.Structure):

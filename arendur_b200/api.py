@@ -66,9 +66,10 @@ def make_ortho_camera(view_parent, screen, znear, zfar, res_x, res_y, lens=None)
     return cam
 
 
-def make_sampler(sampledx, sampledy, ndim=8, seed=0):
+def make_sampler(sampledx, sampledy, ndim=8, seed=0, mode=0):
+    """mode: L.ARN_SAMPLER_PARITY (the reference's effective behaviour) or L.ARN_SAMPLER_STRATIFIED (the sampler as intended)."""
     s = L.Sampler()
-    s.sampledx, s.sampledy, s.ndim, s.seed = sampledx, sampledy, ndim, seed
+    s.sampledx, s.sampledy, s.ndim, s.seed, s.mode = sampledx, sampledy, ndim, seed, mode
     return s
 
 

@@ -669,6 +669,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     uint32_t spp = smp->sampledx * smp->sampledy;
     uint32_t s0 = prm->spp_begin, s1 = prm->spp_end ? prm->spp_end : spp;
     if (s1 <= s0) return set_err(c, ARN_E_INVALID, "arn_render_pt: empty sample range");
+    if (smp->mode > ARN_SAMPLER_STRATIFIED) return set_err(c, ARN_E_INVALID, "arn_render_pt: unknown sampler mode");
+    if (smp->mode == ARN_SAMPLER_STRATIFIED && s1 > spp) return set_err(c, ARN_E_INVALID, "arn_render_pt: the stratified sampler has sampledx * sampledy samples per pixel");
     if (prm->max_depth == 0 || prm->max_depth > 80) return set_err(c, ARN_E_INVALID, "arn_render_pt: max_depth must be in 1..80");
     uint32_t world = prm->world_size ? prm->world_size : 1;
     if (prm->rank >= world) return set_err(c, ARN_E_INVALID, "arn_render_pt: rank >= world_size");
@@ -748,6 +750,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     wp.n_tiles = (uint32_t)rects.size(); wp.tile_rect = c->d_tile_rect; wp.tile_prefix = c->d_tile_prefix;
     wp.spp_begin = s0; wp.spp_count = s1 - s0;
     wp.textured = textured ? 1u : 0u; wp.spp_total = spp;
+    wp.strat_ndim = smp->mode == ARN_SAMPLER_STRATIFIED ? smp->ndim : 0u; wp.sampledx = smp->sampledx; wp.sampledy = smp->sampledy;
 
     size_t ev = 0;
     cudaEvent_t e_begin = get_event(c, ev++), e_end = get_event(c, ev++);

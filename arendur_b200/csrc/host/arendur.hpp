@@ -162,7 +162,8 @@ struct OrthoCam {                                          // filming/ortho.rs:1
     }
 };
 
-struct StrataSampler { arn_sampler s; static StrataSampler make(uint32_t sampledx, uint32_t sampledy, uint32_t ndim, uint32_t seed = 0) { return StrataSampler{{sampledx, sampledy, ndim, seed}}; } };
+struct StrataSampler { arn_sampler s; static StrataSampler make(uint32_t sampledx, uint32_t sampledy, uint32_t ndim, uint32_t seed = 0) { return StrataSampler{{sampledx, sampledy, ndim, seed, ARN_SAMPLER_PARITY}}; }
+    StrataSampler as_intended() const { StrataSampler r = *this; r.s.mode = ARN_SAMPLER_STRATIFIED; return r; } };   // the stratification the reference meant to have (SURVEY A-17)
 
 class Device {                                             // one GPU
 public:

@@ -393,7 +393,7 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
     const Json* js = root.get("sampler");
     float sx, sy, nd;
     if (!js || !json_num(js->get("sampledx"), &sx) || !json_num(js->get("sampledy"), &sy) || !json_num(js->get("ndim"), &nd)) return fs.fail(ARN_E_INVALID, "malformed sampler");
-    sampler->sampledx = (uint32_t)sx; sampler->sampledy = (uint32_t)sy; sampler->ndim = (uint32_t)nd; sampler->seed = 0;
+    sampler->sampledx = (uint32_t)sx; sampler->sampledy = (uint32_t)sy; sampler->ndim = (uint32_t)nd; sampler->seed = 0; sampler->mode = ARN_SAMPLER_PARITY;
     // camera: PerspecCam (filming/perspective.rs:139-260) with its Film (filming/film.rs:38-45)
     const Json* jc = root.get("camera");
     if (!jc) return fs.fail(ARN_E_INVALID, "scene has no camera");

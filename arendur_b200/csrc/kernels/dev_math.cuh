@@ -127,4 +127,33 @@ struct Sampler {
     ARN_DEV float2 next_2d() { float2 r = f2(u01(mix32(k2 + 2 * i2d)), u01(mix32(k2 + 2 * i2d + 1))); i2d++; return r; }
 };
 
+// ---- ARN_SAMPLER_STRATIFIED (include/arn.h): the first `ndim` 1-D / 2-D draws of a sample are placed in the stratum a hash
+// permutation of [0, spp) assigns to that sample — Kensler's permute() ("Correlated Multi-Jittered Sampling", Pixar TM 13-01):
+// cycle walking over the next power of two, 32-bit integer arithmetic only, so the oracle computes the same index.
+ARN_DEV uint32_t hash_permute(uint32_t i, uint32_t l, uint32_t p) {
+    uint32_t w = l - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3fu; i ^= p >> 23; i ^= (i & w) >> 1;
+        i *= 1u | p >> 27; i *= 0x6935fa69u; i ^= (i & w) >> 11; i *= 0x74dcb303u; i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu; i &= w; i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+// stratum index + jitter, kept strictly below the next index (f32 addition may round x + u up to x + 1)
+ARN_DEV float strat_offset(uint32_t x, float u) {
+    const float t = (float)x + u, hi = (float)(x + 1u);
+    return t < hi ? t : __uint_as_float(__float_as_uint(hi) - 1u);
+}
+// pix = px | py << 16, s = the sample's index in the pixel, d = index of the draw within the sample, u = the parity sampler's draw
+ARN_NOINL float strat_1d(uint32_t seed, uint32_t sdx, uint32_t sdy, uint32_t pix, uint32_t s, uint32_t d, float u) {
+    const uint32_t kpix = mix32(mix32(mix32(seed) + (pix & 0xffffu)) + (pix >> 16)), n = sdx * sdy;
+    return strat_offset(hash_permute(s, n, mix32(kpix ^ (0x1D000000u + d))), u) / (float)n;
+}
+ARN_NOINL float2 strat_2d(uint32_t seed, uint32_t sdx, uint32_t sdy, uint32_t pix, uint32_t s, uint32_t d, float2 u) {
+    const uint32_t kpix = mix32(mix32(mix32(seed) + (pix & 0xffffu)) + (pix >> 16));
+    const uint32_t c = hash_permute(s, sdx * sdy, mix32(kpix ^ (0x2D000000u + d)));
+    return f2(strat_offset(c / sdy, u.x) / (float)sdx, strat_offset(c % sdy, u.y) / (float)sdy);
+}
+
 }  // namespace arn

@@ -95,7 +95,11 @@ struct WaveParams {
     const unsigned long long* tile_prefix;  // pixels before tile i (n_tiles + 1 entries)
     uint32_t spp_begin, spp_count;
     uint32_t textured, spp_total;            // image textures present: carry ray differentials, scaled by 1 / spp_total (pt.rs:141-142)
+    uint32_t strat_ndim, sampledx, sampledy; // ARN_SAMPLER_STRATIFIED: the first strat_ndim 1-D / 2-D draws of a sample are stratified (0 = parity sampler)
 };
+// the draw `u` the sampler just returned was its (n - 1)-th of this kind: stratify it if the sampler is in that mode (warp-uniform test)
+#define ARN_STRAT_1D(u, n) do { if (p.strat_ndim && (n) - 1u < p.strat_ndim) (u) = strat_1d(p.seed, p.sampledx, p.sampledy, spix, ssmp, (n) - 1u, (u)); } while (0)
+#define ARN_STRAT_2D(u, n) do { if (p.strat_ndim && (n) - 1u < p.strat_ndim) (u) = strat_2d(p.seed, p.sampledx, p.sampledy, spix, ssmp, (n) - 1u, (u)); } while (0)
 
 // ---- queue append: warp ballots + per-warp shared-memory staging -------------------
 // Each warp compacts the ids it keeps into its own 64-entry staging row in shared memory
@@ -152,9 +156,10 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ 
         uint32_t off = (uint32_t)(pl - p.tile_prefix[lo]);
         uint32_t px = (uint32_t)tr.x + off % (uint32_t)tr.z, py = (uint32_t)tr.y + off / (uint32_t)tr.z;   // row-major in the tile
         Sampler sm; sm.init(p.seed, px, py, s, 0, 0);
-        float2 j = sm.next_2d();
+        const uint32_t spix = px | (py << 16), ssmp = s;
+        float2 j = sm.next_2d(); ARN_STRAT_2D(j, sm.i2d);
         float2 pfilm = f2(j.x + (float)px, j.y + (float)py);
-        float2 plens = sm.next_2d();
+        float2 plens = sm.next_2d(); ARN_STRAT_2D(plens, sm.i2d);
         // PerspecCam::generate_path_differential, main ray
         float3 pview = xform_point(p.raster_view, f3(pfilm.x, pfilm.y, 0.f));
         float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
@@ -362,6 +367,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 uint32_t st = __float_as_uint(d4.w);
                 uint32_t bounces = st & 0xffu; bool spec = ((st >> 8) & 1u) != 0;
                 Sampler sm; sm.init_key(__float_as_uint(o4.w), (st >> 16) & 0xffu, st >> 24);
+                uint32_t spix = 0, ssmp = 0;
+                if (p.strat_ndim && (sm.i1d < p.strat_ndim || sm.i2d < p.strat_ndim)) { spix = pb.pix[pid]; ssmp = pb.smp[pid]; }     // stratified draws are keyed by (pixel, sample)
                 float4 b4 = pb.beta[pid]; float3 beta = f3(b4.x, b4.y, b4.z);
                 uint32_t ref = sc.prims[prim];
                 Surf s; uint32_t mat; SurfTex sx;
@@ -391,9 +398,9 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 uint32_t flags = 0;
                 if (bsdf.n > 0) {                                           // pt.rs:85-91 (have_n(ALL-SPECULAR) > 0 <=> any lobe)
                     // Scene::uniform_sample_one_light (scene.rs:58-66)
-                    float u1 = sm.next();
-                    float2 ulight = sm.next_2d();
-                    float2 uscatter = sm.next_2d();
+                    float u1 = sm.next(); ARN_STRAT_1D(u1, sm.i1d);
+                    float2 ulight = sm.next_2d(); ARN_STRAT_2D(ulight, sm.i2d);
+                    float2 uscatter = sm.next_2d(); ARN_STRAT_2D(uscatter, sm.i2d);
                     if (u1 == 0.f) u1 += ARN_EPS;                            // Distribution1D::search_offset
                     uint32_t lo = 0, hi = sc.n_lights + 1;
                     while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if (sc.light_cdf[mid] < u1) lo = mid + 1; else hi = mid; }
@@ -470,7 +477,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                 // sample the BSDF for the next direction (pt.rs:92-107)
                 float3 next_o = f3(0.f, 0.f, 0.f), next_d = next_o;
                 float3 wo = -raydir;
-                Sampled bs = bsdf_sample_k<DIFFUSE, LOBES>(bsdf, wo, sm.next_2d());
+                float2 ubsdf = sm.next_2d(); ARN_STRAT_2D(ubsdf, sm.i2d);
+                Sampled bs = bsdf_sample_k<DIFFUSE, LOBES>(bsdf, wo, ubsdf);
                 spec = (bs.type & BXDF_SPECULAR) != 0;
                 alive = !(is_black(bs.f) || bs.pdf == 0.f);
                 if (alive) {
@@ -489,7 +497,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
                     float y = 0.212671f * beta.x + 0.715160f * beta.y + 0.072169f * beta.z;
                     if (y < p.rr_threshold && bounces >= p.min_depth) {
                         float qq = fmaxf(p.rr_threshold, 0.05f);
-                        if (sm.next() < qq) alive = false;
+                        float urr = sm.next(); ARN_STRAT_1D(urr, sm.i1d);
+                        if (urr < qq) alive = false;
                         else beta = beta / (1.f - qq);
                     }
                 }

@@ -214,9 +214,18 @@ typedef struct arn_film {
 /* Sampler: `StrataSampler{sampledx, sampledy, ndim}` (sample/strata.rs:25-31) gives the
  * sample count; the draws themselves come from the counter-based ParitySampler
  * (DESIGN.md "Sampler"). */
+#define ARN_SAMPLER_PARITY     0u   /* every draw = hash(seed, pixel, sample, stream, draw index): what the reference's sampler
+                                      amounts to, draw for draw, through its never-reset dimension counter (SURVEY A-17)   */
+#define ARN_SAMPLER_STRATIFIED 1u   /* the sampler AS INTENDED (not reference behaviour): the dimension counters
+                                      restart with every sample; the first `ndim` 1-D draws of sample s are
+                                      (perm_d(s) + u) / spp (the sum kept below perm_d(s) + 1), the first `ndim` 2-D draws fall into cell c = perm_d(s) of the
+                                      sampledx x sampledy grid, x-major like strata.rs:67-80: ((c / sampledy + u) / sampledx,
+                                      (c % sampledy + u') / sampledy); perm_d = a hash permutation of [0, spp) keyed by
+                                      (seed, pixel, dimension); u, u' and every later draw are the parity sampler's        */
 typedef struct arn_sampler {
     uint32_t sampledx, sampledy, ndim;
     uint32_t seed;
+    uint32_t mode;                  /* ARN_SAMPLER_*                                                                        */
 } arn_sampler;
 
 /* `PTRenderer` constants (renderer/pt.rs:37-52): rr_threshold = 0.05,

@@ -211,6 +211,15 @@ int arn_oracle_sampler_draws(uint32_t seed, uint32_t px, uint32_t py, uint32_t s
     for (uint32_t i = 0; i < n2; i++) { V2 v = sp.next_2d(); out[n1 + 2*i] = v.x; out[n1 + 2*i + 1] = v.y; }
     return ARN_OK;
 }
+// the same for a full sampler description (ARN_SAMPLER_STRATIFIED: sample s of sampledx * sampledy)
+int arn_oracle_sampler_draws2(const arn_sampler* smp, uint32_t px, uint32_t py, uint32_t s, uint32_t n1, uint32_t n2, float* out) {
+    ParitySampler sp; sp.seed = smp->seed; sp.spp = smp->sampledx * smp->sampledy;
+    sp.mode = smp->mode; sp.sampledx = smp->sampledx; sp.sampledy = smp->sampledy; sp.ndim = smp->ndim;
+    sp.start_pixel(px, py); sp.set_sample_index(s);
+    for (uint32_t i = 0; i < n1; i++) out[i] = sp.next();
+    for (uint32_t i = 0; i < n2; i++) { V2 v = sp.next_2d(); out[n1 + 2*i] = v.x; out[n1 + 2*i + 1] = v.y; }
+    return ARN_OK;
+}
 float arn_oracle_lanczos(float dx, float dy) { return lanczos_evaluate(v2(dx, dy), 1.f / 3.f); }
 // Filter::evaluate_unsafe of the film's filter at a signed offset (sample/filters.rs)
 float arn_oracle_filter(const arn_film* film, float dx, float dy) { return filter_evaluate(*film, v2(dx, dy)); }

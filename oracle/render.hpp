@@ -426,6 +426,7 @@ inline bool render_pt(const Scene& s, const arn_camera& cam, const arn_film& fil
             const long tw = tile.bounding.x1 - tile.bounding.x0, thh = tile.bounding.y1 - tile.bounding.y0;
             const long ncx = std::min<long>(sub, tw), ncy = std::min<long>(sub, thh), sdx = ncx > 0 ? tw / ncx : 1, sdy = ncy > 0 ? thh / ncy : 1;
             ParitySampler sampler; sampler.seed = smp.seed; sampler.spp = spp;
+            sampler.mode = smp.mode; sampler.sampledx = smp.sampledx; sampler.sampledy = smp.sampledy; sampler.ndim = smp.ndim;
             for (long y = tile.bounding.y0; y < tile.bounding.y1; y++) for (long x = tile.bounding.x0; x < tile.bounding.x1; x++) {
                 if (sub > 1) {      // cell (jx, jy) of tile (ix, iy) -> rank (ix*sub + jx + iy*sub + jy) % world
                     long jx = std::min((x - tile.bounding.x0) / sdx, ncx - 1), jy = std::min((y - tile.bounding.y0) / sdy, ncy - 1);

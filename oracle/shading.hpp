@@ -32,17 +32,52 @@ inline uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16; return h;
 }
 inline Float u01(uint32_t h) { return (Float)(h >> 8) * (1.0f / 16777216.0f); }
+// Hash permutation of [0, l): Kensler, "Correlated Multi-Jittered Sampling" (Pixar TM 13-01), permute(): cycle walking over the
+// next power of two; pure 32-bit integer arithmetic, so the device computes the same index.
+inline uint32_t hash_permute(uint32_t i, uint32_t l, uint32_t p) {
+    uint32_t w = l - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3fu; i ^= p >> 23; i ^= (i & w) >> 1;
+        i *= 1u | p >> 27; i *= 0x6935fa69u; i ^= (i & w) >> 11; i *= 0x74dcb303u; i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu; i &= w; i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+// stratum index + jitter, kept strictly below the next index (f32 addition may round x + u up to x + 1 when u is within half an ulp(x) of 1)
+inline Float strat_offset(uint32_t x, Float u) {
+    Float t = (Float)x + u, hi = (Float)(x + 1u);
+    return t < hi ? t : from_bits(to_bits(hi) - 1u);
+}
 struct ParitySampler {
     uint32_t seed = 0, spp = 1;
     uint32_t px = 0, py = 0, isample = 0, k1 = 0, k2 = 0, i1d = 0, i2d = 0;
+    uint32_t mode = 0, sampledx = 1, sampledy = 1, ndim = 0, kpix = 0;     // ARN_SAMPLER_STRATIFIED (include/arn.h): spp = sampledx * sampledy
     void rekey() {
-        uint32_t key = mix32(mix32(mix32(mix32(seed) + px) + py) + isample);
+        kpix = mix32(mix32(mix32(seed) + px) + py);
+        uint32_t key = mix32(kpix + isample);
         k1 = mix32(key ^ 0xA511E9B3u); k2 = mix32(key ^ 0x63D83595u); i1d = 0; i2d = 0;
     }
     void start_pixel(uint32_t x, uint32_t y) { px = x; py = y; isample = 0; rekey(); }
     void set_sample_index(uint32_t s) { isample = s; rekey(); }
-    Float next() { return u01(mix32(k1 + (i1d++))); }
-    V2 next_2d() { V2 r = v2(u01(mix32(k2 + 2 * i2d)), u01(mix32(k2 + 2 * i2d + 1))); i2d++; return r; }
+    Float next() {
+        const uint32_t d = i1d;
+        Float u = u01(mix32(k1 + (i1d++)));
+        if (mode == 1u && d < ndim) {
+            const uint32_t n = sampledx * sampledy;
+            u = strat_offset(hash_permute(isample, n, mix32(kpix ^ (0x1D000000u + d))), u) / (Float)n;
+        }
+        return u;
+    }
+    V2 next_2d() {
+        const uint32_t d = i2d;
+        V2 r = v2(u01(mix32(k2 + 2 * i2d)), u01(mix32(k2 + 2 * i2d + 1))); i2d++;
+        if (mode == 1u && d < ndim) {
+            const uint32_t c = hash_permute(isample, sampledx * sampledy, mix32(kpix ^ (0x2D000000u + d)));
+            r = v2(strat_offset(c / sampledy, r.x) / (Float)sampledx, strat_offset(c % sampledy, r.y) / (Float)sampledy);
+        }
+        return r;
+    }
     bool next_sample() { isample++; if (isample >= spp) return false; rekey(); return true; }
 };
 

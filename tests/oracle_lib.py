@@ -67,6 +67,7 @@ def load():
     lib.arn_oracle_bbox2i.argtypes = [C.c_int, vp, vp, vp]
     lib.arn_oracle_bbox2f_lerp.argtypes = [vp, C.c_float, C.c_float, vp]
     lib.arn_oracle_sampler_draws.argtypes = [C.c_uint32] * 6 + [vp]
+    lib.arn_oracle_sampler_draws2.argtypes = [C.POINTER(L.Sampler)] + [C.c_uint32] * 5 + [vp]
     lib.arn_oracle_lanczos.restype = C.c_float
     lib.arn_oracle_lanczos.argtypes = [C.c_float, C.c_float]
     lib.arn_oracle_roughness_to_alpha.restype = C.c_float
@@ -314,9 +315,9 @@ def make_film(res_x, res_y):
     return f
 
 
-def make_sampler(sx, sy, ndim=8, seed=0):
+def make_sampler(sx, sy, ndim=8, seed=0, mode=0):
     s = L.Sampler()
-    s.sampledx, s.sampledy, s.ndim, s.seed = sx, sy, ndim, seed
+    s.sampledx, s.sampledy, s.ndim, s.seed, s.mode = sx, sy, ndim, seed, mode
     return s
 
 

@@ -32,6 +32,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.Ray) == 28
     assert ctypes.sizeof(L.Hit) == 8
     assert ctypes.sizeof(L.Mesh) == 16
+    assert ctypes.sizeof(L.Sampler) == 20
 
 
 def test_version_and_no_cpu_fallback():

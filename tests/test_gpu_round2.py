@@ -534,3 +534,35 @@ def test_random_film_configurations_match_the_oracle(ctx, seed):
     scale = max(float(np.abs(of).max()), 1e-6)
     assert np.abs(gf - of).max() <= 1e-5 * scale, f"{cfg}: max diff {np.abs(gf - of).max()} of {scale}"
     sc.close(); osc.close()
+
+
+@pytest.mark.parametrize("case", ["cornell", "zoo_lens", "random3", "textured104"])
+def test_stratified_sampler_mode_is_bit_exact(ctx, case):
+    """ARN_SAMPLER_STRATIFIED (the reference's sampler as intended; include/arn.h): the device's stratified draws — film jitter and lens
+    in k_generate, light choice / light / scatter / BSDF / roulette draws in k_shade — are the oracle's, so every camera sample's radiance
+    still is, bit for bit; and the mode does change the picture's samples (it is not silently the parity sampler)."""
+    if case == "cornell":
+        hs, cam, film, smp, prm = scenes.cornell_scene(64, 48, 4, 4)
+    elif case == "zoo_lens":
+        import test_gpu_parity as P
+        hs, cam, film, smp, prm = P._material_zoo((0.15, 7.5))
+    elif case == "random3":
+        hs, cam, film, smp, prm = _random_scene(3)
+    else:
+        hs, cam, film, smp, prm = _random_scene(104, textured=True)
+    strat = api.make_sampler(smp.sampledx, smp.sampledy, smp.ndim, smp.seed, mode=L.ARN_SAMPLER_STRATIFIED)
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    gf, grad, st = sc.render_pt_samples(cam, film, strat, prm)
+    of, orad = osc.render_pt_samples(cam, film, strat, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1)
+    assert same.all(), f"{(~same).sum()} of {same.size} samples differ, first {np.argwhere(~same)[:3].tolist()}"
+    _, ost, _ = osc.render_pt(cam, film, strat, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
+    assert np.abs(gf - of).max() <= 2e-5 * max(float(np.abs(of).max()), 1e-6)
+    _, prad, _ = sc.render_pt_samples(cam, film, smp, prm)
+    assert not np.array_equal(prad, grad)
+    # the film jitter is stratified: per pixel the spp film positions fall into distinct cells of the sampledx x sampledy grid
+    with pytest.raises(api.ArnError):
+        sc.render_pt(cam, film, api.make_sampler(2, 2, 8, 0, mode=7), prm)
+    sc.close(); osc.close()

@@ -118,3 +118,41 @@ def test_fast_transcendentals_host_sweep(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_cr_math.cpp")])
     r = subprocess.run([exe, "257"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_stratified_sampler_mode_stratifies_every_dimension_it_covers():
+    """ARN_SAMPLER_STRATIFIED (include/arn.h; the reference's sampler as intended): over the spp samples of a
+    pixel every covered 1-D dimension visits each of the spp strata once, every covered 2-D dimension each cell of the
+    sampledx x sampledy grid once; later dimensions and the whole parity mode are the plain hash draws."""
+    import ctypes as C
+    import numpy as np
+    import oracle_lib as O
+    from arendur_b200 import _lib as L
+    lib = O.load()
+    for sx, sy, ndim in ((4, 4, 8), (3, 5, 2), (1, 7, 4), (32, 32, 3)):
+        n = sx * sy
+        smp = O.make_sampler(sx, sy, ndim, seed=11, mode=L.ARN_SAMPLER_STRATIFIED)
+        par = O.make_sampler(sx, sy, ndim, seed=11, mode=L.ARN_SAMPLER_PARITY)
+        n1, n2 = ndim + 3, ndim + 3
+        for (px, py) in ((0, 0), (17, 5)):
+            draws = np.zeros((n, n1 + 2 * n2), np.float32); pdraws = np.zeros_like(draws); old = np.zeros_like(draws)
+            for s in range(n):
+                lib.arn_oracle_sampler_draws2(C.byref(smp), px, py, s, n1, n2, draws[s].ctypes.data)
+                lib.arn_oracle_sampler_draws2(C.byref(par), px, py, s, n1, n2, pdraws[s].ctypes.data)
+                lib.arn_oracle_sampler_draws(11, px, py, s, n1, n2, old[s].ctypes.data)
+            assert np.array_equal(pdraws, old)                                       # mode 0 is the sampler every parity test pins
+            assert ((draws >= 0) & (draws < 1)).all()
+            for d in range(ndim):
+                strata = np.floor(draws[:, d].astype(np.float64) * n).astype(int)
+                assert sorted(strata) == list(range(n)), (sx, sy, d)
+                x, y = draws[:, n1 + 2 * d].astype(np.float64), draws[:, n1 + 2 * d + 1].astype(np.float64)
+                cells = np.floor(x * sx).astype(int) * sy + np.floor(y * sy).astype(int)
+                assert sorted(cells) == list(range(n)), (sx, sy, d)
+            assert np.array_equal(draws[:, ndim:n1], pdraws[:, ndim:n1])              # beyond ndim: the raw draws
+            assert np.array_equal(draws[:, n1 + 2 * ndim:], pdraws[:, n1 + 2 * ndim:])
+            if n > 1:
+                assert not np.array_equal(draws[:, :ndim], pdraws[:, :ndim])
+        # different pixels and dimensions get different permutations
+        a = np.zeros(n1 + 2 * n2, np.float32); b = np.zeros_like(a)
+        lib.arn_oracle_sampler_draws2(C.byref(smp), 3, 4, 0, n1, n2, a.ctypes.data); lib.arn_oracle_sampler_draws2(C.byref(smp), 4, 3, 0, n1, n2, b.ctypes.data)
+        assert not np.array_equal(a, b)
