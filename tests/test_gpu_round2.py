@@ -200,6 +200,11 @@ def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
         if rng.random() < 0.5:
             a = rng.uniform(0, 6.28); t[0, 0], t[0, 1], t[1, 0], t[1, 1] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
         h.add_sphere(rad, -rad * float(rng.uniform(0.3, 1)), rad * float(rng.uniform(0.3, 1)), float(rng.uniform(2, 6.2832)), mat, transform=t)
+    for _ in range(4):                                   # general affine instances (rotation x non-uniform scale): accepted hits rewrite the ray
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        t = np.eye(4, dtype=np.float32); t[:3, :3] = (q * rng.uniform(0.5, 2.0, 3)).astype(np.float32); t[3, :3] = rng.uniform(-1, 1, 3) * S
+        rad = float(rng.uniform(0.1, 0.4)) * float(S)
+        h.add_sphere(rad, -rad, rad * float(rng.uniform(0.3, 1)), float(rng.uniform(3, 6.2832)), mat, transform=t)
     d = h.build()
 
     def rays_of(o, dvec, tmax=np.inf):
@@ -315,7 +320,7 @@ def _random_pyramid(rng, channels, scale):
     return lv
 
 
-def _random_scene(seed, textured=False):
+def _random_scene(seed, textured=False, wild=False):
     """A random scene for the shading fuzz: a closed room of random quads, a soup of triangles with and without shading normals,
     random materials of all four families with parameters out to the clamps, sphere emitters (clipped / transformed) and a random
     set of delta / distant lights, a random camera (perspective with or without lens, or orthographic).  `textured`: random image
@@ -378,6 +383,16 @@ def _random_scene(seed, textured=False):
     for k in range(2):                                    # non-emissive spheres
         rad = float(rng.uniform(0.3, 0.8)); t = np.eye(4, dtype=np.float32); t[3, :3] = rng.uniform(-2, 2, 3)
         hs.add_sphere(rad, -rad, rad, 6.2831855, pick(), transform=t)
+    if wild:                                              # general affine instances: rotation x non-uniform scale, clipped, some emissive
+        rw = np.random.default_rng(seed + 77777)
+        for k in range(4):
+            q, _ = np.linalg.qr(rw.normal(size=(3, 3)))
+            m = (q * rw.uniform(0.5, 1.8, 3)).astype(np.float32)
+            t = np.eye(4, dtype=np.float32); t[:3, :3] = m; t[3, :3] = rw.uniform(-2.2, 2.2, 3)
+            rad = float(rw.uniform(0.25, 0.6)); full = rw.random() < 0.5
+            hs.add_sphere(rad, -rad if full else -rad * float(rw.uniform(0.2, 0.9)), rad if full else rad * float(rw.uniform(0.2, 0.9)),
+                          6.2831855 if full else float(rw.uniform(2.0, 6.0)), pick(),
+                          emission=tuple(float(x) for x in rw.uniform(2, 20, 3)) if k < 2 else None, transform=t)
     if rng.random() < 0.7:
         hs.add_light(api.point_light(rng.uniform(-2, 2, 3), rng.uniform(1, 20, 3)))
     if rng.random() < 0.7:
@@ -565,4 +580,21 @@ def test_stratified_sampler_mode_is_bit_exact(ctx, case):
     # the film jitter is stratified: per pixel the spp film positions fall into distinct cells of the sampledx x sampledy grid
     with pytest.raises(api.ArnError):
         sc.render_pt(cam, film, api.make_sampler(2, 2, 8, 0, mode=7), prm)
+    sc.close(); osc.close()
+
+
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_random_scenes_with_affine_sphere_instances_are_bit_exact(ctx, seed):
+    """The shading fuzz with general affine sphere instances (rotation x non-uniform scale, clipped, two of them emissive): every
+    accepted hit on one of them rewrites the traversal ray (bvh.rs:108-113), their light samples and pdfs live in the local frame
+    (transformed.rs:120-146).  Per-sample radiance and ray counts equal the oracle's."""
+    hs, cam, film, smp, prm = _random_scene(seed, textured=(seed % 3 == 0), wild=True)
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    same = np.all(grad.view(np.uint32) == orad.view(np.uint32), axis=-1) | (np.isnan(grad).any(-1) & np.isnan(orad).any(-1))
+    assert same.all(), f"seed {seed}: {(~same).sum()} of {same.size} samples differ, first {np.argwhere(~same)[:3].tolist()}: gpu {grad[~same][:2]} oracle {orad[~same][:2]}"
+    _, ost, _ = osc.render_pt(cam, film, smp, prm)
+    assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
     sc.close(); osc.close()
