@@ -50,9 +50,13 @@ inline void drop_row(const float col[4], int row, float out[3]) { int k = 0; for
 inline float determinant(const Mat4& m) {
     float acc = 0.f;
     for (int col = 0; col < 4; col++) {
-        // minor of element (col, row 0): the other three columns without row 0
-        float cols[3][3]; int k = 0;
-        for (int c2 = 0; c2 < 4; c2++) if (c2 != col) detail::drop_row(m.c[c2], 0, cols[k++]);
+        // minor of element (col, row 0).  cgmath builds it as Matrix3::new(self[a][1], self[b][1], self[c][1], self[a][2], ...) for the
+        // other columns a < b < c: the TRANSPOSED minor (column j = row j + 1 of the three columns).  Same determinant, but not
+        // the same roundings — and inv_det scales every entry of the inverse, hence every transformed normal.
+        int other[3], k = 0;
+        for (int c2 = 0; c2 < 4; c2++) if (c2 != col) other[k++] = c2;
+        float cols[3][3];
+        for (int j = 0; j < 3; j++) for (int q = 0; q < 3; q++) cols[j][q] = m.c[other[q]][j + 1];
         float d = detail::det3(cols[0], cols[1], cols[2]);
         float term = m.c[col][0] * d;
         if (col == 0) acc = term; else if (col & 1) acc = acc - term; else acc = acc + term;

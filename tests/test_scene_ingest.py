@@ -228,3 +228,38 @@ def test_oracle_only_flattening_equals_the_product_host_layer():
     assert d.light_func_integral == p.light_func_integral
     assert bytes(o.camera(64, 48)) == bytes(cam)
     assert o.max_depth() == prm.max_depth
+
+
+def test_random_transforms_and_cameras_match_the_oracle():
+    """Host-layer fuzz: `from_model_transformed` under random affine and projective matrices (rotation x non-uniform scale x shear,
+    translation, a non-trivial w row) and `PerspecCam::new` / `OrthoCam::new` under random view matrices, screens, fovs, lenses —
+    byte-identical to the oracle's restatement."""
+    rng = np.random.default_rng(2024)
+    for k in range(24):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        t = np.eye(4, dtype=np.float32)
+        t[:3, :3] = (q * rng.uniform(0.2, 4.0, 3)) @ (np.eye(3) + np.triu(rng.normal(scale=0.3, size=(3, 3)), 1))
+        t[3, :3] = rng.uniform(-5, 5, 3)
+        if k % 3 == 0:
+            t[:3, 3] = rng.uniform(-0.05, 0.05, 3); t[3, 3] = rng.uniform(0.5, 2.0)          # projective (cb.json's own matrix is, quirk A-12)
+        n = 64
+        pos = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+        nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+        idx = rng.integers(0, n, 3 * 20).astype(np.uint32)
+        hs = api.HostScene()
+        m = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+        hs.add_mesh(pos, idx, m, normals=nrm, transform=t)
+        a = _desc_arrays(hs.build())
+        op, on = np.zeros_like(pos), np.zeros_like(nrm)
+        O.load().arn_oracle_mesh_transform(O._p(np.ascontiguousarray(t, np.float32)), n, O._p(pos), O._p(nrm), O._p(op), O._p(on))
+        assert np.array_equal(a["positions"].view(np.uint32), op.view(np.uint32)), k
+        assert np.array_equal(a["normals"].view(np.uint32), on.view(np.uint32)), k
+        # cameras
+        view = np.eye(4, dtype=np.float32); view[:3, :3] = q.astype(np.float32); view[3, :3] = rng.uniform(-3, 3, 3)
+        w, h = int(rng.integers(8, 4000)), int(rng.integers(8, 2200))
+        x0, y0 = float(rng.uniform(-2, -0.1)), float(rng.uniform(-2, -0.1))
+        screen = (x0, y0, float(rng.uniform(0.1, 2)), float(rng.uniform(0.1, 2)))
+        fov = float(rng.uniform(0.2, 2.8)); znear = float(rng.uniform(0.01, 1)); zfar = znear + float(rng.uniform(1, 1000))
+        lens = (float(rng.uniform(0.01, 0.5)), float(rng.uniform(0.5, 20))) if k % 2 else None
+        assert bytes(api.make_camera(view, screen, znear, zfar, fov, w, h, lens=lens)) == bytes(O.camera_make(view, screen, znear, zfar, fov, w, h, lens=lens)), k
+        assert bytes(api.make_ortho_camera(view, screen, znear, zfar, w, h, lens=lens)) == bytes(O.ortho_camera_make(view, screen, znear, zfar, w, h, lens=lens)), k
