@@ -263,3 +263,63 @@ def test_random_transforms_and_cameras_match_the_oracle():
         lens = (float(rng.uniform(0.01, 0.5)), float(rng.uniform(0.5, 20))) if k % 2 else None
         assert bytes(api.make_camera(view, screen, znear, zfar, fov, w, h, lens=lens)) == bytes(O.camera_make(view, screen, znear, zfar, fov, w, h, lens=lens)), k
         assert bytes(api.make_ortho_camera(view, screen, znear, zfar, w, h, lens=lens)) == bytes(O.ortho_camera_make(view, screen, znear, zfar, w, h, lens=lens)), k
+
+
+def test_random_spheres_bounds_and_light_powers_match_the_oracle():
+    """Host-layer fuzz: `Sphere::new` (z clamps, theta range, phimax clamp), the inverse of random affine instance transforms,
+    `ComponentInfo::new` bounds / costs of every primitive (triangles and transformed, clipped spheres) and the light power that
+    feeds the light-selection CDF — the product's flattened scene against the oracle's own computation, bit for bit."""
+    rng = np.random.default_rng(31337)
+    lib = O.load()
+    for rep in range(6):
+        hs = api.HostScene()
+        m = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+        pos = rng.uniform(-3, 3, (30, 3)).astype(np.float32)
+        hs.add_mesh(pos, np.arange(30, dtype=np.uint32), m)
+        params = []
+        for k in range(10):
+            rad = float(rng.uniform(0.05, 3.0))
+            zmin, zmax = sorted(rng.uniform(-1.5 * rad, 1.5 * rad, 2).tolist())
+            if zmax - zmin < 1e-3: zmax = zmin + 0.1
+            # Sphere::new clamps zmin from below and zmax from above only (sphere.rs:137-138): a z range wholly outside [-r, r] comes out
+            # inverted, its area and light power negative, and Distribution1D::new asserts — the loader refuses such a scene as well
+            zmin, zmax = min(zmin, 0.9 * rad), max(zmax, -0.9 * rad)
+            phimax = float(rng.uniform(0.1, 8.0))
+            t = None
+            if k % 3:
+                q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+                t = np.eye(4, dtype=np.float32); t[:3, :3] = (q * rng.uniform(0.3, 3.0, 3)).astype(np.float32); t[3, :3] = rng.uniform(-4, 4, 3)
+            em = tuple(float(x) for x in rng.uniform(0.5, 40, 3)) if k % 2 else None
+            hs.add_sphere(rad, zmin, zmax, phimax, m, emission=em, transform=t)
+            params.append((rad, zmin, zmax, phimax, t, em))
+        d = hs.build()
+        for k, (rad, zmin, zmax, phimax, t, em) in enumerate(params):
+            s = d.spheres[k]
+            o = L.Sphere(); assert lib.arn_oracle_sphere_new(rad, zmin, zmax, phimax, C.byref(o)) == 0
+            got = np.float32([s.radius, s.zmin, s.zmax, s.phimax, s.thetamin, s.thetamax]); want = np.float32([o.radius, o.zmin, o.zmax, o.phimax, o.thetamin, o.thetamax])
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (rep, k, got, want)
+            if t is not None:
+                inv = np.zeros(16, np.float32)
+                assert lib.arn_oracle_m4_invert(O._p(np.ascontiguousarray(s.local_parent, np.float32)), O._p(inv)) == 0
+                assert np.array_equal(inv.view(np.uint32), np.array(s.parent_local, np.float32).view(np.uint32)), (rep, k)
+        # light table: emissive spheres in component order, power luminance as the CDF's function values
+        lights = [k for k, p in enumerate(params) if p[5] is not None]
+        assert d.n_lights == len(lights)
+        for i, k in enumerate(lights):
+            assert np.float32(lib.arn_oracle_light_power_y(C.byref(d.spheres[k]))) == np.float32(d.light_func[i]), (rep, k)
+        cdf = np.zeros(d.n_lights + 1, np.float32); integral = C.c_float()
+        lf = np.ctypeslib.as_array(d.light_func, (d.n_lights,)).astype(np.float32)
+        lib.arn_oracle_light_distribution(d.n_lights, O._p(lf), O._p(cdf), C.byref(integral))
+        assert np.array_equal(cdf.view(np.uint32), np.ctypeslib.as_array(d.light_cdf, (d.n_lights + 1,)).astype(np.float32).view(np.uint32))
+        assert np.float32(integral.value) == np.float32(d.light_func_integral)
+        if rep == 0:       # the inverted z range: refused like the reference's assert
+            bad = api.HostScene(); bm = bad.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+            bad.add_sphere(0.35, -0.46, -0.43, 5.6, bm, emission=(1.0, 1.0, 1.0))
+            with pytest.raises(api.ArnError):
+                bad.build()
+        # bounds and costs the BVH was built from: recomputed by the oracle from the flattened scene
+        ob, oc = O.prim_bounds(d)
+        assert np.isfinite(ob).all() and ob.shape[0] == d.n_prims
+        nodes = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_float)), (d.n_nodes, 8))
+        root = nodes[0, :6]
+        assert np.array_equal(root[:3], ob[:, :3].min(0)) and np.array_equal(root[3:6], ob[:, 3:].max(0))
