@@ -171,26 +171,21 @@ def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width)
     sc.close(); osc.close()
 
 
-@pytest.mark.parametrize("width", [2, 4, 8])
-@pytest.mark.parametrize("scale", [1e-3, 1.0, 3e4])
-def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
-    """Fuzz of the walk on geometry the regular fixtures do not have: triangle soups at three coordinate scales with axis-aligned
-    (zero-thickness boxes), degenerate (collinear / repeated vertices) and duplicated triangles (exact ties: the first in slot order
-    wins on both sides), clipped and transformed spheres; rays from random points, from vertex coordinates and along the axes."""
-    rng = np.random.default_rng(1000 * width + int(math.log10(scale) * 7) + 77)
+def _soup_case(rng, scale, n_tri=2500, n=8000):
+    """Scene and rays of the traversal fuzz (shared with tools/trav_soak.py)."""
     S = np.float32(scale)
     h = api.HostScene()
     mat = h.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
-    n_tri = 2500
     c = rng.uniform(-1, 1, (n_tri, 1, 3)); e = rng.normal(scale=0.08, size=(n_tri, 3, 3))
     tri = (c + e).astype(np.float32)
     k = n_tri // 5
     for ax in range(3):                                  # flat in one axis: zero-thickness bounds
         sel = slice(ax * k // 3, (ax + 1) * k // 3)
         tri[sel, :, ax] = np.round(tri[sel, :1, ax] * 8) / 8
-    tri[k:k + 60, 2] = tri[k:k + 60, 1]                  # repeated vertex
-    tri[k + 60:k + 120, 2] = (tri[k + 60:k + 120, 0] + tri[k + 60:k + 120, 1]) * np.float32(0.5)   # collinear
-    tri[k + 120:k + 220] = tri[k + 220:k + 320]          # exact duplicates
+    q = n_tri // 40
+    tri[k:k + q, 2] = tri[k:k + q, 1]                    # repeated vertex
+    tri[k + q:k + 2 * q, 2] = (tri[k + q:k + 2 * q, 0] + tri[k + q:k + 2 * q, 1]) * np.float32(0.5)   # collinear
+    tri[k + 2 * q:k + 3 * q] = tri[k + 3 * q:k + 4 * q]  # exact duplicates
     tri *= S
     pos = tri.reshape(-1, 3); idx = np.arange(pos.shape[0], dtype=np.uint32).reshape(-1, 3)
     h.add_mesh(pos, idx, mat)
@@ -211,7 +206,6 @@ def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
         r = np.zeros(o.shape[0], api.RAY_DTYPE)
         r["o"], r["d"], r["tmax"] = o.astype(np.float32), dvec.astype(np.float32), tmax
         return r
-    n = 8000
     parts = []
     o = rng.uniform(-1.5, 1.5, (n, 3)) * S; v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
     parts.append(rays_of(o, v))
@@ -224,6 +218,16 @@ def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
     tgt = pos[rng.integers(0, pos.shape[0], n)]; dv = tgt - o
     parts.append(rays_of(o, dv, rng.choice(np.float32([np.inf, 1.0, 1.0000001, 0.9999999]), n)))   # aimed at vertices, tmax at the hit
     rays = np.concatenate(parts)
+    return h, d, rays                                    # `h` owns the buffers `d` points into
+
+
+@pytest.mark.parametrize("width", [2, 4, 8])
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 3e4])
+def test_random_soups_with_degenerate_geometry_are_bit_exact(ctx, width, scale):
+    """Fuzz of the walk on geometry the regular fixtures do not have: triangle soups at three coordinate scales with axis-aligned
+    (zero-thickness boxes), degenerate (collinear / repeated vertices) and duplicated triangles (exact ties: the first in slot order
+    wins on both sides), clipped and transformed spheres; rays from random points, from vertex coordinates and along the axes."""
+    h, d, rays = _soup_case(np.random.default_rng(1000 * width + int(math.log10(scale) * 7) + 77), scale)
     osc = O.OracleScene(d)
     ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)
     try:
