@@ -548,7 +548,7 @@ def test_random_film_configurations_match_the_oracle(ctx, seed):
         gf, st = sc.render_pt(cam, film, smp, prm)
     finally:
         ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0)
-    assert st.camera_rays == ost.camera_rays > 0, cfg
+    assert st.camera_rays == ost.camera_rays, cfg                 # 0 when the rank owns no tile of a coarse grid: an empty film on both sides
     assert gf.shape == of.shape and np.isfinite(gf).all(), cfg
     scale = max(float(np.abs(of).max()), 1e-6)
     assert np.abs(gf - of).max() <= 1e-5 * scale, f"{cfg}: max diff {np.abs(gf - of).max()} of {scale}"
