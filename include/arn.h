@@ -401,7 +401,7 @@ void* arn_ctx_stream(arn_ctx* ctx);
  * both this library and the oracle use.  mismatches5 = {sin, cos, exp, log, pow}; all must be 0. */
 int arn_selftest_math(arn_ctx* ctx, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5);
 
-/* Diagnostic: the BSDF of material `m` (Material::compute_scattering with constant textures, material/*.rs) at a fixed local
+/* Diagnostic: the BSDF of material `m` (Material::compute_scattering with constant textures, material/{matte,plastic,glass,translucent}.rs) at a fixed local
  * frame (dpdu = x, shading normal = geometric normal = z; or, with frame9 != NULL, dpdu / shading normal / geometric normal per probe),
  * for n host-side triples (wo[3], u[2], wi[3]):
  * out[12 i ..] = evaluate_sampled(wo, u, ALL) -> f(3), wi(3), pdf, type;  evaluate(wo, wi, ALL)(3);  pdf(wo, wi, ALL)
