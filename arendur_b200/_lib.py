@@ -120,7 +120,7 @@ ARN_H_SYMBOLS = [
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
-    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_hscene_add_texture", "arn_spot_light_make", "arn_point_light_make",
+    "arn_hscene_add_mesh", "arn_hscene_add_sphere", "arn_hscene_add_light", "arn_hscene_add_texture", "arn_hscene_add_texture_file", "arn_spot_light_make", "arn_point_light_make",
     "arn_distant_light_make", "arn_hscene_load_obj", "arn_hscene_load_json",
     "arn_hscene_build", "arn_hscene_build_gpu", "arn_hscene_desc", "arn_camera_make", "arn_ortho_camera_make", "arn_save_png",
 ]
@@ -175,6 +175,7 @@ def load():
         "arn_hscene_add_sphere": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, vp, vp]),
         "arn_hscene_add_light": (C.c_int, [vp, C.POINTER(AnalyticLight)]),
         "arn_hscene_add_texture": (C.c_int, [vp, C.POINTER(Texture), vp, C.c_uint64]),
+        "arn_hscene_add_texture_file": (C.c_int, [vp, C.c_char_p, C.POINTER(Texture), C.c_int, C.c_float, vp]),
         "arn_spot_light_make": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.POINTER(AnalyticLight)]),
         "arn_point_light_make": (C.c_int, [vp, vp, C.POINTER(AnalyticLight)]),
         "arn_distant_light_make": (C.c_int, [vp, vp, C.c_float, C.POINTER(AnalyticLight)]),

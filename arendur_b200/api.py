@@ -153,6 +153,17 @@ class HostScene:
         flat = np.ascontiguousarray(np.concatenate([a.reshape(-1) for a in lv]), dtype=np.float32)
         return self._check(self.lib.arn_hscene_add_texture(self.h, C.byref(t), _ptr(flat), flat.size))
 
+    def add_texture_file(self, path, channels=3, trilinear=False, max_aniso=16.0, wrapping=L.ARN_WRAP_REPEAT, gamma=False, scale=1.0,
+                         scaling=(1.0, 1.0), shifting=(0.0, 0.0)):
+        """An ImageTexture from a PNG file: MipMap::new restated (decode, Lanczos3 pyramid, convert_in) — defaults are load_obj's.
+        Returns (id, mean) with mean = MipMap::mean."""
+        t = L.Texture()
+        t.channels, t.trilinear, t.wrapping, t.max_aniso = channels, int(bool(trilinear)), wrapping, max_aniso
+        t.scale_u, t.scale_v = scaling; t.shift_u, t.shift_v = shifting
+        mean = np.zeros(3, np.float32)
+        tid = self._check(self.lib.arn_hscene_add_texture_file(self.h, str(path).encode(), C.byref(t), int(bool(gamma)), scale, mean.ctypes.data))
+        return tid, mean[:channels].copy()
+
     def add_light(self, light):
         """`lights.push(light.to_arc())` for a Point / Spot / Distant light (examples/arencli.rs:95-98)."""
         return self._check(self.lib.arn_hscene_add_light(self.h, C.byref(light)))

@@ -9,43 +9,99 @@
 #include <vector>
 #include "../../../include/arn_host.h"
 #include "flat_scene.hpp"
+#include "image_io.hpp"
 #include "json.hpp"
 #include "obj_loader.hpp"
 
 using namespace arnhost;
 
-struct arn_hscene { FlatScene fs; };
+// tex_cache: image textures already loaded, keyed by file + ImageInfo + UVMapping (the reference shares MipMaps the same way,
+// texturing/textures/image.rs:170-199)
+struct arn_hscene { FlatScene fs; std::map<std::string, int> tex_cache; };
 
 namespace {
 
-// component::load_obj's material choice (src/component/mod.rs:70-173)
-int obj_material_to_arn(const ObjMaterial& mtl, FlatScene& fs, std::string* warn) {
+// ImageTexture::new_as_arc (image.rs:151-199) for a PNG file: builds the pyramid (host/image_io.hpp), appends it to the scene's
+// texture table.  Returns the texture id (>= 1), or 0 when the picture cannot be opened / decoded (`why` says so).
+int load_image_texture(arn_hscene& hs, const std::string& path, uint32_t channels, bool trilinear, float max_aniso, uint32_t wrapping,
+                       bool gamma, float scale, const float* scaling2, const float* shifting2, float* mean_out, std::string* why) {
+    char keybuf[160];
+    std::snprintf(keybuf, sizeof keybuf, "|%u|%d|%.9g|%u|%d|%.9g|%.9g,%.9g|%.9g,%.9g", channels, (int)trilinear, max_aniso, wrapping, (int)gamma, scale,
+                  scaling2[0], scaling2[1], shifting2[0], shifting2[1]);
+    const std::string key = path + keybuf;
+    arn_texture t; std::memset(&t, 0, sizeof t);
+    std::vector<float> texels; float mean[3] = {0.f, 0.f, 0.f};
+    auto it = hs.tex_cache.find(key);
+    if (it != hs.tex_cache.end() && !mean_out) return it->second;
+    if (!build_pyramid(path, channels, gamma, scale, &t, &texels, mean, why)) return 0;
+    if (mean_out) for (uint32_t c = 0; c < channels; c++) mean_out[c] = mean[c];
+    if (it != hs.tex_cache.end()) return it->second;
+    t.trilinear = trilinear ? 1u : 0u; t.wrapping = wrapping; t.max_aniso = max_aniso;
+    t.scale_u = scaling2[0]; t.scale_v = scaling2[1]; t.shift_u = shifting2[0]; t.shift_v = shifting2[1];
+    int id = hs.fs.add_texture(t, texels.data(), (uint64_t)texels.size());
+    if (id <= 0) { if (why) *why = hs.fs.err; return 0; }
+    hs.tex_cache[key] = id;
+    return id;
+}
+std::string path_join(const std::string& dir, const std::string& name) {
+    if (dir.empty() || (!name.empty() && name[0] == '/')) return name;
+    return dir + (dir.back() == '/' ? "" : "/") + name;
+}
+
+// component::load_obj's material choice (src/component/mod.rs:70-173).  map_Kd / map_Ks are opened next to the OBJ file, map_bump
+// as written (:76, :97, :125): EWA look-ups (trilinear false), max_aniso 16, Repeat, no gamma, scale 1, identity UV mapping;
+// a picture that cannot be opened leaves the MTL constant in place (:88-95,:111-118) — here that includes every non-PNG file.
+int obj_material_to_arn(const ObjMaterial& mtl, arn_hscene& hs, const std::string& parent_dir, std::string* warn) {
+    FlatScene& fs = hs.fs;
     arn_material m; std::memset(&m, 0, sizeof m);
-    if (!mtl.diffuse_texture.empty() || !mtl.specular_texture.empty())
-        if (warn) *warn += "image textures of material '" + mtl.name + "' are outside the hot path; constants used\n";
     for (int k = 0; k < 3; k++) { m.kd[k] = mtl.diffuse[k]; m.ks[k] = mtl.specular[k]; }
+    const float one2[2] = {1.f, 1.f}, zero2[2] = {0.f, 0.f};
+    float spec_mean[3] = {mtl.specular[0], mtl.specular[1], mtl.specular[2]};           // specular.mean(): the constant, or MipMap::mean
+    if (!mtl.diffuse_texture.empty()) {
+        std::string why;
+        int id = load_image_texture(hs, path_join(parent_dir, mtl.diffuse_texture), 3, false, 16.f, ARN_WRAP_REPEAT, false, 1.f, one2, zero2, nullptr, &why);
+        if (id > 0) m.kd_tex = (uint32_t)id; else if (warn) *warn += "diffuse texture " + mtl.diffuse_texture + " unfound (" + why + "); constant used\n";
+    }
+    if (!mtl.specular_texture.empty()) {
+        std::string why; float mean[3];
+        int id = load_image_texture(hs, path_join(parent_dir, mtl.specular_texture), 3, false, 16.f, ARN_WRAP_REPEAT, false, 1.f, one2, zero2, mean, &why);
+        if (id > 0) { m.ks_tex = (uint32_t)id; for (int k = 0; k < 3; k++) spec_mean[k] = mean[k]; }
+        else if (warn) *warn += "specular texture " + mtl.specular_texture + " unfound (" + why + "); constant used\n";
+    }
+    {
+        auto bt = mtl.unknown_param.find("map_bump");
+        if (bt != mtl.unknown_param.end() && !bt->second.empty()) {
+            std::string why;
+            int id = load_image_texture(hs, bt->second, 1, false, 16.f, ARN_WRAP_REPEAT, false, 1.f, one2, zero2, nullptr, &why);
+            if (id > 0) m.bump_tex = (uint32_t)id; else if (warn) *warn += "bump map " + bt->second + " unfound (" + why + "); none used\n";
+        }
+    }
     float rough = (1000.f - mtl.shininess) / 1000.f;                         // :120-122
     rough = rough < 1.f ? rough : 1.f; rough = rough > 0.f ? rough : 0.f;     // .min(1.).max(0.)
     m.roughness = rough;
     std::string illum = "2";
     auto it = mtl.unknown_param.find("illum"); if (it != mtl.unknown_param.end()) illum = it->second;
     float dissolve = mtl.dissolve > 0.f ? mtl.dissolve : 0.f; dissolve = dissolve < 1.f ? dissolve : 1.f;  // .max(0.).min(1.)
-    bool spec_black = m.ks[0] == 0.f && m.ks[1] == 0.f && m.ks[2] == 0.f;
-    bool spec_valid = m.ks[0] >= 0.f && m.ks[1] >= 0.f && m.ks[2] >= 0.f && std::isfinite(m.ks[0]) && std::isfinite(m.ks[1]) && std::isfinite(m.ks[2]);
+    bool spec_black = spec_mean[0] == 0.f && spec_mean[1] == 0.f && spec_mean[2] == 0.f;
+    bool spec_valid = spec_mean[0] >= 0.f && spec_mean[1] >= 0.f && spec_mean[2] >= 0.f && std::isfinite(spec_mean[0]) && std::isfinite(spec_mean[1]) && std::isfinite(spec_mean[2]);
     // relative_eq!(dissolve, 1.0): |d - 1| <= eps or <= eps * max(|d|, 1)
     bool dissolve_is_one = dissolve == 1.f || std::fabs(dissolve - 1.f) <= 1.1920929e-7f;
     if (illum.find('4') != std::string::npos) { m.type = ARN_MAT_GLASS; m.eta = mtl.optical_density; }
     else if (!dissolve_is_one) { m.type = ARN_MAT_TRANSLUCENT; m.dissolve = dissolve; }
-    else if (spec_black || !spec_valid) { m.type = ARN_MAT_MATTE; m.sigma = 0.f; m.ks[0] = m.ks[1] = m.ks[2] = 0.f; }
+    else if (spec_black || !spec_valid) { m.type = ARN_MAT_MATTE; m.sigma = 0.f; m.ks[0] = m.ks[1] = m.ks[2] = 0.f; m.ks_tex = 0; }
     else m.type = ARN_MAT_PLASTIC;
     return fs.add_material(m);
 }
 
-int load_obj_into(FlatScene& fs, const std::string& path, const float* transform16, std::string* err) {
+int load_obj_into(arn_hscene& hs, const std::string& path, const float* transform16, std::string* err) {
+    FlatScene& fs = hs.fs;
     std::vector<ObjModel> models; std::vector<ObjMaterial> mtls;
     if (!load_obj_file(path, models, mtls, err)) return ARN_E_IO;
+    const size_t slash = path.find_last_of('/');
+    const std::string parent_dir = slash == std::string::npos ? std::string() : path.substr(0, slash);      // path.parent()
     std::vector<int> mat_ids; std::string warn;
-    for (auto& mtl : mtls) { int id = obj_material_to_arn(mtl, fs, &warn); if (id < 0) { *err = fs.err; return id; } mat_ids.push_back(id); }
+    for (auto& mtl : mtls) { int id = obj_material_to_arn(mtl, hs, parent_dir, &warn); if (id < 0) { *err = fs.err; return id; } mat_ids.push_back(id); }
+    if (!warn.empty() && std::getenv("ARN_VERBOSE")) std::fprintf(stderr, "%s", warn.c_str());
     // fallback material appended after the MTL ones (:165-171)
     arn_material dflt; std::memset(&dflt, 0, sizeof dflt);
     dflt.type = ARN_MAT_MATTE; dflt.kd[0] = 0.5f; dflt.kd[1] = 0.6f; dflt.kd[2] = 0.7f;
@@ -88,44 +144,76 @@ bool json_vec(const Json* j, const char* const* keys, int n, float* out) {
 }
 const char* const XY[2] = {"x", "y"};
 const char* const XYZ[3] = {"x", "y", "z"};
-// RGBTextureDesc::Constant{value: RGBSpectrumf{inner: Vector3}}
-int json_rgb_texture(const Json* named, float* rgb, std::string* err) {
+// {RGB,Gray}TextureDesc::Image{info: ImageInfo{name, trilinear, max_aniso, wrapping, gamma, scale}, mapping: UVMapping{scaling, shifting}}
+// (examples/arencli.rs:377-380,433-436; image.rs:576-583; mappings.rs:14-19).  `name` is opened as written (image::open), then next to
+// the scene file.  A picture that cannot be opened makes the reference drop the material's primitive silently (to_arc -> None,
+// arencli.rs:307-316); here it is an error.
+int json_image_texture(const Json* img, arn_hscene* hs, const std::string& base_dir, uint32_t channels, uint32_t* tex_out, std::string* err) {
+    const Json* info = img->get("info"); const Json* map = img->get("mapping");
+    if (!hs) { *err = "image textures are not available here (emission textures are constants)"; return ARN_E_UNSUPPORTED; }
+    if (!info || !map || !info->get("name") || info->get("name")->kind != Json::Str) { *err = "malformed Image texture"; return ARN_E_INVALID; }
+    float max_aniso = 8.f, scale = 1.f, scaling[2] = {1.f, 1.f}, shifting[2] = {0.f, 0.f};
+    if (!json_num(info->get("max_aniso"), &max_aniso) || !json_num(info->get("scale"), &scale) || !json_vec(map->get("scaling"), XY, 2, scaling) ||
+        !json_vec(map->get("shifting"), XY, 2, shifting)) { *err = "malformed Image texture parameters"; return ARN_E_INVALID; }
+    auto flag = [](const Json* j, bool* out) { if (!j || j->kind != Json::Bool) return false; *out = j->b; return true; };
+    bool trilinear = false, gamma = false;
+    if (!flag(info->get("trilinear"), &trilinear) || !flag(info->get("gamma"), &gamma)) { *err = "malformed Image texture flags"; return ARN_E_INVALID; }
+    const Json* wr = info->get("wrapping"); uint32_t wrapping;
+    if (!wr || wr->kind != Json::Str) { *err = "malformed Image wrapping mode"; return ARN_E_INVALID; }
+    if (wr->str == "Repeat") wrapping = ARN_WRAP_REPEAT; else if (wr->str == "Black") wrapping = ARN_WRAP_BLACK; else if (wr->str == "Clamp") wrapping = ARN_WRAP_CLAMP;
+    else { *err = "unknown Image wrapping mode " + wr->str; return ARN_E_INVALID; }
+    std::string why;
+    int id = load_image_texture(*hs, info->get("name")->str, channels, trilinear, max_aniso, wrapping, gamma, scale, scaling, shifting, nullptr, &why);
+    if (id <= 0) id = load_image_texture(*hs, path_join(base_dir, info->get("name")->str), channels, trilinear, max_aniso, wrapping, gamma, scale, scaling, shifting, nullptr, &why);
+    if (id <= 0) { *err = "image texture: " + why; return ARN_E_IO; }
+    *tex_out = (uint32_t)id;
+    return ARN_OK;
+}
+// RGBTextureDesc::Constant{value: RGBSpectrumf{inner: Vector3}} or ::Image (hs != nullptr: `*tex_out` receives the texture id)
+int json_rgb_texture(const Json* named, float* rgb, std::string* err, arn_hscene* hs = nullptr, const std::string& base_dir = std::string(), uint32_t* tex_out = nullptr) {
     if (!named) { *err = "missing RGB texture"; return ARN_E_INVALID; }
     const Json* v = named->get("value");
     if (!v || v->is_null()) { *err = "texture referenced by name only (no value); texture reuse by name never resolves in the reference either"; return ARN_E_UNSUPPORTED; }
+    if (const Json* img = v->get("Image")) return json_image_texture(img, tex_out ? hs : nullptr, base_dir, 3, tex_out, err);
     const Json* c = v->get("Constant");
-    if (!c) { *err = "only Constant textures are on the hot path (Image / Product textures: SURVEY.md §8(f) N4)"; return ARN_E_UNSUPPORTED; }
+    if (!c) { *err = "Product textures never resolve in arencli (examples/arencli.rs:413-427): only Constant and Image textures are taken"; return ARN_E_UNSUPPORTED; }
     const Json* val = c->get("value"); const Json* inner = val ? val->get("inner") : nullptr;
     if (!json_vec(inner, XYZ, 3, rgb)) { *err = "malformed constant RGB texture"; return ARN_E_INVALID; }
     return ARN_OK;
 }
-int json_gray_texture(const Json* named, float* g, std::string* err) {
+int json_gray_texture(const Json* named, float* g, std::string* err, arn_hscene* hs = nullptr, const std::string& base_dir = std::string(), uint32_t* tex_out = nullptr) {
     if (!named) { *err = "missing gray texture"; return ARN_E_INVALID; }
     const Json* v = named->get("value");
     if (!v || v->is_null()) { *err = "texture referenced by name only (no value)"; return ARN_E_UNSUPPORTED; }
+    if (const Json* img = v->get("Image")) return json_image_texture(img, tex_out ? hs : nullptr, base_dir, 1, tex_out, err);
     const Json* c = v->get("Constant");
-    if (!c) { *err = "only Constant textures are on the hot path"; return ARN_E_UNSUPPORTED; }
+    if (!c) { *err = "Product textures never resolve in arencli: only Constant and Image textures are taken"; return ARN_E_UNSUPPORTED; }
     if (!json_num(c->get("value"), g)) { *err = "malformed constant gray texture"; return ARN_E_INVALID; }
     return ARN_OK;
 }
 // MaterialDesc::to_arc (examples/arencli.rs:290-379)
-int json_material(const Json& desc, FlatScene& fs, std::string* err) {
+int json_material(const Json& desc, arn_hscene& hs, const std::string& base_dir, std::string* err) {
+    FlatScene& fs = hs.fs;
     arn_material m; std::memset(&m, 0, sizeof m);
     const Json* body; int rc;
     if ((body = desc.get("Matte"))) {
         m.type = ARN_MAT_MATTE;
-        if ((rc = json_rgb_texture(body->get("kd"), m.kd, err)) != ARN_OK) return rc;
-        if ((rc = json_gray_texture(body->get("sigma"), &m.sigma, err)) != ARN_OK) return rc;
+        if ((rc = json_rgb_texture(body->get("kd"), m.kd, err, &hs, base_dir, &m.kd_tex)) != ARN_OK) return rc;
+        if ((rc = json_gray_texture(body->get("sigma"), &m.sigma, err, &hs, base_dir, &m.aux_tex)) != ARN_OK) return rc;
     } else if ((body = desc.get("Glass")) || (body = desc.get("Plastic")) || (body = desc.get("Translucent"))) {
         m.type = desc.get("Glass") ? ARN_MAT_GLASS : (desc.get("Plastic") ? ARN_MAT_PLASTIC : ARN_MAT_TRANSLUCENT);
-        if ((rc = json_rgb_texture(body->get("diffuse"), m.kd, err)) != ARN_OK) return rc;
-        if ((rc = json_rgb_texture(body->get("specular"), m.ks, err)) != ARN_OK) return rc;
-        if ((rc = json_gray_texture(body->get("roughness"), &m.roughness, err)) != ARN_OK) return rc;
+        if ((rc = json_rgb_texture(body->get("diffuse"), m.kd, err, &hs, base_dir, &m.kd_tex)) != ARN_OK) return rc;
+        if ((rc = json_rgb_texture(body->get("specular"), m.ks, err, &hs, base_dir, &m.ks_tex)) != ARN_OK) return rc;
+        if ((rc = json_gray_texture(body->get("roughness"), &m.roughness, err, &hs, base_dir, &m.aux_tex)) != ARN_OK) return rc;
         if (m.type == ARN_MAT_GLASS && !json_num(body->get("eta"), &m.eta)) { *err = "Glass needs eta"; return ARN_E_INVALID; }
         if (m.type == ARN_MAT_TRANSLUCENT && !json_num(body->get("dissolve"), &m.dissolve)) { *err = "Translucent needs dissolve"; return ARN_E_INVALID; }
     } else { *err = "unknown material description"; return ARN_E_INVALID; }
     const Json* bump = body->get("bump");
-    if (bump && !bump->is_null()) { *err = "bump maps are outside the hot path (SURVEY.md §8(f) N4)"; return ARN_E_UNSUPPORTED; }
+    if (bump && !bump->is_null()) {         // Option<Named<GrayTextureDesc>>: an Image displacement map (material/mod.rs:42-86)
+        float unused = 0.f;
+        if ((rc = json_gray_texture(bump, &unused, err, &hs, base_dir, &m.bump_tex)) != ARN_OK) return rc;
+        if (!m.bump_tex) { *err = "constant bump textures are not taken (only Image displacement maps)"; return ARN_E_UNSUPPORTED; }
+    }
     int id = fs.add_material(m);
     if (id < 0) *err = fs.err;
     return id;
@@ -153,6 +241,16 @@ int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, f
     return h->fs.add_sphere(radius, zmin, zmax, phimax, material, emission3, transform16);
 }
 int arn_hscene_add_texture(arn_hscene* h, const arn_texture* tex, const float* texels, uint64_t n_floats) { if (!h || !tex) return ARN_E_INVALID; return h->fs.add_texture(*tex, texels, n_floats); }
+int arn_hscene_add_texture_file(arn_hscene* h, const char* path, const arn_texture* params, int gamma, float scale, float* mean3_out) {
+    if (!h || !path || !params) return ARN_E_INVALID;
+    if ((params->channels != 1 && params->channels != 3) || params->wrapping > ARN_WRAP_CLAMP) return h->fs.fail(ARN_E_INVALID, "texture file: channels must be 1 or 3, a valid wrap mode");
+    const float sc[2] = {params->scale_u, params->scale_v}, sh[2] = {params->shift_u, params->shift_v};
+    float mean[3] = {0.f, 0.f, 0.f}; std::string why;
+    int id = load_image_texture(*h, path, params->channels, params->trilinear != 0, params->max_aniso, params->wrapping, gamma != 0, scale, sc, sh, mean, &why);
+    if (id <= 0) return h->fs.fail(ARN_E_IO, "texture file: " + why);
+    if (mean3_out) for (uint32_t c = 0; c < params->channels; c++) mean3_out[c] = mean[c];
+    return id;
+}
 int arn_hscene_add_light(arn_hscene* h, const arn_analytic_light* light) { if (!h || !light) return ARN_E_INVALID; return h->fs.add_light(*light); }
 
 int arn_point_light_make(const float* pos3, const float* intensity3, arn_analytic_light* out) {
@@ -224,7 +322,7 @@ int arn_spot_light_make(const float* pos3, const float* towards3, const float* i
 
 int arn_hscene_load_obj(arn_hscene* h, const char* path, const float* transform16) {
     if (!h || !path) return ARN_E_INVALID;
-    std::string err; int rc = load_obj_into(h->fs, path, transform16, &err);
+    std::string err; int rc = load_obj_into(*h, path, transform16, &err);
     if (rc < 0) h->fs.err = err;
     return rc;
 }
@@ -355,7 +453,7 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
             // `transform.unwrap_or(identity)` then from_model_transformed: identity is applied as a matrix too
             float ident[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};
             std::string path = (fn->str.size() && fn->str[0] == '/') ? fn->str : base + fn->str;
-            std::string err; int rc = load_obj_into(fs, path, tp ? tp : ident, &err);
+            std::string err; int rc = load_obj_into(*h, path, tp ? tp : ident, &err);
             if (rc < 0) return fs.fail(rc, err);                           // the reference prints "load mesh failed" and goes on
         }
         if (pass == 1 && shaped) {
@@ -368,7 +466,7 @@ int arn_hscene_load_json(arn_hscene* h, const char* json_path, const char* base_
             const Json* mat = shaped->get("material");
             const Json* mname = mat ? mat->get("name") : nullptr; const Json* mval = mat ? mat->get("value") : nullptr;
             if (!mname || mname->kind != Json::Str) return fs.fail(ARN_E_INVALID, "material without a name");
-            if (mval && !mval->is_null()) { std::string err; int id = json_material(*mval, fs, &err); if (id < 0) return fs.fail(id, err); materials[mname->str] = id; }
+            if (mval && !mval->is_null()) { std::string err; int id = json_material(*mval, *h, base, &err); if (id < 0) return fs.fail(id, err); materials[mname->str] = id; }
             auto it = materials.find(mname->str);
             if (it == materials.end()) return fs.fail(ARN_E_INVALID, "load shape failed: unknown material " + mname->str);
             float emission[3]; const float* ep = nullptr;

@@ -49,6 +49,14 @@ int arn_hscene_add_sphere(arn_hscene* h, float radius, float zmin, float zmax, f
  * id to put into arn_material.{kd,ks,aux,bump}_tex (k + 1) or an error. */
 int arn_hscene_add_texture(arn_hscene* h, const arn_texture* tex, const float* texels, uint64_t n_floats);
 
+/* The same from a picture file: `MipMap::new` restated for PNG files (host/image_io.hpp) — one Lanczos3 resize of the original
+ * per level (next-power-of-two sizes), `to_rgb()` (`params->channels` = 3) or `to_luma()` (1), `convert_in(gamma, scale)`.
+ * `params` supplies trilinear / wrapping / max_aniso / UV scale and shift; its level fields are ignored.  PARITY UNPINNED for the
+ * pyramid values: decoder and resampler belong to the `image` crate, which is not part of the reference tree.  `load_obj`'s
+ * map_Kd / map_Ks / map_bump and the scene file's `Image` textures go through the same routine.  mean3_out (optional) receives
+ * MipMap::mean.  Returns the texture id, ARN_E_IO if the file cannot be opened or decoded. */
+int arn_hscene_add_texture_file(arn_hscene* h, const char* path, const arn_texture* params, int gamma, float scale, float* mean3_out);
+
 /* `lights.push(light.to_arc())` for the scene file's Point / Spot / Distant lights
  * (examples/arencli.rs:95-98).  These come first in `Scene.lights`, before the emissive
  * primitives.  Returns the index into analytic_lights or an error. */

@@ -1,0 +1,271 @@
+"""Host-side picture ingest (arendur_b200/csrc/host/image_io.hpp): the PNG decoder against pictures written here, the Lanczos3
+resampler against an independent numpy restatement of the same published algorithm (PARITY UNPINNED against the reference: the
+`image` crate is not part of its tree), the pyramid layout of MipMap::new, and the routes into a scene: load_obj's map_Kd /
+map_Ks / map_bump, the scene file's Image textures, HostScene.add_texture_file."""
+import ctypes as C
+import json
+import math
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from arendur_b200 import api, scenes, _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def write_png(path, img, filters=None, depth=8, palette=None, interlace=0):
+    """img: (h, w) or (h, w, c) uint8 / uint16 array; filters: per-row filter types, cycled; palette: (n, 3) for indexed pictures."""
+    h, w = img.shape[:2]; ch = 1 if img.ndim == 2 else img.shape[2]
+    ctype = 3 if palette is not None else {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    if palette is not None and depth < 8:
+        per = 8 // depth; rows = []
+        for y in range(h):
+            bits = 0; out = bytearray(); n = 0
+            for v in img[y].reshape(-1):
+                bits = (bits << depth) | int(v); n += 1
+                if n == per: out.append(bits); bits = 0; n = 0
+            if n: out.append(bits << (depth * (per - n)))
+            rows.append(np.frombuffer(bytes(out), np.uint8).astype(np.int32))
+        bpp = 1
+    else:
+        data = img.astype(">u2").view(np.uint8).reshape(h, -1) if depth == 16 else img.reshape(h, -1)
+        rows = [data[y].astype(np.int32) for y in range(h)]
+        bpp = ch * (2 if depth == 16 else 1)
+    raw = bytearray(); prev = np.zeros_like(rows[0])
+    for y, line in enumerate(rows):
+        ft = 0 if filters is None else filters[y % len(filters)]
+        a = np.concatenate([np.zeros(bpp, np.int32), line[:-bpp]]) if line.size > bpp else np.zeros_like(line)
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if line.size > bpp else np.zeros_like(line)
+        if ft == 0: enc = line
+        elif ft == 1: enc = line - a
+        elif ft == 2: enc = line - prev
+        elif ft == 3: enc = line - (a + prev) // 2
+        else:
+            p = a + prev - c; pa, pb, pc = abs(p - a), abs(p - prev), abs(p - c)
+            enc = line - np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        raw.append(ft); raw += bytes((enc % 256).astype(np.uint8)); prev = line
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    z = zlib.compress(bytes(raw))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    if palette is not None:
+        png += chunk(b"PLTE", bytes(np.asarray(palette, np.uint8).reshape(-1)))
+    png += chunk(b"tEXt", b"Comment\x00ignored") + chunk(b"IDAT", z[: len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(png)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("imgio") / "test_image_io")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_image_io.cpp"), "-lz"])
+
+    def run(*args):
+        out = subprocess.run([exe, *[str(a) for a in args]], capture_output=True, text=True).stdout.splitlines()
+        if out and out[0].startswith("ERROR"):
+            return None, out[0]
+        w, h, ch = (int(v) for v in out[0].split())
+        return np.frombuffer(bytes.fromhex(out[1]), np.uint8).reshape(h, w, ch), None
+    return run
+
+
+def test_png_decoder_reads_what_was_written(harness, tmp_path):
+    rng = np.random.default_rng(7)
+    for ch in (1, 2, 3, 4):
+        for (h, w) in ((1, 1), (5, 7), (16, 16), (33, 2)):
+            img = rng.integers(0, 256, (h, w, ch)).astype(np.uint8)
+            p = tmp_path / f"c{ch}_{h}x{w}.png"
+            write_png(p, img if ch > 1 else img[..., 0], filters=[4, 3, 2, 1, 0])
+            got, err = harness("decode", p)
+            assert err is None and np.array_equal(got, img), (ch, h, w, err)
+    img16 = rng.integers(0, 65536, (6, 5, 3)).astype(np.uint16)
+    write_png(tmp_path / "d16.png", img16, filters=[1, 4], depth=16)
+    got, _ = harness("decode", tmp_path / "d16.png")
+    assert np.array_equal(got, (img16 >> 8).astype(np.uint8))                      # 16 bit samples: the high byte
+    pal = rng.integers(0, 256, (16, 3)).astype(np.uint8)
+    for depth in (8, 4, 2, 1):
+        idx = rng.integers(0, min(16, 1 << depth), (9, 11)).astype(np.uint8)
+        write_png(tmp_path / f"p{depth}.png", idx, filters=[0, 2], depth=depth, palette=pal)
+        got, err = harness("decode", tmp_path / f"p{depth}.png")
+        assert err is None and np.array_equal(got, pal[idx]), depth
+    # refused: interlaced pictures, other files, missing files
+    write_png(tmp_path / "i.png", rng.integers(0, 256, (4, 4, 3)).astype(np.uint8), interlace=1)
+    assert harness("decode", tmp_path / "i.png")[0] is None
+    (tmp_path / "x.png").write_bytes(b"not a png at all, just some bytes to be long enough for the header check")
+    assert harness("decode", tmp_path / "x.png")[0] is None and harness("decode", tmp_path / "missing.png")[0] is None
+
+
+def _np_sample(a, n_out):
+    """One pass of the `image` 0.12 resampler over axis 0 of a float array (n_in, ...), independent restatement in numpy."""
+    n_in = a.shape[0]
+    ratio = np.float32(n_in) / np.float32(n_out)
+    scale = ratio if ratio > 1 else np.float32(1)
+    radius = np.float32(math.ceil(np.float32(3) * scale))
+    out = np.zeros((n_out,) + a.shape[1:], np.uint8)
+    for o in range(n_out):
+        x = (np.float32(o) + np.float32(0.5)) * ratio
+        left = min(max(int(math.ceil(x - radius)), 0), n_in - 1); right = min(max(int(math.floor(x + radius)), 0), n_in - 1)
+        s = np.float32(0); t = np.zeros(a.shape[1:], np.float32)
+        for i in range(left, right + 1):
+            v = (np.float32(i) - x) / scale
+            if abs(v) >= 3: w = np.float32(0)
+            elif v == 0: w = np.float32(1)
+            else:
+                pa = np.float32(v) * np.float32(math.pi); pb = np.float32(v / np.float32(3)) * np.float32(math.pi)
+                w = np.float32(np.sin(pa, dtype=np.float32) / pa) * np.float32(np.sin(pb, dtype=np.float32) / pb)
+            s = np.float32(s + w); t = (t + a[i].astype(np.float32) * w).astype(np.float32)
+        out[o] = np.clip((t / s).astype(np.float32), 0, 255).astype(np.uint8)
+    return out
+
+
+def test_lanczos3_resampler_against_a_numpy_restatement(harness, tmp_path):
+    rng = np.random.default_rng(11)
+    for (h, w, nh, nw) in ((16, 16, 8, 8), (13, 7, 16, 8), (32, 5, 4, 1), (6, 6, 6, 6), (9, 20, 2, 32)):
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        write_png(tmp_path / "r.png", img)
+        got, err = harness("resize", tmp_path / "r.png", nw, nh)
+        tmp = _np_sample(img, nh)                                   # vertical pass first
+        want = np.transpose(_np_sample(np.transpose(tmp, (1, 0, 2)), nw), (1, 0, 2))
+        assert err is None and got.shape == want.shape
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1, (h, w, nh, nw)      # libm sin last-ulp differences may flip a truncation
+        assert (got != want).mean() < 0.02
+    const = np.full((10, 12, 3), 137, np.uint8); write_png(tmp_path / "c.png", const)
+    got, _ = harness("resize", tmp_path / "c.png", 16, 16)
+    assert np.abs(got.astype(int) - 137).max() <= 2                  # normalised weights: a flat picture stays flat, up to the truncation of each of the two passes
+
+
+def _tex_arrays(d):
+    tex = np.ctypeslib.as_array(d.texels, (d.n_texel_floats,)) if d.n_texel_floats else np.zeros(0, np.float32)
+    return [d.textures[i] for i in range(d.n_textures)], tex
+
+
+def test_pyramid_layout_follows_mipmap_new(tmp_path):
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (5, 12, 3)).astype(np.uint8)             # 12 x 5 -> level 0 is 16 x 8
+    write_png(tmp_path / "t.png", img)
+    hs = api.HostScene()
+    tid, mean = hs.add_texture_file(tmp_path / "t.png", channels=3, gamma=False, scale=2.0)
+    lid, lmean = hs.add_texture_file(tmp_path / "t.png", channels=1, gamma=True, scale=1.0, trilinear=True, wrapping=L.ARN_WRAP_CLAMP, scaling=(2.0, 3.0))
+    assert (tid, lid) == (1, 2)
+    m = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5), kd_tex=tid, bump_tex=lid))
+    hs.add_mesh(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.uint32([0, 1, 2]), m, uvs=np.float32([[0, 0], [1, 0], [0, 1]]))
+    hs.add_sphere(0.3, -0.3, 0.3, 6.28, m, emission=(1, 1, 1))
+    d = hs.build()
+    texs, texels = _tex_arrays(d)
+    t0, t1 = texs
+    assert (t0.channels, t0.n_levels, t0.trilinear, t0.wrapping, t0.max_aniso) == (3, 5, 0, L.ARN_WRAP_REPEAT, 16.0)
+    assert [(t0.level_w[i], t0.level_h[i]) for i in range(5)] == [(16, 8), (8, 4), (4, 2), (2, 1), (1, 1)]      # max(np2 >> i, 1)
+    assert (t1.channels, t1.n_levels, t1.trilinear, t1.wrapping, t1.scale_u, t1.scale_v) == (1, 5, 1, L.ARN_WRAP_CLAMP, 2.0, 3.0)
+    l0 = texels[t0.level_offset[0]: t0.level_offset[0] + 16 * 8 * 3].reshape(8, 16, 3)
+    assert l0.min() >= 0.0 and l0.max() <= 2.0 and np.allclose(mean, l0.reshape(-1, 3).mean(0), rtol=1e-5)
+    q = np.round(l0 / 2.0 * 255.0)
+    assert np.abs(l0 / 2.0 * 255.0 - q).max() < 1e-3                    # convert_in: u8 / 255 * scale
+    g0 = texels[t1.level_offset[0]: t1.level_offset[0] + 16 * 8].reshape(8, 16)
+    assert g0.min() >= 0.0 and g0.max() <= 1.0 and np.allclose(lmean, [g0.mean()], rtol=1e-5)
+    # the same file with the same parameters is shared
+    assert hs.add_texture_file(tmp_path / "t.png", channels=3, gamma=False, scale=2.0)[0] == tid
+    with pytest.raises(api.ArnError):
+        hs.add_texture_file(tmp_path / "nope.png")
+
+
+def _textured_obj(tmp_path, rng):
+    kd = (rng.integers(0, 256, (8, 8, 3))).astype(np.uint8); write_png(tmp_path / "kd.png", kd)
+    ks = np.zeros((4, 4, 3), np.uint8); write_png(tmp_path / "black.png", ks)
+    kss = (rng.integers(100, 256, (4, 4, 3))).astype(np.uint8); write_png(tmp_path / "ks.png", kss)
+    yy, xx = np.mgrid[0:16, 0:16]
+    bump = (127 + 120 * np.sin(xx * 0.8) * np.cos(yy * 0.6)).astype(np.uint8); write_png(tmp_path / "bump.png", bump)
+    (tmp_path / "s.mtl").write_text(
+        f"newmtl textured\nKd 0.1 0.1 0.1\nKs 0 0 0\nmap_Kd kd.png\nmap_bump {tmp_path / 'bump.png'}\n"
+        "newmtl specblack\nKd 0.5 0.5 0.5\nKs 0.9 0.9 0.9\nmap_Ks black.png\n"            # the texture's mean decides: black -> Matte
+        "newmtl shiny\nNs 400\nKd 0.2 0.3 0.4\nKs 0 0 0\nmap_Ks ks.png\n"                  # ... and here -> Plastic
+        "newmtl lost\nKd 0.3 0.6 0.9\nKs 0 0 0\nmap_Kd missing.png\n")
+    (tmp_path / "s.obj").write_text(
+        "mtllib s.mtl\nv -3 -1 8\nv 3 -1 8\nv 3 -1 2\nv -3 -1 2\nv -3 3 8\nv 3 3 8\nv -3 3 2\nv 3 3 2\n"
+        "vt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 1 0\n"
+        "g floor\nusemtl textured\nf 1/1/1 2/2/1 3/3/1 4/4/1\n"
+        "g back\nusemtl specblack\nf 1/1 2/2 6/3 5/4\n"
+        "g left\nusemtl shiny\nf 4/1 1/2 5/3 7/4\n"
+        "g right\nusemtl lost\nf 2/1 3/2 8/3 6/4\n")
+    hs = api.HostScene()
+    assert hs.load_obj(tmp_path / "s.obj") == 8
+    lm = hs.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.5, 0.5, 0.5)))
+    tl = np.eye(4, dtype=np.float32); tl[3, 0:3] = (-0.5, 2.2, 4.5)
+    hs.add_sphere(0.4, -0.4, 0.4, 6.28, lm, emission=(18.0, 16.0, 12.0), transform=tl)
+    hs.build()
+    cam = api.make_camera(api.IDENTITY, (-1.0, -0.75, 1.0, 0.75), 0.1, 100.0, 1.2, 64, 48)
+    return hs, cam, api.make_film(64, 48), api.make_sampler(2, 2, 8, 5), api.make_pt_params(max_depth=4)
+
+
+def test_load_obj_takes_mtl_texture_maps(tmp_path):
+    """component::load_obj (component/mod.rs:70-173): map_Kd / map_Ks next to the OBJ, map_bump as written; a picture that cannot be
+    opened leaves the constant; `specular.mean()` of a texture decides Matte vs Plastic."""
+    hs, cam, film, smp, prm = _textured_obj(tmp_path, np.random.default_rng(21))
+    d = hs.desc()
+    assert d.n_textures == 4                                             # kd, bump, black, ks (missing.png: none)
+    mats = [d.materials[i] for i in range(d.n_materials)]
+    textured, specblack, shiny, lost = mats[0], mats[1], mats[2], mats[3]
+    assert (textured.type, textured.kd_tex > 0, textured.bump_tex > 0, textured.ks_tex) == (L.ARN_MAT_MATTE, True, True, 0)
+    assert (specblack.type, specblack.ks_tex) == (L.ARN_MAT_MATTE, 0)     # black specular texture -> Matte, specular dropped
+    assert (shiny.type, shiny.ks_tex > 0) == (L.ARN_MAT_PLASTIC, True) and abs(shiny.roughness - 0.6) < 1e-6
+    assert (lost.type, lost.kd_tex) == (L.ARN_MAT_MATTE, 0) and abs(lost.kd[2] - 0.9) < 1e-6
+    t = d.textures[textured.kd_tex - 1]
+    assert (t.trilinear, t.max_aniso, t.wrapping, t.scale_u, t.shift_u) == (0, 16.0, L.ARN_WRAP_REPEAT, 1.0, 0.0)
+    # the picture reaches the render: the oracle's frame changes when the texture does
+    osc = O.OracleScene(d)
+    f1, _, _ = osc.render_pt(cam, film, smp, prm)
+    assert np.isfinite(f1).all() and f1[..., :3].max() > 0
+    hs2, *_ = _textured_obj(tmp_path, np.random.default_rng(22))
+    f2, _, _ = O.OracleScene(hs2.desc()).render_pt(cam, film, smp, prm)
+    assert not np.array_equal(f1, f2)
+
+
+def test_scene_file_image_textures(tmp_path):
+    """RGBTextureDesc::Image / GrayTextureDesc::Image and bump maps of a Shaped primitive (examples/arencli.rs:262-460)."""
+    rng = np.random.default_rng(5)
+    write_png(tmp_path / "kd.png", rng.integers(0, 256, (8, 16, 3)).astype(np.uint8))
+    write_png(tmp_path / "rough.png", rng.integers(20, 120, (4, 4)).astype(np.uint8))
+    src = json.load(open(os.path.join("/root/reference/examples/cornellbox/cb.json"))) if os.path.exists("/root/reference/examples/cornellbox/cb.json") else None
+    if src is None:
+        pytest.skip("reference scene file not present (GPU box)")
+    def image(name, trilinear=False):
+        return {"name": "t_" + name, "value": {"Image": {"info": {"name": name, "trilinear": trilinear, "max_aniso": 8.0, "wrapping": "Clamp", "gamma": True, "scale": 1.5},
+                                                         "mapping": {"scaling": {"x": 2.0, "y": 1.0}, "shifting": {"x": 0.25, "y": 0.0}}}}}
+    shaped = [c for c in src["components"] if c.get("value") and "Shaped" in c["value"]]
+    assert shaped
+    mat = shaped[-1]["value"]["Shaped"]["material"]
+    mat["value"] = {"Plastic": {"diffuse": image("kd.png"), "specular": {"name": "s", "value": {"Constant": {"value": {"inner": {"x": 0.5, "y": 0.5, "z": 0.5}}}}},
+                                "roughness": image("rough.png", True), "bump": image("rough.png")}}
+    src["components"] = [c for c in src["components"] if not (c.get("value") and "Mesh" in c["value"])]      # spheres only: no OBJ needed
+    (tmp_path / "scene.json").write_text(json.dumps(src))
+    hs = api.HostScene()
+    cam, film, smp, prm, out = hs.load_json(tmp_path / "scene.json", base_dir=str(tmp_path))
+    d = hs.build()
+    assert d.n_textures == 3                                             # rough.png twice with different parameters
+    m = [d.materials[i] for i in range(d.n_materials) if d.materials[i].kd_tex][0]
+    assert m.type == L.ARN_MAT_PLASTIC and m.aux_tex and m.bump_tex and m.aux_tex != m.bump_tex
+    t = d.textures[m.kd_tex - 1]
+    assert (t.channels, t.trilinear, t.wrapping, t.max_aniso, t.scale_u, t.shift_u) == (3, 0, L.ARN_WRAP_CLAMP, 8.0, 2.0, 0.25)
+    assert (t.level_w[0], t.level_h[0], t.n_levels) == (16, 8, 5)
+    mat["value"]["Plastic"]["diffuse"] = image("nowhere.png")
+    (tmp_path / "bad.json").write_text(json.dumps(src))
+    with pytest.raises(api.ArnError):
+        api.HostScene().load_json(tmp_path / "bad.json", base_dir=str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_png_textured_obj_scene_per_sample_bit_exact(ctx, tmp_path):
+    """End to end: OBJ + MTL with PNG maps -> pyramids -> textured shade instance; every camera sample equals the oracle's."""
+    hs, cam, film, smp, prm = _textured_obj(tmp_path, np.random.default_rng(21))
+    d = hs.desc()
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    _, grad, st = sc.render_pt_samples(cam, film, smp, prm)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    assert np.array_equal(grad.view(np.uint32), orad.view(np.uint32))
+    sc.close(); osc.close()
