@@ -33,7 +33,9 @@ int load_image_texture(arn_hscene& hs, const std::string& path, uint32_t channel
     std::vector<float> texels; float mean[3] = {0.f, 0.f, 0.f};
     auto it = hs.tex_cache.find(key);
     if (it != hs.tex_cache.end() && !mean_out) return it->second;
-    if (!build_pyramid(path, channels, gamma, scale, &t, &texels, mean, why)) return 0;
+    try {
+        if (!build_pyramid(path, channels, gamma, scale, &t, &texels, mean, why)) return 0;
+    } catch (const std::exception& e) { if (why) *why = path + ": " + e.what(); return 0; }      // e.g. bad_alloc on a huge picture: never across the C boundary
     if (mean_out) for (uint32_t c = 0; c < channels; c++) mean_out[c] = mean[c];
     if (it != hs.tex_cache.end()) return it->second;
     t.trilinear = trilinear ? 1u : 0u; t.wrapping = wrapping; t.max_aniso = max_aniso;

@@ -64,8 +64,9 @@ inline bool png_decode(const std::string& path, Image8* out, std::string* err) {
         else if (!std::memcmp(type, "IEND", 4)) end = true;
         pos += 12 + (size_t)len;
     }
-    if (ctype < 0 || w == 0 || h == 0 || w > 65536 || h > 65536) return fail("missing or implausible IHDR");
+    if (ctype < 0 || w == 0 || h == 0 || w > 32768 || h > 32768) return fail("missing or implausible IHDR (pictures up to 32768 x 32768)");
     if (interlace != 0) return fail("interlaced PNG is not supported");
+    if (idat.empty()) return fail("no image data");
     int samples;                                       // samples per pixel in the file
     switch (ctype) { case 0: samples = 1; break; case 2: samples = 3; break; case 3: samples = 1; break; case 4: samples = 2; break; case 6: samples = 4; break; default: return fail("unknown colour type"); }
     if (ctype == 3) { if (depth != 1 && depth != 2 && depth != 4 && depth != 8) return fail("bad palette bit depth"); if (plte.size() < 3) return fail("palette image without PLTE"); }

@@ -269,3 +269,23 @@ def test_png_textured_obj_scene_per_sample_bit_exact(ctx, tmp_path):
     _, orad = osc.render_pt_samples(cam, film, smp, prm)
     assert np.array_equal(grad.view(np.uint32), orad.view(np.uint32))
     sc.close(); osc.close()
+
+
+def test_png_decoder_survives_damaged_files(harness, tmp_path):
+    """Truncated and bit-flipped files are refused (or decoded to something) — never a crash: the harness must exit normally."""
+    rng = np.random.default_rng(99)
+    write_png(tmp_path / "ok.png", rng.integers(0, 256, (12, 9, 3)).astype(np.uint8), filters=[4, 1])
+    data = bytearray((tmp_path / "ok.png").read_bytes())
+    exe_ok = 0
+    for k in range(120):
+        d = bytearray(data)
+        if k % 3 == 0:
+            d = d[: int(rng.integers(0, len(d)))]
+        else:
+            for _ in range(int(rng.integers(1, 6))):
+                d[int(rng.integers(8, len(d)))] = int(rng.integers(0, 256))
+        (tmp_path / "bad.png").write_bytes(bytes(d))
+        img, err = harness("decode", tmp_path / "bad.png")
+        assert (img is None) != (err is None)                           # a verdict either way; a crash would give neither
+        exe_ok += img is not None
+    assert exe_ok < 120
