@@ -10,11 +10,12 @@
 // u8), `to_luma` its BT.709 weights.  Nothing in the reference pins these numbers, so no test claims bit-exactness for
 // them; the renderer downstream of the pyramid IS pinned (kernels/shade_tex.cuh against oracle/texture.hpp).
 //
-// Decoder: PNG only (8 / 16 bit gray, gray + alpha, RGB, RGBA; palette 1 .. 8 bit; no Adam7 interlace), inflate by zlib.
-// Any other file, like a missing one, makes the caller fall back to the MTL constant — `image::open(..)` failing has the
+// Decoders: PNG (8 / 16 bit gray, gray + alpha, RGB, RGBA; palette 1 .. 8 bit; no Adam7 interlace; inflate by zlib) and TGA
+// (true colour, gray, colour-mapped; raw or run-length encoded).  Any other file, like a missing one, makes the caller fall back to the MTL constant — `image::open(..)` failing has the
 // same effect in load_obj (component/mod.rs:88-95).
 #pragma once
 #include <zlib.h>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -112,6 +113,70 @@ inline bool png_decode(const std::string& path, Image8* out, std::string* err) {
     return true;
 }
 
+// Truevision TGA: true-colour (24 / 32 bit), gray (8 bit) and colour-mapped (8 bit indices into a 24 / 32 bit map) pictures, raw or
+// run-length encoded; rows are returned top to bottom whatever the file's origin flag says.
+inline bool tga_decode(const std::string& path, Image8* out, std::string* err) {
+    auto fail = [&](const std::string& why) { if (err) *err = path + ": " + why; return false; };
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return fail("cannot open");
+    std::vector<uint8_t> file;
+    { uint8_t buf[65536]; size_t n; while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) file.insert(file.end(), buf, buf + n); }
+    std::fclose(f);
+    if (file.size() < 18) return fail("not a TGA file");
+    const uint8_t* h = file.data();
+    const uint32_t id_len = h[0], cmap_type = h[1], type = h[2], cmap_first = h[3] | (h[4] << 8), cmap_len = h[5] | (h[6] << 8), cmap_bits = h[7];
+    const uint32_t w = h[12] | (h[13] << 8), ht = h[14] | (h[15] << 8), bits = h[16], desc = h[17];
+    const bool rle = type == 9 || type == 10 || type == 11;
+    const uint32_t base = rle ? type - 8 : type;                           // 1 colour-mapped, 2 true colour, 3 gray
+    if (w == 0 || ht == 0 || base < 1 || base > 3) return fail("unsupported TGA image type");
+    if ((base == 2 && bits != 24 && bits != 32) || (base == 3 && bits != 8) || (base == 1 && (bits != 8 || cmap_type != 1 || (cmap_bits != 24 && cmap_bits != 32))))
+        return fail("unsupported TGA pixel format");
+    size_t pos = 18 + id_len;
+    const uint8_t* cmap = nullptr; const uint32_t cbytes = cmap_bits / 8;
+    if (cmap_type == 1) { if (pos + (size_t)cmap_len * cbytes > file.size()) return fail("truncated colour map"); cmap = &file[pos]; pos += (size_t)cmap_len * cbytes; }
+    const uint32_t bpp = bits / 8; const size_t npix = (size_t)w * ht;
+    std::vector<uint8_t> raw(npix * bpp);
+    if (!rle) { if (pos + raw.size() > file.size()) return fail("truncated image data"); std::memcpy(raw.data(), &file[pos], raw.size()); }
+    else {
+        size_t o = 0;
+        while (o < npix) {
+            if (pos >= file.size()) return fail("truncated run-length data");
+            const uint32_t hdr = file[pos++], cnt = (hdr & 127u) + 1u;
+            if (o + cnt > npix) return fail("run past the end of the picture");
+            if (hdr & 128u) {
+                if (pos + bpp > file.size()) return fail("truncated run-length data");
+                for (uint32_t k = 0; k < cnt; k++) std::memcpy(&raw[(o + k) * bpp], &file[pos], bpp);
+                pos += bpp;
+            } else {
+                if (pos + (size_t)cnt * bpp > file.size()) return fail("truncated run-length data");
+                std::memcpy(&raw[o * bpp], &file[pos], (size_t)cnt * bpp); pos += (size_t)cnt * bpp;
+            }
+            o += cnt;
+        }
+    }
+    out->w = w; out->h = ht; out->ch = base == 3 ? 1u : ((base == 2 ? bits : cmap_bits) == 32 ? 4u : 3u);
+    out->px.assign(npix * out->ch, 0);
+    const bool top_origin = (desc & 0x20u) != 0, right_origin = (desc & 0x10u) != 0;
+    for (uint32_t y = 0; y < ht; y++) for (uint32_t x = 0; x < w; x++) {
+        const uint32_t sy = top_origin ? y : ht - 1 - y, sx = right_origin ? w - 1 - x : x;
+        const uint8_t* s = &raw[((size_t)sy * w + sx) * bpp];
+        uint8_t* d = &out->px[((size_t)y * w + x) * out->ch];
+        if (base == 3) d[0] = s[0];
+        else {
+            const uint8_t* c = s;
+            if (base == 1) { const uint32_t idx = s[0]; if (idx < cmap_first || idx - cmap_first >= cmap_len) return fail("colour index outside the map"); c = cmap + (size_t)(idx - cmap_first) * cbytes; }
+            d[0] = c[2]; d[1] = c[1]; d[2] = c[0]; if (out->ch == 4) d[3] = c[3];             // BGR(A) -> RGB(A)
+        }
+    }
+    return true;
+}
+// image::open: by content for PNG, by extension for TGA (the format has no signature)
+inline bool image_decode(const std::string& path, Image8* out, std::string* err) {
+    auto ends_with = [&](const char* e) { const size_t n = std::strlen(e); if (path.size() < n) return false; for (size_t i = 0; i < n; i++) if (std::tolower((unsigned char)path[path.size() - n + i]) != e[i]) return false; return true; };
+    if (ends_with(".tga")) return tga_decode(path, out, err);
+    return png_decode(path, out, err);
+}
+
 namespace detail {
 inline float lanczos3_kernel(float x) {                                   // imageops::sample::lanczos3_kernel
     const float t = 3.f;
@@ -165,7 +230,7 @@ inline float inverse_gamma_correct(float v) {                             // ima
 inline bool build_pyramid(const std::string& path, uint32_t channels, bool gamma, float scale, arn_texture* t, std::vector<float>* texels,
                           float* mean, std::string* err) {
     Image8 img;
-    if (!png_decode(path, &img, err)) return false;
+    if (!image_decode(path, &img, err)) return false;
     auto np2 = [](uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; };
     const uint32_t np2x = np2(img.w), np2y = np2(img.h);
     uint32_t big = np2x > np2y ? np2x : np2y, levels = 1;

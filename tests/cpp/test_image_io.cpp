@@ -9,7 +9,7 @@
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
     arnhost::Image8 img; std::string err;
-    if (!arnhost::png_decode(argv[2], &img, &err)) { std::printf("ERROR %s\n", err.c_str()); return 1; }
+    if (!arnhost::image_decode(argv[2], &img, &err)) { std::printf("ERROR %s\n", err.c_str()); return 1; }
     if (!std::strcmp(argv[1], "resize") && argc >= 5) img = arnhost::resize_lanczos3(img, (uint32_t)std::atoi(argv[3]), (uint32_t)std::atoi(argv[4]));
     std::printf("%u %u %u\n", img.w, img.h, img.ch);
     for (uint8_t b : img.px) std::printf("%02x", b);

@@ -289,3 +289,59 @@ def test_png_decoder_survives_damaged_files(harness, tmp_path):
         assert (img is None) != (err is None)                           # a verdict either way; a crash would give neither
         exe_ok += img is not None
     assert exe_ok < 120
+
+
+def write_tga(path, img, rle=False, top_origin=False, palette=None):
+    """img: (h, w) gray / index or (h, w, 3 | 4) RGB(A) uint8; rows are stored bottom-up unless top_origin."""
+    h, w = img.shape[:2]
+    rows = img if top_origin else img[::-1]
+    if img.ndim == 2:
+        px = [bytes([int(v)]) for v in rows.reshape(-1)]; bits = 8; base = 1 if palette is not None else 3
+    else:
+        ch = img.shape[2]; bits = 8 * ch; base = 2
+        px = [bytes([int(p[2]), int(p[1]), int(p[0])] + ([int(p[3])] if ch == 4 else [])) for p in rows.reshape(-1, ch)]
+    body = bytearray()
+    if rle:
+        i = 0
+        while i < len(px):
+            run = 1
+            while i + run < len(px) and run < 128 and px[i + run] == px[i]: run += 1
+            if run > 1: body += bytes([128 | (run - 1)]) + px[i]; i += run
+            else:
+                lit = 1
+                while i + lit < len(px) and lit < 128 and (i + lit + 1 >= len(px) or px[i + lit] != px[i + lit + 1]): lit += 1
+                body += bytes([lit - 1]) + b"".join(px[i:i + lit]); i += lit
+    else:
+        body += b"".join(px)
+    cmap = b""; cmap_len = 0
+    if palette is not None:
+        cmap_len = len(palette); cmap = b"".join(bytes([int(c[2]), int(c[1]), int(c[0])]) for c in palette)
+    hdr = struct.pack("<BBBHHBHHHHBB", 3, 1 if palette is not None else 0, base + (8 if rle else 0), 0, cmap_len, 24 if palette is not None else 0,
+                      0, 0, w, h, bits, (0x20 if top_origin else 0) | (8 if bits == 32 else 0))
+    with open(path, "wb") as f:
+        f.write(hdr + b"id!" + cmap + bytes(body))
+
+
+def test_tga_decoder_reads_what_was_written(harness, tmp_path):
+    rng = np.random.default_rng(17)
+    for ch in (1, 3, 4):
+        for rle in (False, True):
+            for top in (False, True):
+                img = rng.integers(0, 4, (7, 10, ch)).astype(np.uint8) * 60       # few levels: runs for the encoder
+                write_tga(tmp_path / "t.tga", img if ch > 1 else img[..., 0], rle=rle, top_origin=top)
+                got, err = harness("decode", tmp_path / "t.tga")
+                assert err is None and np.array_equal(got, img), (ch, rle, top, err)
+    pal = rng.integers(0, 256, (9, 3)).astype(np.uint8); idx = rng.integers(0, 9, (5, 6)).astype(np.uint8)
+    write_tga(tmp_path / "p.TGA", idx, rle=True, palette=pal)
+    got, err = harness("decode", tmp_path / "p.TGA")
+    assert err is None and np.array_equal(got, pal[idx])
+    (tmp_path / "short.tga").write_bytes(b"\x00" * 10)
+    assert harness("decode", tmp_path / "short.tga")[0] is None
+    data = (tmp_path / "t.tga").read_bytes()
+    (tmp_path / "cut.tga").write_bytes(data[: len(data) // 2])
+    assert harness("decode", tmp_path / "cut.tga")[0] is None
+    # through the scene route
+    hs = api.HostScene()
+    write_tga(tmp_path / "tex.tga", rng.integers(0, 256, (4, 8, 3)).astype(np.uint8))
+    tid, mean = hs.add_texture_file(tmp_path / "tex.tga")
+    assert tid == 1 and 0.2 < float(mean.mean()) < 0.8
