@@ -60,6 +60,7 @@ struct arn_ctx {
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
     int g_trace_8 = 0, g_closest_8 = 0, g_any_8 = 0;      // compressed 8-wide walk
     size_t opt_wave = 0;
+    int opt_smem_off = 0;        // ARN_OPT_SMEM_NODES = 1: never walk small trees from shared memory
     int opt_refill = 0;          // ARN_OPT_TRACE_REFILL: lane-refilling trace (kernels/trace_refill.cuh) for trees walked with the binary nodes
     int g_setup = 0, g_refill = 0, g_classify = 0, g_shade_tex = 0;
 };
@@ -203,6 +204,8 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_generate = grid_for(c, (const void*)k_generate);
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
+    CTX_TRY( cudaFuncSetAttribute((const void*)k_trace<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
+    { const char* e = std::getenv("ARN_SMEM_NODES"); if (e) c->opt_smem_off = std::atoi(e) == 0; }
     c->g_trace_8 = grid_for(c, (const void*)k_trace<ARN_TRAV_CW8>);
     c->g_closest_8 = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_CW8>);
     c->g_any_8 = grid_for(c, (const void*)k_any_batch<ARN_TRAV_CW8>);
@@ -256,6 +259,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     case ARN_OPT_BVH_WIDTH: if (value != 0 && value != 2 && value != 4 && value != 8) return set_err(c, ARN_E_INVALID, "BVH width must be 0 (auto), 2, 4 or 8"); c->opt_width = (int)value; return ARN_OK;
     case ARN_OPT_PIPELINES: if (value < 0 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 0 (auto) ..8"); c->opt_pipes = (int)value; return ARN_OK;
     case ARN_OPT_TRACE_REFILL: c->opt_refill = value != 0; return ARN_OK;
+    case ARN_OPT_SMEM_NODES: c->opt_smem_off = value != 0; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -726,6 +730,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
     const bool wide = use_wide(s), cw8 = use_cw8(s);
     const bool refill = c->opt_refill && !wide && !cw8 && !c->opt_count;
+    const size_t node_bytes = (size_t)s->dev.n_nodes * sizeof(arn_node);
+    const bool smem_nodes = !c->opt_smem_off && !wide && !cw8 && !refill && !c->opt_count && node_bytes <= ARN_SMEM_NODE_BYTES;
     const bool textured = s->dev.n_textures != 0;
     for (int i = 0; i < np; i++) {
         int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;
@@ -781,6 +787,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             else if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else if (cw8) k_trace<ARN_TRAV_CW8><<<c->g_trace_8, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            else if (smem_nodes) k_trace<ARN_TRAV_BINARY_SMEM><<<c->sm_count, ARN_BLOCK_SMEM, node_bytes, st>>>(s->dev, P.pb, P.q, j);
             else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), st);
         };

@@ -155,6 +155,18 @@ ARN_DEV Node8 ld_node(const float4* __restrict__ p) {      // one 256-bit load p
         : "=f"(n.q0.x), "=f"(n.q0.y), "=f"(n.q0.z), "=f"(n.q0.w), "=f"(n.q1.x), "=f"(n.q1.y), "=f"(n.q1.z), "=f"(n.q1.w) : "l"(p));
     return n;
 }
+// Small trees (ARN_TRAV_BINARY_SMEM): the whole node array is staged in dynamic shared memory by the block, a node fetch is two
+// LDS.128 (~25 cycles, flat) instead of an L1 hit / L2 round trip on the walk's dependent fetch -> test -> branch chain.
+extern __shared__ __align__(16) float4 arn_snodes[];
+// `sbase`: the shared-window address of arn_snodes, computed once per ray and kept in a register (left to the compiler, the
+// window base is rebuilt from SR_CgaCtaId with four uniform-pipe instructions in front of every fetch)
+ARN_DEV uint32_t snodes_base() { uint32_t b = (uint32_t)__cvta_generic_to_shared(arn_snodes); asm volatile("" : "+r"(b)); return b; }
+ARN_DEV float4 lds128(uint32_t addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; }
+template <bool SM>
+ARN_DEV Node8 ld_node_x(const DevScene& sc, uint32_t sbase, uint32_t idx) {
+    if (SM) { Node8 n; n.q0 = lds128(sbase + idx * 32u); n.q1 = lds128(sbase + idx * 32u + 16u); return n; }
+    return ld_node(sc.nodes + 2 * (size_t)idx);
+}
 ARN_DEV float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }   // FMNMX3
 ARN_DEV float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 ARN_DEV bool ray_is_regular(const DevScene& sc, const TravRay& r) {
@@ -288,14 +300,15 @@ ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& 
 // component/mod.rs:35-38, so the boolean is identical).
 // COUNT: accumulate nodes/primitives tested into ctr[0..2] (for the algorithmic-bytes figure).
 // pop the next stack entry whose entry distance is still below tmax; false when the stack is empty
+template <bool SM = false>
 ARN_DEV bool trav_pop(const DevScene& sc, const TravRay& r, const uint2* stack, int& sp,
-                      uint32_t& idx, uint32_t& offset, uint32_t& len_axis) {
+                      uint32_t& idx, uint32_t& offset, uint32_t& len_axis, uint32_t sbase = 0u) {
     for (;;) {
         if (sp == 0) return false;
         uint2 e = stack[--sp];
         if (__uint_as_float(e.y) < r.tmax) {
             idx = e.x;
-            float4 n1 = __ldg(&sc.nodes[2 * idx + 1]);
+            float4 n1 = SM ? lds128(sbase + idx * 32u + 16u) : __ldg(&sc.nodes[2 * idx + 1]);
             offset = __float_as_uint(n1.z); len_axis = __float_as_uint(n1.w);
             return true;
         }
@@ -396,6 +409,7 @@ ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, Trav
 // the reference's order.  What the walk does between the two with a tmax the postponed leaf might have shortened is interior
 // culling only, which merely has to be conservative (a larger tmax culls less); every leaf still takes the exact test with the
 // tmax current at ITS turn.  The warp switches phases half as often and both phases run with more lanes.
+template <bool SM = false>          // (the speculative variant always reads global memory)
 ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
@@ -451,13 +465,17 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
     }
 }
 #else
+template <bool SM = false>
 ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
     int sp = 0;
     uint32_t idx = 0, offset, len_axis;
+    const uint32_t sbase = SM ? snodes_base() : 0u;
+    uint32_t nb = c.negbits;
+    if (SM) asm volatile("" : "+r"(nb));            // keep the three sign bits in a register: rebuilding them from 1/d costs ten instructions per push
     {
-        const Node8 n = ld_node(sc.nodes);
+        const Node8 n = ld_node_x<SM>(sc, sbase, 0u);
         float lo;
         if (!slab_cull(n.q0, n.q1, r, c, lo)) return;
         offset = __float_as_uint(n.q1.z); len_axis = __float_as_uint(n.q1.w);
@@ -467,10 +485,10 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
         // ---- interior nodes: cull both children (first child = idx+1, second = idx+offset) conservatively
         while ((len_axis >> 2) == 0) {
             const uint32_t ia = idx + 1, ib = idx + offset;
-            const Node8 a = ld_node(sc.nodes + 2 * ia), b = ld_node(sc.nodes + 2 * ib);
+            const Node8 a = ld_node_x<SM>(sc, sbase, ia), b = ld_node_x<SM>(sc, sbase, ib);
             float la, lb;
             const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
-            const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
+            const bool first_b = SM ? ((nb >> len_axis) & 1u) != 0u : ((c.negbits >> (len_axis & 3u)) & 1u) != 0u;   // dir_is_neg[split_axis]: second child first (interior: len_axis == axis)
             if (ha && hb) {
                 ARN_STACK_CHECK(sp, ARN_STACK);
                 stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
@@ -479,18 +497,18 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             } else if (ha || hb) {
                 idx = ha ? ia : ib;
                 offset = __float_as_uint(ha ? a.q1.z : b.q1.z); len_axis = __float_as_uint(ha ? a.q1.w : b.q1.w);
-            } else if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) { alive = false; break; }
+            } else if (!trav_pop<SM>(sc, r, stack, sp, idx, offset, len_axis, sbase)) { alive = false; break; }
         }
         if (!alive) return;
         // ---- leaf: the reference's own slab test (its bounds come back from L1), then the primitives
         {
-            const Node8 n = ld_node(sc.nodes + 2 * idx);
+            const Node8 n = ld_node_x<SM>(sc, sbase, idx);
             float t0;
             if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
                 if (leaf_prims(sc, offset, len_axis >> 2, r, h, any)) return;
             }
         }
-        if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
+        if (!trav_pop<SM>(sc, r, stack, sp, idx, offset, len_axis, sbase)) return;
     }
 }
 #endif
@@ -676,6 +694,7 @@ ARN_DEV void traverse8(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
 #define ARN_TRAV_COUNTED 1
 #define ARN_TRAV_WIDE 2
 #define ARN_TRAV_CW8 3
+#define ARN_TRAV_BINARY_SMEM 4        /* binary walk, node array staged in shared memory by the calling kernel (k_trace only) */
 // out-of-line exact walks for the rare rays the conservative test does not cover (one copy per kernel)
 ARN_NOINL void traverse_exact_closest(const DevScene& sc, TravRay& r, HitRec& h) { traverse<false, false>(sc, r, h, nullptr); }
 ARN_NOINL void traverse_exact_any(const DevScene& sc, TravRay& r, HitRec& h) { traverse<true, false>(sc, r, h, nullptr); }
@@ -696,7 +715,8 @@ ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr,
     CullRay c; cull_setup(sc, r, c);
     if (MODE == ARN_TRAV_CW8) traverse8(sc, r, c, h, any);
     else if (MODE == ARN_TRAV_WIDE) traverse4(sc, r, c, h, any);
-    else traverse2(sc, r, c, h, any);
+    else if (MODE == ARN_TRAV_BINARY_SMEM) traverse2<true>(sc, r, c, h, any);
+    else traverse2<false>(sc, r, c, h, any);
 }
 
 }  // namespace arn

@@ -222,8 +222,15 @@ template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 #ifndef ARN_TRAV_MINB_WIDE
 #define ARN_TRAV_MINB_WIDE (ARN_TRAV_MINB + 1)
 #endif
-__global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == ARN_TRAV_CW8) ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
+// ARN_TRAV_BINARY_SMEM (trees of <= ARN_SMEM_NODE_BYTES): ONE block of ARN_BLOCK_SMEM threads per SM stages the node array in dynamic
+// shared memory once per launch (the same number of resident warps as three 256-thread blocks, one copy of the nodes instead of three)
+#ifndef ARN_BLOCK_SMEM
+#define ARN_BLOCK_SMEM 768
+#endif
+#define ARN_TRACE_BLOCK(MODE) ((MODE) == ARN_TRAV_BINARY_SMEM ? ARN_BLOCK_SMEM : ARN_BLOCK)
+__global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY_SMEM ? 1 : ((MODE == ARN_TRAV_WIDE || MODE == ARN_TRAV_CW8) ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB)) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
+    constexpr int BLOCK = ARN_TRACE_BLOCK(MODE);
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par; const int first = j == 0;
     const uint32_t n_ext = *cnt_active(q.counts, par), n_sh = *cnt_nee(q.counts, par, 1), n_mis = *cnt_nee(q.counts, par, 2);
@@ -235,13 +242,17 @@ __global__ void __launch_bounds__(ARN_BLOCK, (MODE == ARN_TRAV_WIDE || MODE == A
     const uint32_t* __restrict__ ids = q.active[cur];
     // staging state lives in shared memory, not in registers: the traversal below is register-bound (occupancy) and
     // would otherwise carry five row pointers and five fill counters through every walk
-    __shared__ uint32_t stage_rows[ARN_NCLS][ARN_BLOCK / 32][64];
-    __shared__ uint32_t stage_fill[ARN_NCLS][ARN_BLOCK / 32];
+    __shared__ uint32_t stage_rows[ARN_NCLS][BLOCK / 32][64];
+    __shared__ uint32_t stage_fill[ARN_NCLS][BLOCK / 32];
     if ((threadIdx.x & 31u) == 0) {
 #pragma unroll
         for (int c = 0; c < ARN_NCLS; c++) stage_fill[c][threadIdx.x >> 5] = 0;
     }
     __syncwarp();
+    if (MODE == ARN_TRAV_BINARY_SMEM && blockIdx.x * blockDim.x < s3) {       // a block without rays skips the copy (block-uniform)
+        for (uint32_t i = threadIdx.x; i < 2u * sc.n_nodes; i += blockDim.x) arn_snodes[i] = __ldg(&sc.nodes[i]);
+        __syncthreads();
+    }
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {
         // the three kinds of query share ONE inlined walk (instruction-cache footprint): kind and `any` are warp-uniform
         const uint32_t kind = gi < s1 ? 0u : (gi < s2 ? 1u : 2u);                 // 0 path ray, 1 shadow ray, 2 BSDF-sampled light ray
