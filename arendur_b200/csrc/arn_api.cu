@@ -364,7 +364,7 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
                      + align256((size_t)d->n_spheres * sizeof(arn_sphere)) + align256((size_t)d->n_triangles * 12) + align256((size_t)d->n_vertices * 12) * 2
                      + align256((size_t)d->n_vertices * 8) + align256((size_t)d->n_triangles * 4) + align256((size_t)d->n_meshes * sizeof(arn_mesh))
                      + align256((size_t)d->n_materials * sizeof(arn_material)) + align256((size_t)d->n_prims * 4) + align256((size_t)d->n_lights * 4) * 2
-                     + align256((size_t)d->n_analytic_lights * sizeof(arn_analytic_light)) + align256(((size_t)d->n_lights + 1) * 4) + 4096
+                     + align256((size_t)d->n_analytic_lights * sizeof(arn_analytic_light)) + align256(((size_t)d->n_lights + 1) * 4) + 4096 + align256(ARN_SMEM_NODE_BYTES)
                      + align256((size_t)d->n_textures * sizeof(arn_texture)) + align256((size_t)d->n_texel_floats * 4);
         void* pool = nullptr;
         cudaError_t ce = cudaMalloc(&pool, total);
@@ -382,6 +382,37 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     if ((rc = dev_upload(s, d->nodes, d->n_nodes, &dn)) != ARN_OK) return fail(rc);
     s->dev.nodes = (const float4*)dn;
     lap("node upload");
+    s->dev.pairs = nullptr; s->dev.n_pairs = 0; s->dev.root_axis = 0;
+    std::vector<float> rec;                             // staging of the pair records: lives until the upload's final sync
+    if (d->n_nodes >= 3 && (d->nodes[0].len_axis >> 2) == 0 && ((size_t)d->n_nodes - 1) / 2 * ARN_PAIR_BYTES <= ARN_SMEM_NODE_BYTES) {
+        // pair records of a small tree (kernels/traverse.cuh, traverse2p): one per interior node, in node order
+        const uint32_t n_int = (d->n_nodes - 1) / 2;
+        std::vector<uint32_t> pair_of(d->n_nodes, 0u);
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < d->n_nodes; i++) if ((d->nodes[i].len_axis >> 2) == 0) pair_of[i] = k++;
+        if (k == n_int) {                                   // a full binary tree, as validated above
+            rec.assign((size_t)n_int * (ARN_PAIR_BYTES / 4), 0.f);
+            for (uint32_t i = 0; i < d->n_nodes; i++) {
+                const arn_node& nd = d->nodes[i];
+                if ((nd.len_axis >> 2) != 0) continue;
+                float* r = &rec[(size_t)pair_of[i] * (ARN_PAIR_BYTES / 4)];
+                const uint32_t ch[2] = {i + 1, i + nd.offset};
+                for (int cidx = 0; cidx < 2; cidx++) {
+                    const arn_node& cn = d->nodes[ch[cidx]];
+                    for (int a = 0; a < 3; a++) {           // axis block: (A.min, A.max, B.min, B.max) then the same with min / max swapped
+                        float* q = r + a * 8 + cidx * 2;
+                        q[0] = cn.bmin[a]; q[1] = cn.bmax[a]; q[4] = cn.bmax[a]; q[5] = cn.bmin[a];
+                    }
+                    const bool leaf = (cn.len_axis >> 2) != 0;
+                    const uint32_t w0 = leaf ? cn.offset : pair_of[ch[cidx]] * ARN_PAIR_BYTES, w1 = cn.len_axis;
+                    for (int rep = 0; rep < 2; rep++) { std::memcpy(r + 24 + rep * 4 + cidx * 2, &w0, 4); std::memcpy(r + 25 + rep * 4 + cidx * 2, &w1, 4); }
+                }
+            }
+            const float4* dp = nullptr;
+            if ((rc = dev_upload(s, (const float4*)rec.data(), rec.size() / 4, &dp)) != ARN_OK) return fail(rc);
+            s->dev.pairs = dp; s->dev.n_pairs = n_int; s->dev.root_axis = d->nodes[0].len_axis & 3u;
+        }
+    }
     {   // 4-wide collapse on the device (kernels/wide_build.cuh; layout: kernels/traverse.cuh, traverse4)
         auto is_leaf = [&](uint32_t i) { return (d->nodes[i].len_axis >> 2) != 0; };
         arn_node root = d->nodes[0];
@@ -730,8 +761,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const int np = (int)std::min<unsigned long long>((unsigned long long)pipes_wanted, n_waves);
     const bool wide = use_wide(s), cw8 = use_cw8(s);
     const bool refill = c->opt_refill && !wide && !cw8 && !c->opt_count;
-    const size_t node_bytes = (size_t)s->dev.n_nodes * sizeof(arn_node);
-    const bool smem_nodes = !c->opt_smem_off && !wide && !cw8 && !refill && !c->opt_count && node_bytes <= ARN_SMEM_NODE_BYTES;
+    const size_t node_bytes = (size_t)s->dev.n_pairs * ARN_PAIR_BYTES;
+    const bool smem_nodes = !c->opt_smem_off && !wide && !cw8 && !refill && !c->opt_count && s->dev.pairs != nullptr;
     const bool textured = s->dev.n_textures != 0;
     for (int i = 0; i < np; i++) {
         int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;

@@ -53,6 +53,8 @@ struct DevScene {
     float3 absmax;                           // max(|bmin|, |bmax|) of the root per axis: scale of the conservative slab test's slack
     const uint4* __restrict__ cw8;           // compressed 8-wide nodes, 8 uint4 each (kernels/cw8_build.cuh); null unless built
     const float4* __restrict__ blob;         // leaf blob of the 8-wide walk: [exact bounds, count] + primitive records per leaf
+    const float4* __restrict__ pairs;        // pair records of a small tree (traverse2p), 8 float4 per interior node; null when the tree is too large
+    uint32_t n_pairs, root_axis;
     const arn_texture* __restrict__ textures;   // image textures (N4); null without
     const float* __restrict__ texels;
     uint32_t n_textures;
@@ -154,18 +156,6 @@ ARN_DEV Node8 ld_node(const float4* __restrict__ p) {      // one 256-bit load p
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(n.q0.x), "=f"(n.q0.y), "=f"(n.q0.z), "=f"(n.q0.w), "=f"(n.q1.x), "=f"(n.q1.y), "=f"(n.q1.z), "=f"(n.q1.w) : "l"(p));
     return n;
-}
-// Small trees (ARN_TRAV_BINARY_SMEM): the whole node array is staged in dynamic shared memory by the block, a node fetch is two
-// LDS.128 (~25 cycles, flat) instead of an L1 hit / L2 round trip on the walk's dependent fetch -> test -> branch chain.
-extern __shared__ __align__(16) float4 arn_snodes[];
-// `sbase`: the shared-window address of arn_snodes, computed once per ray and kept in a register (left to the compiler, the
-// window base is rebuilt from SR_CgaCtaId with four uniform-pipe instructions in front of every fetch)
-ARN_DEV uint32_t snodes_base() { uint32_t b = (uint32_t)__cvta_generic_to_shared(arn_snodes); asm volatile("" : "+r"(b)); return b; }
-ARN_DEV float4 lds128(uint32_t addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; }
-template <bool SM>
-ARN_DEV Node8 ld_node_x(const DevScene& sc, uint32_t sbase, uint32_t idx) {
-    if (SM) { Node8 n; n.q0 = lds128(sbase + idx * 32u); n.q1 = lds128(sbase + idx * 32u + 16u); return n; }
-    return ld_node(sc.nodes + 2 * (size_t)idx);
 }
 ARN_DEV float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }   // FMNMX3
 ARN_DEV float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
@@ -300,15 +290,14 @@ ARN_DEV void sphere_slot(const DevScene& sc, uint32_t comp, TravRay& r, HitRec& 
 // component/mod.rs:35-38, so the boolean is identical).
 // COUNT: accumulate nodes/primitives tested into ctr[0..2] (for the algorithmic-bytes figure).
 // pop the next stack entry whose entry distance is still below tmax; false when the stack is empty
-template <bool SM = false>
 ARN_DEV bool trav_pop(const DevScene& sc, const TravRay& r, const uint2* stack, int& sp,
-                      uint32_t& idx, uint32_t& offset, uint32_t& len_axis, uint32_t sbase = 0u) {
+                      uint32_t& idx, uint32_t& offset, uint32_t& len_axis) {
     for (;;) {
         if (sp == 0) return false;
         uint2 e = stack[--sp];
         if (__uint_as_float(e.y) < r.tmax) {
             idx = e.x;
-            float4 n1 = SM ? lds128(sbase + idx * 32u + 16u) : __ldg(&sc.nodes[2 * idx + 1]);
+            float4 n1 = __ldg(&sc.nodes[2 * idx + 1]);
             offset = __float_as_uint(n1.z); len_axis = __float_as_uint(n1.w);
             return true;
         }
@@ -409,7 +398,6 @@ ARN_DEV bool leaf_prims(const DevScene& sc, uint32_t first, uint32_t count, Trav
 // the reference's order.  What the walk does between the two with a tmax the postponed leaf might have shortened is interior
 // culling only, which merely has to be conservative (a larger tmax culls less); every leaf still takes the exact test with the
 // tmax current at ITS turn.  The warp switches phases half as often and both phases run with more lanes.
-template <bool SM = false>          // (the speculative variant always reads global memory)
 ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
@@ -465,17 +453,13 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
     }
 }
 #else
-template <bool SM = false>
 ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     uint2 stack[ARN_STACK];
     int sp = 0;
     uint32_t idx = 0, offset, len_axis;
-    const uint32_t sbase = SM ? snodes_base() : 0u;
-    uint32_t nb = c.negbits;
-    if (SM) asm volatile("" : "+r"(nb));            // keep the three sign bits in a register: rebuilding them from 1/d costs ten instructions per push
     {
-        const Node8 n = ld_node_x<SM>(sc, sbase, 0u);
+        const Node8 n = ld_node(sc.nodes);
         float lo;
         if (!slab_cull(n.q0, n.q1, r, c, lo)) return;
         offset = __float_as_uint(n.q1.z); len_axis = __float_as_uint(n.q1.w);
@@ -485,10 +469,10 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
         // ---- interior nodes: cull both children (first child = idx+1, second = idx+offset) conservatively
         while ((len_axis >> 2) == 0) {
             const uint32_t ia = idx + 1, ib = idx + offset;
-            const Node8 a = ld_node_x<SM>(sc, sbase, ia), b = ld_node_x<SM>(sc, sbase, ib);
+            const Node8 a = ld_node(sc.nodes + 2 * ia), b = ld_node(sc.nodes + 2 * ib);
             float la, lb;
             const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
-            const bool first_b = SM ? ((nb >> len_axis) & 1u) != 0u : ((c.negbits >> (len_axis & 3u)) & 1u) != 0u;   // dir_is_neg[split_axis]: second child first (interior: len_axis == axis)
+            const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
             if (ha && hb) {
                 ARN_STACK_CHECK(sp, ARN_STACK);
                 stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
@@ -497,21 +481,137 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             } else if (ha || hb) {
                 idx = ha ? ia : ib;
                 offset = __float_as_uint(ha ? a.q1.z : b.q1.z); len_axis = __float_as_uint(ha ? a.q1.w : b.q1.w);
-            } else if (!trav_pop<SM>(sc, r, stack, sp, idx, offset, len_axis, sbase)) { alive = false; break; }
+            } else if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) { alive = false; break; }
         }
         if (!alive) return;
         // ---- leaf: the reference's own slab test (its bounds come back from L1), then the primitives
         {
-            const Node8 n = ld_node_x<SM>(sc, sbase, idx);
+            const Node8 n = ld_node(sc.nodes + 2 * idx);
             float t0;
             if (slab(n.q0, n.q1, r, t0) && t0 < r.tmax) {
                 if (leaf_prims(sc, offset, len_axis >> 2, r, h, any)) return;
             }
         }
-        if (!trav_pop<SM>(sc, r, stack, sp, idx, offset, len_axis, sbase)) return;
+        if (!trav_pop(sc, r, stack, sp, idx, offset, len_axis)) return;
     }
 }
 #endif
+
+
+// ---- binary walk of a SMALL tree from shared memory (ARN_TRAV_BINARY_SMEM; k_trace stages sc.pairs) -----------------------
+// Cache-resident trees are bound by instruction issue in the interior loop (profiles/r02_trace_hotloop_source.txt), so the
+// records the loop reads are laid out for the fewest instructions per step — and for the fewest SHARED-MEMORY instructions: a first
+// layout with one 8-byte load per (child, axis) ran fewer instructions and was slower (8 LDS per step against 4).
+// One PAIR RECORD per interior node, 128 bytes; A = first child (node + 1), B = second child (node + offset):
+//     +0   x, direction >= 0: (A.min, A.max, B.min, B.max)     +16  x, direction < 0: (A.max, A.min, B.max, B.min)
+//     +32  y, ...                                               +48  y, ...
+//     +64  z, ...                                               +80  z, ...
+//     +96  A.w0, A.w1, B.w0, B.w1                               +112 the same four words again
+//          w1 = the child's len_axis; w0 = byte offset of the child's own pair record (interior child) or its first primitive slot (leaf child)
+// A lane reads the (near, far) planes of BOTH children on one axis with ONE 16-byte load at +0 or +16 according to the sign of
+// 1/d — no selects — and two packed FFMA2 (sm_100 fma.rn.f32x2) turn them into the conservative (entry, exit) distances of
+// slab_cull: the same fma(plane, 1/d, oi0 / oi1) values, so the walk visits exactly what traverse2 visits.  The three per-ray
+// bases (shared window + axis block + 16 for a negative direction) are all the addressing state; the reference words are stored
+// twice so that they too can be read relative to the x base.  Stack entry = (record offset | child slot, entry distance); a
+// leaf's exact test reads its (near, far) pairs back from its parent's record and runs the reference's arithmetic on them (slab_nf).
+extern __shared__ __align__(16) float4 arn_spairs[];
+#define ARN_PAIR_BYTES 128u
+ARN_DEV float2 lds64(uint32_t addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); return v; }
+ARN_DEV float4 lds128(uint32_t addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; }
+ARN_DEV uint4 lds128u(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+ARN_DEV uint2 lds64u(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+ARN_DEV unsigned long long pack2(float lo, float hi) { unsigned long long v; asm("mov.b64 %0, {%1,%2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
+ARN_DEV float2 ffma2(float2 a, unsigned long long b, unsigned long long c) {           // (a.x * b.lo + c.lo, a.y * b.hi + c.hi), each an IEEE fma.rn
+    unsigned long long d; float2 v;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(a.x, a.y)), "l"(b), "l"(c));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(d));
+    return v;
+}
+// BBox3f::intersect_ray_cached (bbox.rs:549-580) on planes already ordered by the sign of 1/d: slab() after its selects
+ARN_DEV bool slab_nf(const float2 X, const float2 Y, const float2 Z, const TravRay& r, float& t0_out) {
+    const float k = 1.f + 2.f * gamma_n(3.f);
+    const float3 co = r.co;
+    float t0 = (X.x - co.x) * r.inv.x, t1 = (X.y - co.x) * r.inv.x;
+    float ty0 = (Y.x - co.y) * r.inv.y, ty1 = (Y.y - co.y) * r.inv.y;
+    float tz0 = (Z.x - co.z) * r.inv.z, tz1 = (Z.y - co.z) * r.inv.z;
+    t1 *= k; ty1 *= k; tz1 *= k;
+    const bool miss_xy = (t0 > ty1) | (ty0 > t1);
+    t0 = ty0 > t0 ? ty0 : t0;
+    t1 = ty1 < t1 ? ty1 : t1;
+    const bool miss_z = (t0 > tz1) | (tz0 > t1);
+    t0 = tz0 > t0 ? tz0 : t0;
+    t1 = tz1 < t1 ? tz1 : t1;
+    t0_out = t0;
+    return !miss_xy & !miss_z & (t1 > 0.f);
+}
+// 4-byte stack entries: the entry distance truncated to its upper 16 bits (it is >= 0, so truncation rounds DOWN: the pop-time
+// re-check stays conservative) over (record index << 1 | child slot) — a warp's stack level is one 128-byte line of local memory
+ARN_DEV uint32_t pair_entry(uint32_t ref, float lo) { return (__float_as_uint(lo) & 0xffff0000u) | (ref >> 6) | (ref & 1u); }      // ref = record offset (multiple of 128) | slot
+ARN_DEV bool trav_pop_p(const TravRay& r, const uint32_t* stack, int& sp, uint32_t bx, uint32_t& ref, uint32_t& w0, uint32_t& w1) {
+    for (;;) {
+        if (sp == 0) return false;
+        const uint32_t e = stack[--sp];
+        if (__uint_as_float(e & 0xffff0000u) < r.tmax) {
+            ref = ((e & 0xfffeu) << 6) | (e & 1u);
+            const uint2 m = lds64u(bx + (ref & ~15u) + 96u + (ref & 1u) * 8u);
+            w0 = m.x; w1 = m.y;
+            return true;
+        }
+    }
+}
+ARN_DEV void traverse2p(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
+    h.prim = -1; h.a = h.b = h.c = 0.f;
+    uint32_t stack[ARN_STACK];
+    int sp = 0;
+    {
+        float lo;
+        if (!slab_cull(sc.root0, sc.root1, r, c, lo)) return;
+    }
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(arn_spairs);
+    uint32_t nb = c.negbits;
+    uint32_t bx = sbase + ((nb & 1u) ? 16u : 0u), by = sbase + 32u + ((nb & 2u) ? 16u : 0u), bz = sbase + 64u + ((nb & 4u) ? 16u : 0u);
+    asm volatile("" : "+r"(nb), "+r"(bx), "+r"(by), "+r"(bz));     // kept in registers: left alone, the compiler rebuilds them in front of every use
+    const unsigned long long ix = pack2(r.inv.x, r.inv.x), iy = pack2(r.inv.y, r.inv.y), iz = pack2(r.inv.z, r.inv.z);
+    const unsigned long long ox = pack2(c.oi0.x, c.oi1.x), oy = pack2(c.oi0.y, c.oi1.y), oz = pack2(c.oi0.z, c.oi1.z);
+    uint32_t w0 = 0u, w1 = sc.root_axis, ref = 0u;              // the root is interior (the kernel is not chosen otherwise); its record is the first
+    for (;;) {
+        bool alive = true;
+        while ((w1 >> 2) == 0u) {
+            const uint32_t pa = w0, px = bx + pa;
+            uint32_t fb;                                         // dir_is_neg[split_axis] (interior: w1 == axis), taken BEFORE the loads so that
+            asm volatile("shr.u32 %0, %1, %2;" : "=r"(fb) : "r"(nb), "r"(w1));    // a spilled `nb` comes back under their latency, not after the test
+            const float4 X = lds128(px), Y = lds128(by + pa), Z = lds128(bz + pa);
+            const uint4 m = lds128u(px + 96u);
+            const uint2 ma = make_uint2(m.x, m.y), mb = make_uint2(m.z, m.w);
+            const float2 tax = ffma2(make_float2(X.x, X.y), ix, ox), tay = ffma2(make_float2(Y.x, Y.y), iy, oy), taz = ffma2(make_float2(Z.x, Z.y), iz, oz);
+            const float2 tbx = ffma2(make_float2(X.z, X.w), ix, ox), tby = ffma2(make_float2(Y.z, Y.w), iy, oy), tbz = ffma2(make_float2(Z.z, Z.w), iz, oz);
+            const float la = fmax3(tax.x, tay.x, fmaxf(taz.x, 0.f)), ua = fmin3(tax.y, tay.y, fminf(taz.y, r.tmax));
+            const float lb = fmax3(tbx.x, tby.x, fmaxf(tbz.x, 0.f)), ub = fmin3(tbx.y, tby.y, fminf(tbz.y, r.tmax));
+            const bool ha = la <= ua, hb = lb <= ub;
+            const bool first_b = (fb & 1u) != 0u;                // second child first
+            if (ha && hb) {
+                ARN_STACK_CHECK(sp, ARN_STACK);
+                stack[sp++] = pair_entry(pa | (first_b ? 0u : 1u), first_b ? la : lb);
+                ref = pa | (first_b ? 1u : 0u);
+                w0 = first_b ? mb.x : ma.x; w1 = first_b ? mb.y : ma.y;
+            } else if (ha || hb) {
+                ref = pa | (ha ? 0u : 1u);
+                w0 = ha ? ma.x : mb.x; w1 = ha ? ma.y : mb.y;
+            } else if (!trav_pop_p(r, stack, sp, bx, ref, w0, w1)) { alive = false; break; }
+        }
+        if (!alive) return;
+        // ---- leaf: the reference's own slab test on its bounds, then the primitives
+        {
+            const uint32_t lp = (ref & ~15u) + (ref & 1u) * 8u;
+            const float2 X = lds64(bx + lp), Y = lds64(by + lp), Z = lds64(bz + lp);
+            float t0;
+            if (slab_nf(X, Y, Z, r, t0) && t0 < r.tmax) {
+                if (leaf_prims(sc, w0, w1 >> 2, r, h, any)) return;
+            }
+        }
+        if (!trav_pop_p(r, stack, sp, bx, ref, w0, w1)) return;
+    }
+}
 
 // ---- 4-wide walk (trees that do not fit the caches) ------------------------------------------------------------
 // The wide tree is the binary tree with every second level removed: wide node = (children of the first child, children
@@ -694,7 +794,7 @@ ARN_DEV void traverse8(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
 #define ARN_TRAV_COUNTED 1
 #define ARN_TRAV_WIDE 2
 #define ARN_TRAV_CW8 3
-#define ARN_TRAV_BINARY_SMEM 4        /* binary walk, node array staged in shared memory by the calling kernel (k_trace only) */
+#define ARN_TRAV_BINARY_SMEM 4        /* binary walk over pair records staged in shared memory by the calling kernel (k_trace only) */
 // out-of-line exact walks for the rare rays the conservative test does not cover (one copy per kernel)
 ARN_NOINL void traverse_exact_closest(const DevScene& sc, TravRay& r, HitRec& h) { traverse<false, false>(sc, r, h, nullptr); }
 ARN_NOINL void traverse_exact_any(const DevScene& sc, TravRay& r, HitRec& h) { traverse<true, false>(sc, r, h, nullptr); }
@@ -715,8 +815,8 @@ ARN_DEV void trace_ray(const DevScene& sc, TravRay& r, HitRec& h, uint32_t* ctr,
     CullRay c; cull_setup(sc, r, c);
     if (MODE == ARN_TRAV_CW8) traverse8(sc, r, c, h, any);
     else if (MODE == ARN_TRAV_WIDE) traverse4(sc, r, c, h, any);
-    else if (MODE == ARN_TRAV_BINARY_SMEM) traverse2<true>(sc, r, c, h, any);
-    else traverse2<false>(sc, r, c, h, any);
+    else if (MODE == ARN_TRAV_BINARY_SMEM) traverse2p(sc, r, c, h, any);
+    else traverse2(sc, r, c, h, any);
 }
 
 }  // namespace arn

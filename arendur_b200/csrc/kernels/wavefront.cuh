@@ -222,8 +222,8 @@ template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 #ifndef ARN_TRAV_MINB_WIDE
 #define ARN_TRAV_MINB_WIDE (ARN_TRAV_MINB + 1)
 #endif
-// ARN_TRAV_BINARY_SMEM (trees of <= ARN_SMEM_NODE_BYTES): ONE block of ARN_BLOCK_SMEM threads per SM stages the node array in dynamic
-// shared memory once per launch (the same number of resident warps as three 256-thread blocks, one copy of the nodes instead of three)
+// ARN_TRAV_BINARY_SMEM (trees whose pair records fit ARN_SMEM_NODE_BYTES, traverse2p): ONE block of ARN_BLOCK_SMEM threads per SM stages the
+// records in dynamic shared memory once per launch (the same number of resident warps as three 256-thread blocks, one copy instead of three)
 #ifndef ARN_BLOCK_SMEM
 #define ARN_BLOCK_SMEM 768
 #endif
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY
     }
     __syncwarp();
     if (MODE == ARN_TRAV_BINARY_SMEM && blockIdx.x * blockDim.x < s3) {       // a block without rays skips the copy (block-uniform)
-        for (uint32_t i = threadIdx.x; i < 2u * sc.n_nodes; i += blockDim.x) arn_snodes[i] = __ldg(&sc.nodes[i]);
+        for (uint32_t i = threadIdx.x; i < (ARN_PAIR_BYTES / 16u) * sc.n_pairs; i += blockDim.x) arn_spairs[i] = __ldg(&sc.pairs[i]);
         __syncthreads();
     }
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {

@@ -390,9 +390,9 @@ int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_fil
                                        with the binary nodes; same bits; also env ARN_REFILL */
 #define ARN_OPT_BVH_WIDTH       3   /* 0 auto (default), 2 binary nodes, 4 the 4-wide collapse, 8 the compressed 8-wide collapse (set BEFORE the
                                        upload for trees below 2^20 nodes: the 8-wide nodes are built at upload); same bits */
-#define ARN_OPT_SMEM_NODES      6   /* 0 auto (default): trees whose nodes fit ARN_SMEM_NODE_BYTES are walked by k_trace from a copy in shared
-                                       memory; 1: never (also env ARN_SMEM_NODES=0); same bits */
-#define ARN_SMEM_NODE_BYTES (96 * 1024)
+#define ARN_OPT_SMEM_NODES      6   /* 0 auto (default): trees with up to ARN_SMEM_NODE_BYTES / 112 interior nodes are walked by k_trace from
+                                       pair records staged in shared memory; 1: never (also env ARN_SMEM_NODES=0); same bits */
+#define ARN_SMEM_NODE_BYTES (160 * 1024)
 int arn_ctx_set_option(arn_ctx* ctx, int option, long long value);
 
 int arn_ctx_synchronize(arn_ctx* ctx);
