@@ -602,3 +602,33 @@ def test_random_scenes_with_affine_sphere_instances_are_bit_exact(ctx, seed):
     _, ost, _ = osc.render_pt(cam, film, smp, prm)
     assert (st.extend_rays, st.shadow_rays, st.mis_rays, st.invalid_samples) == (ost.extend_rays, ost.shadow_rays, ost.mis_rays, ost.invalid_samples)
     sc.close(); osc.close()
+
+
+@pytest.mark.parametrize("scene", ["cornell", "box972", "box2352"])
+def test_shared_memory_pair_walk_is_bit_exact(ctx, cornell_small, scene):
+    """Small trees are walked by k_trace from pair records staged in shared memory (traverse2p: sign-selected LDS.128 per axis,
+    packed FFMA2 conservative test, 4-byte stack entries).  Same leaves in the same order as the global-memory walk: every
+    camera sample's radiance and the ray counts are those of ARN_OPT_SMEM_NODES = 1 (never) and of the oracle.  box972 fits
+    the shared-memory budget (734 interior nodes), box2352 (1783) does not and takes the global-memory walk either way."""
+    if scene == "cornell":
+        hs, cam, film, smp, prm = cornell_small
+    else:
+        hs, cam, film, smp, prm = scenes.c4_box_scene(cells=9 if scene == "box972" else 14, res=64, sampledx=2, sampledy=2)
+    d = hs.desc()
+    assert (((d.n_nodes - 1) // 2) * 128 <= L.ARN_SMEM_NODE_BYTES) == (scene != "box2352")
+    sc = ctx.upload(d); osc = O.OracleScene(d)
+    f0, rad0, st0 = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 5000); ctx.set_option(L.ARN_OPT_PIPELINES, 1)      # ragged waves, thin launches
+    try:
+        f2, rad2, st2 = sc.render_pt_samples(cam, film, smp, prm)
+        ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0); ctx.set_option(L.ARN_OPT_PIPELINES, 0)
+        ctx.set_option(L.ARN_OPT_SMEM_NODES, 1)
+        f1, rad1, st1 = sc.render_pt_samples(cam, film, smp, prm)
+    finally:
+        ctx.set_option(L.ARN_OPT_SMEM_NODES, 0); ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0); ctx.set_option(L.ARN_OPT_PIPELINES, 0)
+    assert np.array_equal(rad0, rad1) and np.array_equal(rad0, rad2)
+    assert (st0.extend_rays, st0.shadow_rays, st0.mis_rays) == (st1.extend_rays, st1.shadow_rays, st1.mis_rays) == (st2.extend_rays, st2.shadow_rays, st2.mis_rays)
+    assert np.allclose(f0, f1, rtol=1e-5, atol=1e-6)
+    _, orad = osc.render_pt_samples(cam, film, smp, prm)
+    assert np.array_equal(rad0[..., :3], orad[..., :3])
+    sc.close(); osc.close()
