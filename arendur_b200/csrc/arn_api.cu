@@ -161,10 +161,13 @@ int ensure_trace_buf(arn_ctx* ctx, arn_ctx::Pipe* c, size_t wave_cap) {
     return ARN_OK;
 }
 
-size_t wave_capacity_default(int pipes, bool big_scene) {
+size_t wave_capacity_default(int pipes, bool big_scene, bool smem_walk, unsigned long long total) {
     const char* e = std::getenv("ARN_WAVE");
     if (e) { long v = std::atol(e); if (v >= 1024) return (size_t)v; }
     if (big_scene && pipes >= 6) return (size_t)1 << 17;
+    // the shared-memory walk stages the pair records once per launch and block: larger launches amortise it (C3, 64 spp, 4 pipelines:
+    // 2^19 253.2 ms, 2^20 244.2, 2^21 247.9; tools/wave_sweep.py) — as long as every pipeline still gets two waves
+    if (smem_walk && total >= ((unsigned long long)pipes << 21)) return (size_t)1 << 20;
     return pipes >= 3 ? (size_t)1 << 19 : (size_t)1 << 20;
 }
 
@@ -754,7 +757,8 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     // large scenes (DRAM-latency-bound trace) prefer more and smaller waves: C4 4 x 2^19 191.7 ms, 8 x 2^18 188.8, 8 x 2^17 185.9, 8 x 2^16 190.4
     const bool big = s->dev.n_nodes >= ARN_WIDE_MIN_NODES;
     const int pipes_wanted = c->opt_count ? 1 : (c->opt_pipes ? c->opt_pipes : (big ? 8 : 4));
-    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default(pipes_wanted, big);
+    const bool smem_walk = !c->opt_smem_off && !use_wide(s) && !use_cw8(s) && !c->opt_refill && !c->opt_count && s->dev.pairs != nullptr;
+    size_t cap = c->opt_wave ? c->opt_wave : wave_capacity_default(pipes_wanted, big, smem_walk, total);
     if ((unsigned long long)cap > total) cap = (size_t)((total + ARN_BLOCK - 1) / ARN_BLOCK * ARN_BLOCK);
     const unsigned long long n_waves = (total + cap - 1) / cap;
     // per-kernel event timing needs serial launches: it is only taken with one pipeline (ARN_OPT_PIPELINES = 1)
@@ -762,7 +766,7 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
     const bool wide = use_wide(s), cw8 = use_cw8(s);
     const bool refill = c->opt_refill && !wide && !cw8 && !c->opt_count;
     const size_t node_bytes = (size_t)s->dev.n_pairs * ARN_PAIR_BYTES;
-    const bool smem_nodes = !c->opt_smem_off && !wide && !cw8 && !refill && !c->opt_count && s->dev.pairs != nullptr;
+    const bool smem_nodes = smem_walk;
     const bool textured = s->dev.n_textures != 0;
     for (int i = 0; i < np; i++) {
         int rc = ensure_wave(c, &c->pipes[i], cap); if (rc != ARN_OK) return rc;

@@ -459,7 +459,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "spp_per_step": spp_step, "tiles": f"{TILES[0]}x{TILES[1]}" + (f", each cut into {subdiv}x{subdiv} cells, cell -> rank (ix*k + jx + iy*k + jy) % N" if world > 1 else ""),
-                       "l2": "256 MB flush write between timed steps; wave buffers (4 x 124 MB) also exceed L2", "wave_pipelines": PIPELINES,
+                       "l2": "256 MB flush write between timed steps; wave buffers (4 pipelines x 124 MB, 248 MB when a rank has >= 8 waves of 2^20 samples per step) also exceed L2", "wave_pipelines": PIPELINES,
                        "film_reduce": "per step: arn_film_reduce (ncclReduce, sum to rank 0) of the step's films + arn_film_merge into the running film, inside the timed region" if world > 1 else "none (1 GPU)"},
             "spp_per_s": samples_all / (total_ms_max * 1e-3),
             "rays_per_sample": rays_all / max(1.0, samples_all),

@@ -382,7 +382,7 @@ int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_fil
 
 /* Context options. */
 #define ARN_OPT_COUNT_TRAVERSAL 1   /* value != 0: arn_render_pt* use instrumented extend kernels          */
-#define ARN_OPT_WAVE_CAPACITY   2   /* camera samples per wave; 0 = auto: 1 << 19 (1 << 17 for large trees, 1 << 20 with < 3 pipelines); env ARN_WAVE       */
+#define ARN_OPT_WAVE_CAPACITY   2   /* camera samples per wave; 0 = auto: 1 << 19 (1 << 17 for large trees, 1 << 20 with < 3 pipelines or when small trees are walked from shared memory and every pipeline gets two waves); env ARN_WAVE       */
 #define ARN_OPT_PIPELINES       4   /* 1..8 concurrent wave pipelines; 0 = auto (default): 4, or 8 for large trees (also env ARN_PIPES). Per-kernel
                                        timings in arn_stats (extend_ms, extend_bounce_ms) need serial launches and
                                        are only filled with 1                                                      */

@@ -1,8 +1,9 @@
 """profiles/roofline_traffic.json from an ncu metrics pass over bench.py ITSELF.
   ncu --metrics smsp__thread_inst_executed.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-      --clock-control none -k regex:k_trace -c 1152 --csv --log-file trace.csv python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline > bench.json
+      --clock-control none -k regex:k_trace -c 576 --csv --log-file trace.csv python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline > bench.json
   python tools/roofline_from_ncu.py trace.csv bench.json profiles/roofline_traffic.json
-The first 1152 k_trace launches are the 128 waves x 9 trace launches of warm-up step 0 (64 spp of the 1024^2 frame); its ray
+The first 576 k_trace launches are the 64 waves (2^20 samples each) x 9 trace launches of warm-up step 0 (64 spp of the 1024^2 frame;
+1152 launches while the waves were 2^19 samples); its ray
 count is bench.py's `rays_warmup_step0_rank0`."""
 import csv, json, sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
@@ -27,7 +28,7 @@ out = {
     "k_trace_launches": n, "rays": rays, "k_trace_ms_under_ncu": tot["gpu__time_duration.sum"] / 1e6,
     "fp32_issue_peak_thread_inst_per_s": 36285000000000.0,
     "source": f"ncu --metrics (thread / warp instructions, DRAM bytes, duration) --clock-control none over the first {n} k_trace launches of `python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline` "
-              "= warm-up step 0 of the bench command itself (C3, 64 spp of 1024x1024, 128 waves x 9 launches); issue peak: profiles/r01_fp32_issue.json; written by tools/roofline_from_ncu.py",
+              f"= warm-up step 0 of the bench command itself (C3, 64 spp of 1024x1024, {n // 9} waves x 9 launches); issue peak: profiles/r01_fp32_issue.json; written by tools/roofline_from_ncu.py",
 }
 json.dump(out, open(sys.argv[3], "w"), indent=1)
 print(json.dumps(out, indent=1))
