@@ -648,6 +648,10 @@ ARN_DEV bool trav_pop4(const DevScene& sc, const TravRay& r, const WideEntry* st
         }
     }
 }
+#ifndef ARN_WIDE_SPEC_PREFETCH
+#define ARN_WIDE_SPEC_PREFETCH 0
+#endif
+ARN_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec& h, const bool any) {
     h.prim = -1; h.a = h.b = h.c = 0.f;
     WideEntry stack[ARN_STACK4];
@@ -674,6 +678,14 @@ ARN_DEV void traverse4(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const uint32_t r0 = base + g1 + s1, r1 = base + g1 + (s1 ^ 1u), r2 = base + g2 + s2, r3 = base + g2 + (s2 ^ 1u);
             const Node8 na = ld_node(sc.wide + 2 * (size_t)r0), nb = ld_node(sc.wide + 2 * (size_t)r1);
             const Node8 nc = ld_node(sc.wide + 2 * (size_t)r2), nd = ld_node(sc.wide + 2 * (size_t)r3);
+#if ARN_WIDE_SPEC_PREFETCH
+            // speculative: ask L2 for the wide nodes of all interior children before their boxes are tested, so that the fetch of the
+            // child visited next overlaps the tests instead of following them
+            if ((__float_as_uint(na.q1.w) & 3u) == ARN_W_INNER) prefetch_l2(sc.wide + 8 * (size_t)__float_as_uint(na.q1.z));
+            if ((__float_as_uint(nb.q1.w) & 3u) == ARN_W_INNER) prefetch_l2(sc.wide + 8 * (size_t)__float_as_uint(nb.q1.z));
+            if ((__float_as_uint(nc.q1.w) & 3u) == ARN_W_INNER) prefetch_l2(sc.wide + 8 * (size_t)__float_as_uint(nc.q1.z));
+            if ((__float_as_uint(nd.q1.w) & 3u) == ARN_W_INNER) prefetch_l2(sc.wide + 8 * (size_t)__float_as_uint(nd.q1.z));
+#endif
             float ta, tb, tc, td;
             const bool ha = slab_cull(na.q0, na.q1, r, c, ta), hb = slab_cull(nb.q0, nb.q1, r, c, tb);
             const bool hc = slab_cull(nc.q0, nc.q1, r, c, tc), hd = slab_cull(nd.q0, nd.q1, r, c, td);
