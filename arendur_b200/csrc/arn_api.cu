@@ -208,6 +208,8 @@ int arn_ctx_create(int device, arn_ctx** out) {
     c->g_trace = grid_for(c, (const void*)k_trace<ARN_TRAV_BINARY>);
     c->g_trace_w = grid_for(c, (const void*)k_trace<ARN_TRAV_WIDE>);
     CTX_TRY( cudaFuncSetAttribute((const void*)k_trace<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
+    CTX_TRY( cudaFuncSetAttribute((const void*)k_closest_batch<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
+    CTX_TRY( cudaFuncSetAttribute((const void*)k_any_batch<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
     { const char* e = std::getenv("ARN_SMEM_NODES"); if (e) c->opt_smem_off = std::atoi(e) == 0; }
     c->g_trace_8 = grid_for(c, (const void*)k_trace<ARN_TRAV_CW8>);
     c->g_closest_8 = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_CW8>);
@@ -536,6 +538,7 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
 // the chain of dependent node fetches and wins once the tree no longer sits in L1 (C4: +10 %), the
 // binary walk issues fewer instructions per node and wins on cache-resident trees (Cornell: +15 %).
 #define ARN_WIDE_MIN_NODES (1u << 16)
+#define ARN_SMEM_BATCH_MIN ((size_t)1 << 15)      /* rays: below this a batched query does not amortise the copy of the pair records */
 static bool use_cw8(const arn_scene* s) {        // compressed 8-wide walk: trees far larger than the caches (needs the 8-wide nodes, built at upload)
     int w = s->ctx->opt_width;
     return s->dev.cw8 != nullptr && w == 8;
@@ -555,7 +558,10 @@ int arn_intersect_closest_dev(arn_scene* s, const void* rays_dev, size_t n, void
     int grid = (int)std::min<size_t>((size_t)(cw8 ? c->g_closest_8 : wide ? c->g_closest_w : c->g_closest), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    if (cw8) k_closest_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    // batches large enough to pay for staging the pair records of a small tree take the shared-memory walk, like k_trace
+    const bool smem = !c->opt_smem_off && !wide && !cw8 && s->dev.pairs != nullptr && n >= ARN_SMEM_BATCH_MIN;
+    if (smem) k_closest_batch<ARN_TRAV_BINARY_SMEM><<<(int)std::min<size_t>((size_t)c->sm_count, (n + ARN_BLOCK_SMEM - 1) / ARN_BLOCK_SMEM), ARN_BLOCK_SMEM, (size_t)s->dev.n_pairs * ARN_PAIR_BYTES, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
+    else if (cw8) k_closest_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     else if (wide) k_closest_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     else k_closest_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (arn_hit*)hits_dev, nullptr);
     CUDA_TRY(c, cudaGetLastError());
@@ -576,7 +582,9 @@ int arn_intersect_any_dev(arn_scene* s, const void* rays_dev, size_t n, void* ou
     int grid = (int)std::min<size_t>((size_t)(cw8 ? c->g_any_8 : wide ? c->g_any_w : c->g_any), (n + ARN_BLOCK - 1) / ARN_BLOCK);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { e0 = get_event(c, 0); e1 = get_event(c, 1); cudaEventRecord(e0, c->stream); }
-    if (cw8) k_any_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    const bool smem = !c->opt_smem_off && !wide && !cw8 && s->dev.pairs != nullptr && n >= ARN_SMEM_BATCH_MIN;
+    if (smem) k_any_batch<ARN_TRAV_BINARY_SMEM><<<(int)std::min<size_t>((size_t)c->sm_count, (n + ARN_BLOCK_SMEM - 1) / ARN_BLOCK_SMEM), ARN_BLOCK_SMEM, (size_t)s->dev.n_pairs * ARN_PAIR_BYTES, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
+    else if (cw8) k_any_batch<ARN_TRAV_CW8><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     else if (wide) k_any_batch<ARN_TRAV_WIDE><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     else k_any_batch<ARN_TRAV_BINARY><<<grid, ARN_BLOCK, 0, c->stream>>>(s->dev, (const arn_ray*)rays_dev, n, (uint8_t*)out_dev);
     CUDA_TRY(c, cudaGetLastError());

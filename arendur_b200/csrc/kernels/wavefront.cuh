@@ -216,6 +216,13 @@ ARN_DEV int shading_class(const arn_material& m) {
 //   path ray   : closest hit -> hit record; hits sorted into the per-material-class queues
 //   shadow ray : any hit (LightSample::occluded, lighting/mod.rs:125-133)      -> occluded[pid]
 //   light ray  : closest hit, `ptr::eq(light, hit)` and lsi.le(-wi) (scene.rs:146-155) -> mis_ok[pid]
+// ARN_TRAV_BINARY_SMEM: a block stages the pair records of a small tree in dynamic shared memory (k_trace and the batched queries)
+ARN_DEV void stage_pairs(const DevScene& sc, bool block_has_work) {
+    if (block_has_work) {                       // block-uniform
+        for (uint32_t i = threadIdx.x; i < (ARN_PAIR_BYTES / 16u) * sc.n_pairs; i += blockDim.x) arn_spairs[i] = __ldg(&sc.pairs[i]);
+        __syncthreads();
+    }
+}
 template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 // the 4-wide instance serves trees that miss the caches: it trades a few spills for a fourth resident block per SM
 // (64 registers; C4 k_trace 36.3 -> 35.9 ms, whole frame +4 %); the binary instance stays at three (80 registers)
@@ -249,10 +256,7 @@ __global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY
         for (int c = 0; c < ARN_NCLS; c++) stage_fill[c][threadIdx.x >> 5] = 0;
     }
     __syncwarp();
-    if (MODE == ARN_TRAV_BINARY_SMEM && blockIdx.x * blockDim.x < s3) {       // a block without rays skips the copy (block-uniform)
-        for (uint32_t i = threadIdx.x; i < (ARN_PAIR_BYTES / 16u) * sc.n_pairs; i += blockDim.x) arn_spairs[i] = __ldg(&sc.pairs[i]);
-        __syncthreads();
-    }
+    if (MODE == ARN_TRAV_BINARY_SMEM) stage_pairs(sc, blockIdx.x * blockDim.x < s3);      // a block without rays skips the copy
     for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < s3; gi += gridDim.x * blockDim.x) {
         // the three kinds of query share ONE inlined walk (instruction-cache footprint): kind and `any` are warp-uniform
         const uint32_t kind = gi < s1 ? 0u : (gi < s2 ? 1u : 2u);                 // 0 path ray, 1 shadow ray, 2 BSDF-sampled light ray
@@ -712,10 +716,11 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_const
 
 // ---- standalone batched queries (arn_intersect_closest / arn_intersect_any) ----------------------
 template <int MODE>
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
+__global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY_SMEM ? 1 : ARN_TRAV_MINB) k_closest_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, arn_hit* __restrict__ hits,
                                                              unsigned long long* ctr_out) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     uint32_t ctr[3] = {0, 0, 0};
+    if (MODE == ARN_TRAV_BINARY_SMEM) stage_pairs(sc, (size_t)blockIdx.x * blockDim.x < n);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);
@@ -736,7 +741,8 @@ __global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_closest_batch(cons
     }
 }
 template <int MODE>
-__global__ void __launch_bounds__(ARN_BLOCK, ARN_TRAV_MINB) k_any_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY_SMEM ? 1 : ARN_TRAV_MINB) k_any_batch(const __grid_constant__ DevScene sc, const arn_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ out) {
+    if (MODE == ARN_TRAV_BINARY_SMEM) stage_pairs(sc, (size_t)blockIdx.x * blockDim.x < n);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         arn_ray ry = rays[i];
         TravRay r; trav_init(r, f3(ry.o[0], ry.o[1], ry.o[2]), f3(ry.d[0], ry.d[1], ry.d[2]), ry.tmax);

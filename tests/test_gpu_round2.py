@@ -112,20 +112,15 @@ def test_film_reduce_over_nccl_two_ranks():
     assert "film reduce OK" in r.stdout
 
 
-@pytest.mark.parametrize("width", [2, 4, 8])
-def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width):
-    """Interior nodes are culled with a cheap conservative slab test, leaves with the reference's (traverse.cuh).  Rays that
-    stress the argument: axis-parallel rays whose origins sit exactly on node planes (0 * inf = NaN in the reference's slab
-    arithmetic: sticky on x, ignored on y / z), direction components of 1e-20 / 1e-38 / denormal, grazing rays along the
-    grid, tmax <= 0, huge origins.  Hit ids and t must equal the oracle's bit for bit."""
+def _adversarial_case(cells, seed):
+    """Height field + a sphere and the rays of the adversarial-ray tests; returns (host scene, desc, rays)."""
     h = api.HostScene()
     mat = h.add_material(api.material(L.ARN_MAT_MATTE, kd=(0.7, 0.7, 0.7)))
-    cells = 64
     pos, idx = scenes.heightfield(cells, -2.0, 2.0, 4.0, 0.15, 0x5EED)
     h.add_mesh(pos, idx, mat)
     h.add_sphere(0.4, -0.4, 0.4, 6.28, mat, transform=np.float32([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0.25, -0.5, 3.0, 1]]))
     d = h.build()
-    rng = np.random.default_rng(width)
+    rng = np.random.default_rng(seed)
     grid = (-2.0 + 4.0 * np.arange(cells + 1) / cells).astype(np.float32)      # vertex coordinates = node plane coordinates
     parts = []
 
@@ -155,6 +150,16 @@ def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width)
     tgt = np.float32([0.25, -0.5, 3.0]) + rng.normal(scale=0.3, size=(n, 3)); dv = tgt - o
     parts.append(rays_of(o, dv / np.linalg.norm(dv, axis=1, keepdims=True)))
     rays = np.concatenate(parts)
+    return h, d, rays
+
+
+@pytest.mark.parametrize("width", [2, 4, 8])
+def test_conservative_interior_walk_is_bit_exact_on_adversarial_rays(ctx, width):
+    """Interior nodes are culled with a cheap conservative slab test, leaves with the reference's (traverse.cuh).  Rays that
+    stress the argument: axis-parallel rays whose origins sit exactly on node planes (0 * inf = NaN in the reference's slab
+    arithmetic: sticky on x, ignored on y / z), direction components of 1e-20 / 1e-38 / denormal, grazing rays along the
+    grid, tmax <= 0, huge origins.  Hit ids and t must equal the oracle's bit for bit."""
+    h, d, rays = _adversarial_case(64, width)
     osc = O.OracleScene(d)
     ctx.set_option(L.ARN_OPT_BVH_WIDTH, width)          # before the upload: the compressed 8-wide nodes are built there
     try:
@@ -632,3 +637,44 @@ def test_shared_memory_pair_walk_is_bit_exact(ctx, cornell_small, scene):
     _, orad = osc.render_pt_samples(cam, film, smp, prm)
     assert np.array_equal(rad0[..., :3], orad[..., :3])
     sc.close(); osc.close()
+
+
+def test_shared_memory_walk_is_bit_exact_on_adversarial_rays(ctx):
+    """The same rays against a tree small enough for the pair records: batches of >= 2^15 rays take the shared-memory walk
+    (traverse2p: sign-selected LDS.128, FFMA2, truncated entry distances on the stack) in k_closest_batch / k_any_batch.  Ids and t
+    equal the oracle's and those of the global-memory walk (ARN_OPT_SMEM_NODES = 1) bit for bit."""
+    h, d, rays = _adversarial_case(24, 5)
+    assert ((d.n_nodes - 1) // 2) * 128 <= L.ARN_SMEM_NODE_BYTES and rays.shape[0] >= 1 << 15
+    osc = O.OracleScene(d); sc = ctx.upload(d)
+    gh, ga = sc.intersect_closest(rays), sc.intersect_any(rays)
+    ctx.set_option(L.ARN_OPT_SMEM_NODES, 1)
+    try:
+        gh1, ga1 = sc.intersect_closest(rays), sc.intersect_any(rays)
+    finally:
+        ctx.set_option(L.ARN_OPT_SMEM_NODES, 0)
+    oh = osc.intersect_closest(rays)
+    assert (oh["prim_id"] >= 0).sum() > rays.shape[0] // 10
+    assert (oh["prim_id"] == d.n_prims - 1).sum() > 100, "the sphere should be reached"
+    mism = np.nonzero((gh["prim_id"] != oh["prim_id"]) | (gh["t"] != oh["t"]))[0]
+    assert mism.size == 0, f"{mism.size} mismatches, first rays {mism[:5]}: o {rays['o'][mism[:3]]} d {rays['d'][mism[:3]]} gpu {gh[mism[:3]]} oracle {oh[mism[:3]]}"
+    assert np.array_equal(gh, gh1) and np.array_equal(ga, ga1)
+    assert np.array_equal(ga != 0, oh["prim_id"] >= 0)
+    sc.close(); osc.close()
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 3e4])
+def test_shared_memory_walk_on_random_soups_with_degenerate_geometry(ctx, scale):
+    """Traversal fuzz (flat, collinear, duplicated triangles, clipped and affine spheres, origins on box planes, tmax at the hit) on
+    soups small enough for the shared-memory walk, at three coordinate scales."""
+    for seed in range(3):
+        h, d, rays = _soup_case(np.random.default_rng(100 + seed), scale, n_tri=1000, n=8000)
+        assert ((d.n_nodes - 1) // 2) * 128 <= L.ARN_SMEM_NODE_BYTES and rays.shape[0] >= 1 << 15
+        osc = O.OracleScene(d); sc = ctx.upload(d)
+        gh, ga = sc.intersect_closest(rays), sc.intersect_any(rays)
+        oh = osc.intersect_closest(rays)
+        mism = np.nonzero((gh["prim_id"] != oh["prim_id"]) | (gh["t"] != oh["t"]))[0]
+        assert mism.size == 0, f"seed {seed}: {mism.size} mismatches, first rays {mism[:5]}"
+        assert np.array_equal(ga != 0, oh["prim_id"] >= 0)
+        sc.close(); osc.close()
+
+
