@@ -10,11 +10,12 @@
 // u8), `to_luma` its BT.709 weights.  Nothing in the reference pins these numbers, so no test claims bit-exactness for
 // them; the renderer downstream of the pyramid IS pinned (kernels/shade_tex.cuh against oracle/texture.hpp).
 //
-// Decoders: PNG (8 / 16 bit gray, gray + alpha, RGB, RGBA; palette 1 .. 8 bit; no Adam7 interlace; inflate by zlib) and TGA
-// (true colour, gray, colour-mapped; raw or run-length encoded).  Any other file, like a missing one, makes the caller fall back to the MTL constant — `image::open(..)` failing has the
+// Decoders: PNG (8 / 16 bit gray, gray + alpha, RGB, RGBA; palette 1 .. 8 bit; no Adam7 interlace; inflate by zlib), TGA
+// (true colour, gray, colour-mapped; raw or run-length encoded) and baseline JPEG (gray / YCbCr, 4:4:4 .. 4:2:0, restart intervals).  Any other file, like a missing one, makes the caller fall back to the MTL constant — `image::open(..)` failing has the
 // same effect in load_obj (component/mod.rs:88-95).
 #pragma once
 #include <zlib.h>
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdint>
@@ -170,10 +171,199 @@ inline bool tga_decode(const std::string& path, Image8* out, std::string* err) {
     }
     return true;
 }
-// image::open: by content for PNG, by extension for TGA (the format has no signature)
+
+// JPEG, baseline / extended sequential Huffman (SOF0 / SOF1, 8 bit; gray or YCbCr, sampling factors 1 .. 2 per axis, restart
+// intervals).  Progressive, arithmetic-coded, 12-bit and CMYK files are refused (-> the caller's fall-back, as above).  The
+// inverse DCT is the separable double-precision definition, chroma is brought to full resolution with the triangle filter
+// libjpeg calls "fancy upsampling" for 2:1 factors (replication otherwise), YCbCr -> RGB by the JFIF equations.
+namespace detail {
+struct JpegHuff { uint16_t code[256]; uint8_t size[256], val[256]; int n = 0; int maxcode[18]; int valptr[17]; int mincode[17]; bool set = false; };
+inline bool jpeg_build_huff(const uint8_t* bits, const uint8_t* vals, int nvals, JpegHuff* h) {
+    int k = 0, code = 0;
+    for (int l = 1; l <= 16; l++) {
+        h->valptr[l] = k; h->mincode[l] = code;
+        for (int i = 0; i < bits[l - 1]; i++) { if (k >= nvals || k >= 256) return false; h->val[k] = vals[k]; k++; code++; }
+        h->maxcode[l] = bits[l - 1] ? code - 1 : -1;
+        if (code > (1 << l)) return false;
+        code <<= 1;
+    }
+    h->n = k; h->set = true;
+    return true;
+}
+struct JpegBits {
+    const uint8_t* p; const uint8_t* end; uint32_t acc = 0; int cnt = 0; bool hit_marker = false;
+    int bit() {
+        if (cnt == 0) {
+            uint8_t b = 0;
+            if (!hit_marker && p < end) {
+                b = *p++;
+                if (b == 0xff) {
+                    if (p < end && *p == 0x00) p++;                        // stuffed byte
+                    else { hit_marker = true; p--; b = 0; }               // a marker: feed zeros until the caller resynchronises
+                }
+            } else hit_marker = true;
+            acc = b; cnt = 8;
+        }
+        cnt--;
+        return (int)((acc >> cnt) & 1u);
+    }
+    int bits(int n) { int v = 0; for (int i = 0; i < n; i++) v = (v << 1) | bit(); return v; }
+    void reset() { cnt = 0; acc = 0; hit_marker = false; }
+};
+inline int jpeg_decode_sym(JpegBits& br, const JpegHuff& h) {
+    int code = 0;
+    for (int l = 1; l <= 16; l++) {
+        code = (code << 1) | br.bit();
+        if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.val[h.valptr[l] + code - h.mincode[l]];
+    }
+    return -1;
+}
+inline int jpeg_extend(int v, int t) { return t == 0 ? 0 : (v < (1 << (t - 1)) ? v - (1 << t) + 1 : v); }
+inline void jpeg_idct8x8(const int* coef, const uint16_t* q, uint8_t* out, size_t stride) {
+    static double c[8][8]; static bool init = false;
+    if (!init) { for (int x = 0; x < 8; x++) for (int u = 0; u < 8; u++) c[x][u] = (u == 0 ? std::sqrt(0.125) : 0.5) * std::cos((2 * x + 1) * u * 3.14159265358979323846 / 16.0); init = true; }
+    double tmp[64];
+    for (int v = 0; v < 8; v++) for (int x = 0; x < 8; x++) { double a = 0; for (int u = 0; u < 8; u++) a += c[x][u] * (double)(coef[v * 8 + u] * (int)q[v * 8 + u]); tmp[v * 8 + x] = a; }
+    for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+        double a = 0; for (int v = 0; v < 8; v++) a += c[y][v] * tmp[v * 8 + x];
+        long r = std::lround(a + 128.0);
+        out[(size_t)y * stride + x] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+}
+}  // namespace detail
+
+inline bool jpeg_decode(const std::string& path, Image8* out, std::string* err) {
+    using namespace detail;
+    auto fail = [&](const std::string& why) { if (err) *err = path + ": " + why; return false; };
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return fail("cannot open");
+    std::vector<uint8_t> file;
+    { uint8_t buf[65536]; size_t n; while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) file.insert(file.end(), buf, buf + n); }
+    std::fclose(f);
+    if (file.size() < 4 || file[0] != 0xff || file[1] != 0xd8) return fail("not a JPEG file");
+    static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    uint16_t qt[4][64]; bool qset[4] = {false, false, false, false};
+    JpegHuff hdc[4], hac[4];
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; uint32_t w = 0, ht = 0; std::vector<uint8_t> plane; } comp[3];
+    int ncomp = 0; uint32_t W = 0, H = 0; int hmax = 1, vmax = 1; uint32_t restart = 0; bool have_sof = false, done = false;
+    size_t pos = 2;
+    while (!done) {
+        while (pos < file.size() && file[pos] != 0xff) pos++;                 // to the next marker
+        while (pos < file.size() && file[pos] == 0xff) pos++;
+        if (pos >= file.size()) return fail("no image data before the end of the file");
+        const uint8_t m = file[pos++];
+        if (m == 0xd8 || m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;      // stand-alone markers
+        if (m == 0xd9) return fail("end of image before any scan");
+        if (pos + 2 > file.size()) return fail("truncated segment");
+        const size_t len = ((size_t)file[pos] << 8) | file[pos + 1];
+        if (len < 2 || pos + len > file.size()) return fail("truncated segment");
+        const uint8_t* seg = &file[pos + 2]; const size_t n = len - 2;
+        if (m == 0xdb) {                                                       // DQT
+            size_t o = 0;
+            while (o < n) {
+                const int pq = seg[o] >> 4, tq = seg[o] & 15; o++;
+                if (tq > 3 || pq > 1 || o + (size_t)64 * (pq + 1) > n) return fail("bad quantisation table");
+                for (int i = 0; i < 64; i++) { qt[tq][zz[i]] = pq ? (uint16_t)((seg[o] << 8) | seg[o + 1]) : seg[o]; o += pq + 1; }
+                qset[tq] = true;
+            }
+        } else if (m == 0xc4) {                                                // DHT
+            size_t o = 0;
+            while (o < n) {
+                if (o + 17 > n) return fail("bad Huffman table");
+                const int tc = seg[o] >> 4, th = seg[o] & 15; int cnt = 0;
+                for (int i = 0; i < 16; i++) cnt += seg[o + 1 + i];
+                if (tc > 1 || th > 3 || cnt > 256 || o + 17 + (size_t)cnt > n) return fail("bad Huffman table");
+                if (!jpeg_build_huff(&seg[o + 1], &seg[o + 17], cnt, tc ? &hac[th] : &hdc[th])) return fail("bad Huffman table");
+                o += 17 + (size_t)cnt;
+            }
+        } else if (m == 0xc0 || m == 0xc1) {                                   // SOF0 / SOF1
+            if (n < 6 || seg[0] != 8) return fail("only 8-bit JPEG is supported");
+            H = ((uint32_t)seg[1] << 8) | seg[2]; W = ((uint32_t)seg[3] << 8) | seg[4]; ncomp = seg[5];
+            if (W == 0 || H == 0 || W > 32768 || H > 32768) return fail("implausible JPEG size");
+            if ((ncomp != 1 && ncomp != 3) || n < (size_t)6 + 3 * (size_t)ncomp) return fail("only gray and YCbCr JPEG files are supported");
+            for (int i = 0; i < ncomp; i++) {
+                comp[i].id = seg[6 + 3 * i]; comp[i].h = seg[7 + 3 * i] >> 4; comp[i].v = seg[7 + 3 * i] & 15; comp[i].tq = seg[8 + 3 * i];
+                if (comp[i].h < 1 || comp[i].h > 2 || comp[i].v < 1 || comp[i].v > 2 || comp[i].tq > 3) return fail("unsupported JPEG sampling factors");
+                hmax = std::max(hmax, comp[i].h); vmax = std::max(vmax, comp[i].v);
+            }
+            if (ncomp == 1) { comp[0].h = comp[0].v = 1; hmax = vmax = 1; }
+            have_sof = true;
+        } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
+            return fail("progressive, lossless and arithmetic-coded JPEG files are not supported");
+        } else if (m == 0xdd) {                                                // DRI
+            if (n < 2) return fail("bad restart interval"); restart = ((uint32_t)seg[0] << 8) | seg[1];
+        } else if (m == 0xda) {                                                // SOS: the one scan of a sequential file
+            if (!have_sof) return fail("scan before the frame header");
+            if (n < 1 || seg[0] != ncomp || n < (size_t)1 + 2 * (size_t)ncomp + 3) return fail("multi-scan sequential JPEG files are not supported");
+            for (int i = 0; i < ncomp; i++) {
+                int ci = -1; for (int k = 0; k < ncomp; k++) if (comp[k].id == seg[1 + 2 * i]) ci = k;
+                if (ci != i) return fail("unexpected component order in the scan");
+                comp[i].td = seg[2 + 2 * i] >> 4; comp[i].ta = seg[2 + 2 * i] & 15;
+                if (comp[i].td > 3 || comp[i].ta > 3 || !hdc[comp[i].td].set || !hac[comp[i].ta].set || !qset[comp[i].tq]) return fail("scan refers to a table that was not defined");
+            }
+            const uint32_t mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+            for (int i = 0; i < ncomp; i++) { comp[i].w = mcux * 8 * comp[i].h; comp[i].ht = mcuy * 8 * comp[i].v; comp[i].plane.assign((size_t)comp[i].w * comp[i].ht, 0); comp[i].pred = 0; }
+            JpegBits br; br.p = &file[pos + len]; br.end = file.data() + file.size();
+            uint32_t until_restart = restart; int coef[64];
+            for (uint32_t my = 0; my < mcuy; my++) for (uint32_t mx = 0; mx < mcux; mx++) {
+                if (restart && until_restart == 0) {                           // RSTn: byte-align, skip the marker, reset the predictors
+                    br.reset();
+                    while (br.p + 1 < br.end && !(br.p[0] == 0xff && br.p[1] >= 0xd0 && br.p[1] <= 0xd7)) br.p++;
+                    if (br.p + 1 < br.end) br.p += 2;
+                    for (int i = 0; i < ncomp; i++) comp[i].pred = 0;
+                    until_restart = restart;
+                }
+                for (int i = 0; i < ncomp; i++) for (int by = 0; by < comp[i].v; by++) for (int bx = 0; bx < comp[i].h; bx++) {
+                    std::memset(coef, 0, sizeof coef);
+                    const int t = jpeg_decode_sym(br, hdc[comp[i].td]);
+                    if (t < 0 || t > 11) return fail("corrupt entropy-coded data");
+                    comp[i].pred += jpeg_extend(br.bits(t), t); coef[0] = comp[i].pred;
+                    for (int k = 1; k < 64;) {
+                        const int rs = jpeg_decode_sym(br, hac[comp[i].ta]);
+                        if (rs < 0) return fail("corrupt entropy-coded data");
+                        const int r = rs >> 4, sz = rs & 15;
+                        if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
+                        k += r; if (k > 63) return fail("corrupt entropy-coded data");
+                        coef[zz[k]] = jpeg_extend(br.bits(sz), sz); k++;
+                    }
+                    if (br.hit_marker && br.p >= br.end) return fail("truncated entropy-coded data");
+                    const size_t x0 = ((size_t)mx * comp[i].h + bx) * 8, y0 = ((size_t)my * comp[i].v + by) * 8;
+                    jpeg_idct8x8(coef, qt[comp[i].tq], &comp[i].plane[y0 * comp[i].w + x0], comp[i].w);
+                }
+                if (restart) until_restart--;
+            }
+            done = true;
+        }
+        pos += len;
+    }
+    out->w = W; out->h = H; out->ch = ncomp == 1 ? 1u : 3u; out->px.assign((size_t)W * H * out->ch, 0);
+    if (ncomp == 1) { for (uint32_t y = 0; y < H; y++) std::memcpy(&out->px[(size_t)y * W], &comp[0].plane[(size_t)y * comp[0].w], W); return true; }
+    // chroma to full resolution: sample centres of a 2:1 plane sit between the luma samples -> weights 3/4, 1/4 per axis
+    auto sample_full = [&](const Comp& c, uint32_t x, uint32_t y) -> double {
+        const int fx = hmax / c.h, fy = vmax / c.v;
+        // the part of the plane that carries picture content (the rest is MCU padding)
+        const long cw = (long)((W * (uint32_t)c.h + hmax - 1) / hmax), chh = (long)((H * (uint32_t)c.v + vmax - 1) / vmax);
+        auto at = [&](long xx, long yy) { xx = xx < 0 ? 0 : (xx >= cw ? cw - 1 : xx); yy = yy < 0 ? 0 : (yy >= chh ? chh - 1 : yy); return (double)c.plane[(size_t)yy * c.w + (size_t)xx]; };
+        long x0 = x, x1 = x; double wx = 0; long y0 = y, y1 = y; double wy = 0;
+        if (fx == 2) { x0 = x / 2; x1 = (x & 1) ? x0 + 1 : x0 - 1; wx = 0.25; }
+        if (fy == 2) { y0 = y / 2; y1 = (y & 1) ? y0 + 1 : y0 - 1; wy = 0.25; }
+        const double a = at(x0, y0) * (1 - wx) + at(x1, y0) * wx, b = at(x0, y1) * (1 - wx) + at(x1, y1) * wx;
+        return a * (1 - wy) + b * wy;
+    };
+    auto clamp8 = [](double v) { long r = std::lround(v); return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r)); };
+    for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) {
+        const double Y = sample_full(comp[0], x, y), cb = sample_full(comp[1], x, y) - 128.0, cr = sample_full(comp[2], x, y) - 128.0;
+        uint8_t* d = &out->px[((size_t)y * W + x) * 3];
+        d[0] = clamp8(Y + 1.402 * cr); d[1] = clamp8(Y - 0.344136 * cb - 0.714136 * cr); d[2] = clamp8(Y + 1.772 * cb);
+    }
+    return true;
+}
+// image::open: by content for PNG and JPEG, by extension for TGA (the format has no signature)
 inline bool image_decode(const std::string& path, Image8* out, std::string* err) {
     auto ends_with = [&](const char* e) { const size_t n = std::strlen(e); if (path.size() < n) return false; for (size_t i = 0; i < n; i++) if (std::tolower((unsigned char)path[path.size() - n + i]) != e[i]) return false; return true; };
     if (ends_with(".tga")) return tga_decode(path, out, err);
+    { FILE* f = std::fopen(path.c_str(), "rb"); uint8_t sig[2] = {0, 0}; if (f) { size_t got = std::fread(sig, 1, 2, f); std::fclose(f); if (got == 2 && sig[0] == 0xff && sig[1] == 0xd8) return jpeg_decode(path, out, err); } }
     return png_decode(path, out, err);
 }
 

@@ -345,3 +345,46 @@ def test_tga_decoder_reads_what_was_written(harness, tmp_path):
     write_tga(tmp_path / "tex.tga", rng.integers(0, 256, (4, 8, 3)).astype(np.uint8))
     tid, mean = hs.add_texture_file(tmp_path / "tex.tga")
     assert tid == 1 and 0.2 < float(mean.mean()) < 0.8
+
+
+def test_jpeg_decoder_agrees_with_libjpeg(harness, tmp_path):
+    """Baseline JPEG (gray, 4:4:4, 4:2:2, 4:2:0, odd sizes, restart intervals, optimised Huffman tables) against Pillow's libjpeg decode of
+    the same file.  The `image` crate's decoder is not in the reference tree (parity unpinned), so the check is agreement within the
+    rounding differences two correct decoders have: exact IDCT + triangle chroma filter here, integer IDCT + fancy upsampling there."""
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(23)
+    yy, xx = np.mgrid[0:45, 0:70]
+    smooth = np.stack([128 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 128 + 90 * np.cos(xx / 13.0 + yy / 5.0), 40 + 2.5 * xx + 0.5 * yy], -1)
+    img = np.clip(smooth + rng.normal(scale=6.0, size=smooth.shape), 0, 255).astype(np.uint8)
+    cases = [("444", dict(subsampling=0)), ("422", dict(subsampling=1)), ("420", dict(subsampling=2)), ("420opt", dict(subsampling=2, optimize=True)),
+             ("420rst", dict(subsampling=2, restart_marker_blocks=3)), ("q30", dict(subsampling=2, quality=30))]
+    for name, kw in cases:
+        p = tmp_path / f"{name}.jpg"
+        PIL.fromarray(img).save(p, "JPEG", quality=kw.pop("quality", 92), **kw)
+        ref = np.asarray(PIL.open(p).convert("RGB")).astype(np.int32)
+        got, err = harness("decode", p)
+        assert err is None, (name, err)
+        assert got.shape == ref.shape
+        diff = np.abs(got.astype(np.int32) - ref)
+        assert diff.mean() < 0.6 and diff.max() <= 6, (name, float(diff.mean()), int(diff.max()))
+    gray = img[..., 0]
+    PIL.fromarray(gray).save(tmp_path / "g.jpg", "JPEG", quality=90)
+    got, err = harness("decode", tmp_path / "g.jpg")
+    ref = np.asarray(PIL.open(tmp_path / "g.jpg")).astype(np.int32)
+    assert err is None and got.shape == (45, 70, 1) and np.abs(got[..., 0].astype(np.int32) - ref).max() <= 1
+    # refused, not mis-decoded: progressive files; damaged files give a verdict, never a crash
+    PIL.fromarray(img).save(tmp_path / "prog.jpg", "JPEG", progressive=True)
+    assert harness("decode", tmp_path / "prog.jpg")[0] is None
+    data = (tmp_path / "420.jpg").read_bytes()
+    for k in range(60):
+        b = bytearray(data)
+        if k % 3 == 0: b = b[: rng.integers(2, len(b))]
+        else:
+            for _ in range(int(rng.integers(1, 6))): b[int(rng.integers(2, len(b)))] = int(rng.integers(0, 256))
+        (tmp_path / "bad.jpg").write_bytes(bytes(b))
+        img2, err2 = harness("decode", tmp_path / "bad.jpg")
+        assert (img2 is None) != (err2 is None)
+    # through the scene route
+    hs = api.HostScene()
+    tid, mean = hs.add_texture_file(tmp_path / "444.jpg")
+    assert tid == 1 and abs(float(mean[0]) - float((img[..., 0] / 255.0).mean())) < 0.3
