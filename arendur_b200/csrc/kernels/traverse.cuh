@@ -458,6 +458,8 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
     uint2 stack[ARN_STACK];
     int sp = 0;
     uint32_t idx = 0, offset, len_axis;
+    uint32_t nb = c.negbits;
+    asm volatile("" : "+r"(nb));        // pinned: left alone, the compiler rebuilds the three sign bits from 1/d (ten instructions) on every push
     {
         const Node8 n = ld_node(sc.nodes);
         float lo;
@@ -472,7 +474,7 @@ ARN_DEV void traverse2(const DevScene& sc, TravRay& r, const CullRay& c, HitRec&
             const Node8 a = ld_node(sc.nodes + 2 * ia), b = ld_node(sc.nodes + 2 * ib);
             float la, lb;
             const bool ha = slab_cull(a.q0, a.q1, r, c, la), hb = slab_cull(b.q0, b.q1, r, c, lb);
-            const bool first_b = (c.negbits >> (len_axis & 3u)) & 1u;           // dir_is_neg[split_axis]: second child first
+            const bool first_b = ((nb >> len_axis) & 1u) != 0u;                 // dir_is_neg[split_axis]: second child first (interior: len_axis == axis)
             if (ha && hb) {
                 ARN_STACK_CHECK(sp, ARN_STACK);
                 stack[sp++] = first_b ? make_uint2(ia, __float_as_uint(la)) : make_uint2(ib, __float_as_uint(lb));
