@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("ARN_LIB_PATH") or os.path.join(_HERE, "libarn_b200.so
 ARN_OK, ARN_E_INVALID, ARN_E_CUDA, ARN_E_OOM, ARN_E_IO, ARN_E_UNSUPPORTED, ARN_E_NCCL = 0, -1, -2, -3, -4, -5, -6
 ARN_PRIM_SPHERE = 0x80000000
 ARN_BVH_SAH, ARN_BVH_MIDDLECOUNT, ARN_BVH_MIDPOINT = 0, 1, 2
-ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY, ARN_OPT_BVH_WIDTH, ARN_OPT_PIPELINES, ARN_OPT_TRACE_REFILL, ARN_OPT_SMEM_NODES = 1, 2, 3, 4, 5, 6
+ARN_OPT_COUNT_TRAVERSAL, ARN_OPT_WAVE_CAPACITY, ARN_OPT_BVH_WIDTH, ARN_OPT_PIPELINES, ARN_OPT_TRACE_REFILL, ARN_OPT_SMEM_NODES, ARN_OPT_PDL = 1, 2, 3, 4, 5, 6, 7
 ARN_SMEM_NODE_BYTES = 160 * 1024        # arn.h: budget of the pair records k_trace stages in shared memory (128 B per interior node)
 ARN_LIGHT_POINT, ARN_LIGHT_SPOT, ARN_LIGHT_DISTANT = 0, 1, 2
 ARN_LIGHT_ANALYTIC = 0x80000000

@@ -60,6 +60,7 @@ struct arn_ctx {
     int g_trace_w = 0, g_closest_w = 0, g_any_w = 0, g_shade_p = 0, g_shade_g = 0;
     int g_trace_8 = 0, g_closest_8 = 0, g_any_8 = 0;      // compressed 8-wide walk
     size_t opt_wave = 0;
+    int opt_pdl = 0;             // ARN_OPT_PDL: programmatic dependent launch along a pipeline's kernel chain
     int opt_smem_off = 0;        // ARN_OPT_SMEM_NODES = 1: never walk small trees from shared memory
     int opt_refill = 0;          // ARN_OPT_TRACE_REFILL: lane-refilling trace (kernels/trace_refill.cuh) for trees walked with the binary nodes
     int g_setup = 0, g_refill = 0, g_classify = 0, g_shade_tex = 0;
@@ -107,6 +108,17 @@ int grid_for(arn_ctx* c, const void* kernel) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ARN_BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     return c->sm_count * per_sm;
+}
+
+// One launch of the render chain; `pdl`: with the programmatic-stream-serialization attribute (kernels/wavefront.cuh, pdl_prologue)
+template <typename... KArgs, typename... Args>
+void launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 cudaEvent_t get_event(arn_ctx* c, size_t i) {
@@ -211,6 +223,7 @@ int arn_ctx_create(int device, arn_ctx** out) {
     CTX_TRY( cudaFuncSetAttribute((const void*)k_closest_batch<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
     CTX_TRY( cudaFuncSetAttribute((const void*)k_any_batch<ARN_TRAV_BINARY_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARN_SMEM_NODE_BYTES));
     { const char* e = std::getenv("ARN_SMEM_NODES"); if (e) c->opt_smem_off = std::atoi(e) == 0; }
+    { const char* e = std::getenv("ARN_PDL"); if (e) c->opt_pdl = std::atoi(e) != 0; }
     c->g_trace_8 = grid_for(c, (const void*)k_trace<ARN_TRAV_CW8>);
     c->g_closest_8 = grid_for(c, (const void*)k_closest_batch<ARN_TRAV_CW8>);
     c->g_any_8 = grid_for(c, (const void*)k_any_batch<ARN_TRAV_CW8>);
@@ -265,6 +278,7 @@ int arn_ctx_set_option(arn_ctx* c, int option, long long value) {
     case ARN_OPT_PIPELINES: if (value < 0 || value > ARN_MAX_PIPES) return set_err(c, ARN_E_INVALID, "pipelines must be in 0 (auto) ..8"); c->opt_pipes = (int)value; return ARN_OK;
     case ARN_OPT_TRACE_REFILL: c->opt_refill = value != 0; return ARN_OK;
     case ARN_OPT_SMEM_NODES: c->opt_smem_off = value != 0; return ARN_OK;
+    case ARN_OPT_PDL: c->opt_pdl = value != 0; return ARN_OK;
     case ARN_OPT_WAVE_CAPACITY: if (value != 0 && value < 1024) return set_err(c, ARN_E_INVALID, "wave capacity must be >= 1024"); c->opt_wave = (size_t)value; return ARN_OK;
     default: return set_err(c, ARN_E_INVALID, "unknown option");
     }
@@ -811,13 +825,16 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
         if (i > 0) cudaStreamWaitEvent(c->pipes[i].stream, e_begin, 0);       // after the tile tables / whatever the caller queued
         CUDA_TRY(c, cudaMemsetAsync(c->pipes[i].q.stats, 0, 64, c->pipes[i].stream));
     }
+    // ARN_OPT_PDL: every kernel of the chain below starts with pdl_prologue(); the variants without it (counted, refill, textured) launch plainly
+    const bool pdl = c->opt_pdl && !time_kernels && !refill && !c->opt_count && !textured;
+#define ARN_LAUNCH(kern, grid, block, smem, ...) do { if (pdl) launch_chain(true, kern, grid, block, smem, st, __VA_ARGS__); else kern<<<grid, block, smem, st>>>(__VA_ARGS__); } while (0)
     unsigned long long wave = 0;
     for (unsigned long long base = 0; base < total; base += cap, wave++) {
         arn_ctx::Pipe& P = c->pipes[wave % (unsigned long long)np];
         cudaStream_t st = P.stream;
         uint32_t n = (uint32_t)std::min<unsigned long long>(cap, total - base);
         // k_generate empties the wave's queue counters; every k_trace empties the counter set of the other parity (wavefront.cuh, cnt_*)
-        k_generate<<<std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, base, n);
+        ARN_LAUNCH(k_generate, std::min(c->g_generate, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, wp, P.pb, P.q, base, n);
         launches += 1;
         auto trace = [&](int j) {
             if (time_kernels) { size_t i0 = ev; cudaEventRecord(get_event(c, ev++), st); ext_events.push_back({i0, j}); }
@@ -828,10 +845,10 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
                 launches += 2;
             }
             else if (c->opt_count) k_trace<ARN_TRAV_COUNTED><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
-            else if (cw8) k_trace<ARN_TRAV_CW8><<<c->g_trace_8, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
-            else if (wide) k_trace<ARN_TRAV_WIDE><<<c->g_trace_w, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
-            else if (smem_nodes) k_trace<ARN_TRAV_BINARY_SMEM><<<c->sm_count, ARN_BLOCK_SMEM, node_bytes, st>>>(s->dev, P.pb, P.q, j);
-            else k_trace<ARN_TRAV_BINARY><<<c->g_trace, ARN_BLOCK, 0, st>>>(s->dev, P.pb, P.q, j);
+            else if (cw8) ARN_LAUNCH(k_trace<ARN_TRAV_CW8>, c->g_trace_8, ARN_BLOCK, 0, s->dev, P.pb, P.q, j);
+            else if (wide) ARN_LAUNCH(k_trace<ARN_TRAV_WIDE>, c->g_trace_w, ARN_BLOCK, 0, s->dev, P.pb, P.q, j);
+            else if (smem_nodes) ARN_LAUNCH(k_trace<ARN_TRAV_BINARY_SMEM>, c->sm_count, ARN_BLOCK_SMEM, node_bytes, s->dev, P.pb, P.q, j);
+            else ARN_LAUNCH(k_trace<ARN_TRAV_BINARY>, c->g_trace, ARN_BLOCK, 0, s->dev, P.pb, P.q, j);
             if (time_kernels) cudaEventRecord(get_event(c, ev++), st);
         };
         trace(0);                                                  // camera rays
@@ -841,25 +858,26 @@ static int render_pt_impl(arn_scene* s, const arn_camera* cam, const arn_film* f
             // heavy classes first: the tail of the bounce is cheap Lambert work
             if (textured) { k_shade<SHADE_GENERIC, true><<<c->g_shade_tex, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
             else {
-            if (s->class_mask & 0x08u) { k_shade<SHADE_GLASS><<<c->g_shade_g, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
-            if (s->class_mask & 0x04u) { k_shade<SHADE_PLASTIC><<<c->g_shade_p, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
-            if (s->class_mask & 0x10u) { k_shade<SHADE_GENERIC><<<c->g_shade, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
-            if (s->class_mask & 0x03u) { k_shade<SHADE_DIFFUSE><<<c->g_shade_d, ARN_BLOCK, 0, st>>>(s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x08u) { ARN_LAUNCH(k_shade<SHADE_GLASS>, c->g_shade_g, ARN_BLOCK, 0, s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x04u) { ARN_LAUNCH(k_shade<SHADE_PLASTIC>, c->g_shade_p, ARN_BLOCK, 0, s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x10u) { ARN_LAUNCH(k_shade<SHADE_GENERIC>, c->g_shade, ARN_BLOCK, 0, s->dev, wp, P.pb, P.q, (int)b); launches++; }
+            if (s->class_mask & 0x03u) { ARN_LAUNCH(k_shade<SHADE_DIFFUSE>, c->g_shade_d, ARN_BLOCK, 0, s->dev, wp, P.pb, P.q, (int)b); launches++; }
             }
             trace((int)b + 1);                                     // path rays of bounce b+1, shadow + light rays of bounce b
-            k_resolve<<<c->g_resolve, ARN_BLOCK, 0, st>>>(P.pb, P.q, (int)b);
+            ARN_LAUNCH(k_resolve, c->g_resolve, ARN_BLOCK, 0, P.pb, P.q, (int)b);
             launches += 2;
         }
         if (film->filter_radius_x <= 4.f && film->filter_radius_y <= 4.f && film->filter_radius_x >= 0.5f && film->filter_radius_y >= 0.5f) {
             unsigned long long npix = (base + n - 1) / wp.spp_count - base / wp.spp_count + 1;
             int blocks = (int)std::min<unsigned long long>((unsigned long long)c->g_accum_px, (npix * 32 + ARN_BLOCK - 1) / ARN_BLOCK);
-            k_accumulate_px<<<std::max(blocks, 1), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, (float4*)film_dev, base, n);
+            ARN_LAUNCH(k_accumulate_px, std::max(blocks, 1), ARN_BLOCK, 0, wp, P.pb, P.q, (float4*)film_dev, base, n);
         } else
-        k_accumulate<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, P.q, (float4*)film_dev, n);
+        ARN_LAUNCH(k_accumulate, std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, wp, P.pb, P.q, (float4*)film_dev, n);
         launches += 1;
-        if (radiance_dev) { k_store_radiance<<<std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, st>>>(wp, P.pb, radiance_dev, n); launches += 1; }
+        if (radiance_dev) { ARN_LAUNCH(k_store_radiance, std::min(c->g_accum, (int)((n + ARN_BLOCK - 1) / ARN_BLOCK)), ARN_BLOCK, 0, wp, P.pb, radiance_dev, n); launches += 1; }
         CUDA_TRY(c, cudaGetLastError());
     }
+#undef ARN_LAUNCH
     // join: everything the pipelines did is ordered before whatever follows on the context's stream
     for (int i = 1; i < np; i++) { cudaEventRecord(c->pipes[i].done, c->pipes[i].stream); cudaStreamWaitEvent(c->stream, c->pipes[i].done, 0); }
     cudaEventRecord(e_end, c->stream);

@@ -141,9 +141,15 @@ ARN_DEV void stage_flush(WarpStage& st, uint32_t* __restrict__ queue, uint32_t* 
     }
 }
 
+// Programmatic dependent launch (ARN_OPT_PDL, off by default): with the launch attribute set, the blocks of the NEXT kernel of a pipeline
+// may become resident as this kernel's blocks retire and park at `wait` until this grid has completed and flushed; without the attribute
+// both instructions do nothing.
+ARN_DEV void pdl_prologue() { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- K1 generate ------------------------------------------------------------------------
 __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q,
                                                          unsigned long long wave_base, uint32_t n) {
+    pdl_prologue();
     if (blockIdx.x == 0 && threadIdx.x < ARN_NCOUNTS) q.counts[threadIdx.x] = threadIdx.x == 0 ? n : 0u;     // begin the wave: every queue empty, n camera rays
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long g = wave_base + i;
@@ -238,6 +244,7 @@ template <int MODE>     // ARN_TRAV_BINARY / _COUNTED / _WIDE (traverse.cuh)
 __global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY_SMEM ? 1 : ((MODE == ARN_TRAV_WIDE || MODE == ARN_TRAV_CW8) ? ARN_TRAV_MINB_WIDE : ARN_TRAV_MINB)) k_trace(const __grid_constant__ DevScene sc, PathBuf pb, Queues q, int j) {
     constexpr bool COUNT = MODE == ARN_TRAV_COUNTED;
     constexpr int BLOCK = ARN_TRACE_BLOCK(MODE);
+    pdl_prologue();
     uint32_t ctr[3] = {0, 0, 0};
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par; const int first = j == 0;
     const uint32_t n_ext = *cnt_active(q.counts, par), n_sh = *cnt_nee(q.counts, par, 1), n_mis = *cnt_nee(q.counts, par, 2);
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(ARN_TRACE_BLOCK(MODE), MODE == ARN_TRAV_BINARY
 template <int KIND, bool TEX = false>
 __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_MINB_DIFFUSE : ARN_SHADE_MINB) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ WaveParams p, PathBuf pb, Queues q, int j) {
     constexpr bool DIFFUSE = KIND == SHADE_DIFFUSE;
+    pdl_prologue();
     const uint32_t par = (uint32_t)j & 1u; const int cur = (int)par;      // shade(j) consumes the hits of trace(j)
     constexpr uint32_t LOBES = KIND == SHADE_PLASTIC ? LOBES_PLASTIC : (KIND == SHADE_GLASS ? LOBES_GLASS : LOBES_ALL);
     // One launch over the concatenation of this instance's class queues, each padded to a multiple of 32 so that
@@ -542,6 +550,7 @@ __global__ void __launch_bounds__(ARN_BLOCK, KIND == SHADE_DIFFUSE ? ARN_SHADE_M
 
 // ---- resolve: L += beta * (light term + BSDF term) / p_light  (evaluate_direct's sum, pt.rs:89) -----
 __global__ void __launch_bounds__(ARN_BLOCK) k_resolve(PathBuf pb, Queues q, int j) {      // resolve(j): the direct-light terms shade(j) queued, after trace(j + 1) traced their rays
+    pdl_prologue();
     const uint32_t n = *cnt_nee(q.counts, ((uint32_t)j + 1u) & 1u, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pid = q.connect[i];
@@ -589,6 +598,7 @@ ARN_DEV void tile_sink(const WaveParams& p, int px, int py, int& sx0, int& sy0, 
 }
 
 __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q, float4* __restrict__ film, uint32_t n) {
+    pdl_prologue();
     unsigned long long invalid = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 l4 = pb.L[i];
@@ -634,6 +644,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
                                                               unsigned long long wave_base, uint32_t n) {
     __shared__ float s_w[ARN_BLOCK / 32][32 * ARN_ACC_STRIDE];
     __shared__ float4 s_L[ARN_BLOCK / 32][32];
+    pdl_prologue();
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     float* __restrict__ wrow = s_w[wib];
     float4* __restrict__ lrow = s_L[wib];
@@ -707,6 +718,7 @@ __global__ void __launch_bounds__(ARN_BLOCK) k_accumulate_px(const __grid_consta
 // diagnostic: per-sample radiance, indexed ((y*crop_w + x)*spp_count + (s - spp_begin)) by the TILE pixel (x, y),
 // which runs over [0, crop_w) x [0, crop_h) whatever crop.pmin is (film.rs:118-121) (parity tests)
 __global__ void __launch_bounds__(ARN_BLOCK) k_store_radiance(const __grid_constant__ WaveParams p, PathBuf pb, float4* __restrict__ out, uint32_t n) {
+    pdl_prologue();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t pix = pb.pix[i]; uint32_t x = pix & 0xffffu, y = pix >> 16;
         size_t idx = ((size_t)y * p.crop_w + x) * p.spp_count + (pb.smp[i] - p.spp_begin);

@@ -393,6 +393,8 @@ int arn_render_pt_samples(arn_scene* scene, const arn_camera* cam, const arn_fil
 #define ARN_OPT_SMEM_NODES      6   /* 0 auto (default): trees with up to ARN_SMEM_NODE_BYTES / 112 interior nodes are walked by k_trace from
                                        pair records staged in shared memory; 1: never (also env ARN_SMEM_NODES=0); same bits */
 #define ARN_SMEM_NODE_BYTES (160 * 1024)
+#define ARN_OPT_PDL             7   /* value != 0: programmatic dependent launch along each pipeline's kernel chain (measured; off by
+                                       default; also env ARN_PDL) */
 int arn_ctx_set_option(arn_ctx* ctx, int option, long long value);
 
 int arn_ctx_synchronize(arn_ctx* ctx);

@@ -678,3 +678,20 @@ def test_shared_memory_walk_on_random_soups_with_degenerate_geometry(ctx, scale)
         sc.close(); osc.close()
 
 
+
+
+def test_programmatic_dependent_launch_is_bit_exact(ctx, cornell_small):
+    """ARN_OPT_PDL: the kernels of a pipeline are launched with the programmatic-stream-serialization attribute and park at
+    griddepcontrol.wait until their predecessor has completed (measured slower, off by default).  Same results."""
+    hs, cam, film, smp, prm = cornell_small
+    sc = ctx.upload(hs.desc())
+    f0, rad0, st0 = sc.render_pt_samples(cam, film, smp, prm)
+    ctx.set_option(L.ARN_OPT_PDL, 1); ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 3000); ctx.set_option(L.ARN_OPT_PIPELINES, 3)
+    try:
+        f1, rad1, st1 = sc.render_pt_samples(cam, film, smp, prm)
+    finally:
+        ctx.set_option(L.ARN_OPT_PDL, 0); ctx.set_option(L.ARN_OPT_WAVE_CAPACITY, 0); ctx.set_option(L.ARN_OPT_PIPELINES, 0)
+    assert np.array_equal(rad0, rad1)
+    assert (st0.extend_rays, st0.shadow_rays, st0.mis_rays) == (st1.extend_rays, st1.shadow_rays, st1.mis_rays)
+    assert np.allclose(f0, f1, rtol=1e-5, atol=1e-6)
+    sc.close()

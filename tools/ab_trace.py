@@ -7,7 +7,7 @@ import os, sys, json, time
 sys.path.insert(0, os.environ["ARN_ROOT"])
 import numpy as np, torch
 from arendur_b200 import api, scenes, _lib as L
-out = {"lib": os.environ.get("ARN_LIB_PATH", "default") + ("+refill" if os.environ.get("ARN_REFILL") else "") + ("+w" + os.environ["AB_WIDTH"] if os.environ.get("AB_WIDTH") else "") + ("+nosmem" if os.environ.get("ARN_SMEM_NODES") == "0" else "")}
+out = {"lib": os.environ.get("ARN_LIB_PATH", "default") + ("+refill" if os.environ.get("ARN_REFILL") else "") + ("+w" + os.environ["AB_WIDTH"] if os.environ.get("AB_WIDTH") else "") + ("+nosmem" if os.environ.get("ARN_SMEM_NODES") == "0" else "") + ("+pdl" if os.environ.get("ARN_PDL") == "1" else "")}
 ctx = api.Context(0)
 if os.environ.get('AB_WIDTH'): ctx.set_option(L.ARN_OPT_BVH_WIDTH, int(os.environ['AB_WIDTH']))
 def run(name, hs, cam, film, smp, prm, reps):
@@ -50,6 +50,8 @@ for lib in libs:
         env["AB_WIDTH"] = "4"; lib = lib[:-3]
     if lib.endswith("+nosmem"):                 # small trees walked from global memory (the round-2 default until the shared-memory walk)
         env["ARN_SMEM_NODES"] = "0"; lib = lib[:-7]
+    if lib.endswith("+pdl"):                    # programmatic dependent launch along the kernel chain (ARN_OPT_PDL)
+        env["ARN_PDL"] = "1"; lib = lib[:-4]
     if lib.endswith("+refill"):                 # the lane-refilling trace of the same build
         env["ARN_REFILL"] = "1"; lib = lib[:-7]
     if lib != "default":
