@@ -144,7 +144,15 @@ ARN_DEV void stage_flush(WarpStage& st, uint32_t* __restrict__ queue, uint32_t* 
 // Programmatic dependent launch (ARN_OPT_PDL, off by default): with the launch attribute set, the blocks of the NEXT kernel of a pipeline
 // may become resident as this kernel's blocks retire and park at `wait` until this grid has completed and flushed; without the attribute
 // both instructions do nothing.
-ARN_DEV void pdl_prologue() { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef ARN_PDL_EARLY_TRIGGER
+#define ARN_PDL_EARLY_TRIGGER 1        /* 0: no explicit trigger — the next kernel is released when this one's blocks exit (measured: no better) */
+#endif
+ARN_DEV void pdl_prologue() {
+#if ARN_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---- K1 generate ------------------------------------------------------------------------
 __global__ void __launch_bounds__(ARN_BLOCK) k_generate(const __grid_constant__ WaveParams p, PathBuf pb, Queues q,
