@@ -117,7 +117,7 @@ ARN_H_SYMBOLS = [
     "arn_last_error", "arn_scene_upload", "arn_scene_destroy", "arn_intersect_closest", "arn_intersect_any",
     "arn_intersect_closest_dev", "arn_intersect_any_dev", "arn_intersect_closest_counted_dev",
     "arn_bvh_build_gpu", "arn_render_pt", "arn_render_pt_dev", "arn_render_pt_samples", "arn_ctx_set_option", "arn_ctx_synchronize", "arn_ctx_stream", "arn_version",
-    "arn_film_reduce", "arn_film_merge", "arn_nccl_unique_id", "arn_nccl_comm_create", "arn_nccl_comm_destroy", "arn_selftest_math", "arn_selftest_bsdf",
+    "arn_film_reduce", "arn_film_merge", "arn_nccl_unique_id", "arn_nccl_comm_create", "arn_nccl_comm_destroy", "arn_selftest_math", "arn_selftest_bsdf", "arn_selftest_pair_records",
 ]
 ARN_HOST_H_SYMBOLS = [
     "arn_hscene_create", "arn_hscene_destroy", "arn_hscene_last_error", "arn_hscene_add_material",
@@ -167,6 +167,7 @@ def load():
         "arn_nccl_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
         "arn_nccl_comm_destroy": (C.c_int, [vp]),
         "arn_selftest_math": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+        "arn_selftest_pair_records": (C.c_int, [vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]),
         "arn_selftest_bsdf": (C.c_int, [vp, C.POINTER(Material), C.c_size_t, vp, vp, vp, vp, vp]),
         "arn_hscene_create": (C.c_int, [C.POINTER(vp)]),
         "arn_hscene_destroy": (None, [vp]),

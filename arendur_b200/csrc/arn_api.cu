@@ -121,6 +121,37 @@ void launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Pair records of a small tree (kernels/traverse.cuh, traverse2p): one 128-byte record per interior node, in node order.  Returns the number
+// of records, 0 when the tree is a single leaf, not a full binary tree, or too large for the shared-memory budget (`rec` is then left empty).
+uint32_t build_pair_records(const arn_node* nodes, uint32_t n_nodes, std::vector<float>* rec) {
+    rec->clear();
+    if (n_nodes < 3 || (nodes[0].len_axis >> 2) != 0 || ((size_t)n_nodes - 1) / 2 * ARN_PAIR_BYTES > ARN_SMEM_NODE_BYTES) return 0;
+    const uint32_t n_int = (n_nodes - 1) / 2;
+    std::vector<uint32_t> pair_of(n_nodes, 0u);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n_nodes; i++) if ((nodes[i].len_axis >> 2) == 0) pair_of[i] = k++;
+    if (k != n_int) return 0;
+    rec->assign((size_t)n_int * (ARN_PAIR_BYTES / 4), 0.f);
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        const arn_node& nd = nodes[i];
+        if ((nd.len_axis >> 2) != 0) continue;
+        float* r = &(*rec)[(size_t)pair_of[i] * (ARN_PAIR_BYTES / 4)];
+        const uint32_t ch[2] = {i + 1, i + nd.offset};
+        for (int cidx = 0; cidx < 2; cidx++) {
+            if (ch[cidx] >= n_nodes) { rec->clear(); return 0; }
+            const arn_node& cn = nodes[ch[cidx]];
+            for (int a = 0; a < 3; a++) {           // axis block: (A.min, A.max, B.min, B.max) then the same with min / max swapped
+                float* q = r + a * 8 + cidx * 2;
+                q[0] = cn.bmin[a]; q[1] = cn.bmax[a]; q[4] = cn.bmax[a]; q[5] = cn.bmin[a];
+            }
+            const bool leaf = (cn.len_axis >> 2) != 0;
+            const uint32_t w0 = leaf ? cn.offset : pair_of[ch[cidx]] * ARN_PAIR_BYTES, w1 = cn.len_axis;
+            for (int rep = 0; rep < 2; rep++) { std::memcpy(r + 24 + rep * 4 + cidx * 2, &w0, 4); std::memcpy(r + 25 + rep * 4 + cidx * 2, &w1, 4); }
+        }
+    }
+    return n_int;
+}
+
 cudaEvent_t get_event(arn_ctx* c, size_t i) {
     while (c->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); c->events.push_back(e); }
     return c->events[i];
@@ -403,30 +434,9 @@ int arn_scene_upload(arn_ctx* c, const arn_scene_desc* d, arn_scene** out) {
     lap("node upload");
     s->dev.pairs = nullptr; s->dev.n_pairs = 0; s->dev.root_axis = 0;
     std::vector<float> rec;                             // staging of the pair records: lives until the upload's final sync
-    if (d->n_nodes >= 3 && (d->nodes[0].len_axis >> 2) == 0 && ((size_t)d->n_nodes - 1) / 2 * ARN_PAIR_BYTES <= ARN_SMEM_NODE_BYTES) {
-        // pair records of a small tree (kernels/traverse.cuh, traverse2p): one per interior node, in node order
-        const uint32_t n_int = (d->n_nodes - 1) / 2;
-        std::vector<uint32_t> pair_of(d->n_nodes, 0u);
-        uint32_t k = 0;
-        for (uint32_t i = 0; i < d->n_nodes; i++) if ((d->nodes[i].len_axis >> 2) == 0) pair_of[i] = k++;
-        if (k == n_int) {                                   // a full binary tree, as validated above
-            rec.assign((size_t)n_int * (ARN_PAIR_BYTES / 4), 0.f);
-            for (uint32_t i = 0; i < d->n_nodes; i++) {
-                const arn_node& nd = d->nodes[i];
-                if ((nd.len_axis >> 2) != 0) continue;
-                float* r = &rec[(size_t)pair_of[i] * (ARN_PAIR_BYTES / 4)];
-                const uint32_t ch[2] = {i + 1, i + nd.offset};
-                for (int cidx = 0; cidx < 2; cidx++) {
-                    const arn_node& cn = d->nodes[ch[cidx]];
-                    for (int a = 0; a < 3; a++) {           // axis block: (A.min, A.max, B.min, B.max) then the same with min / max swapped
-                        float* q = r + a * 8 + cidx * 2;
-                        q[0] = cn.bmin[a]; q[1] = cn.bmax[a]; q[4] = cn.bmax[a]; q[5] = cn.bmin[a];
-                    }
-                    const bool leaf = (cn.len_axis >> 2) != 0;
-                    const uint32_t w0 = leaf ? cn.offset : pair_of[ch[cidx]] * ARN_PAIR_BYTES, w1 = cn.len_axis;
-                    for (int rep = 0; rep < 2; rep++) { std::memcpy(r + 24 + rep * 4 + cidx * 2, &w0, 4); std::memcpy(r + 25 + rep * 4 + cidx * 2, &w1, 4); }
-                }
-            }
+    {
+        const uint32_t n_int = build_pair_records(d->nodes, d->n_nodes, &rec);
+        if (n_int) {
             const float4* dp = nullptr;
             if ((rc = dev_upload(s, (const float4*)rec.data(), rec.size() / 4, &dp)) != ARN_OK) return fail(rc);
             s->dev.pairs = dp; s->dev.n_pairs = n_int; s->dev.root_axis = d->nodes[0].len_axis & 3u;
@@ -986,7 +996,16 @@ __global__ void __launch_bounds__(256) k_selftest_math(unsigned long long* out, 
 }
 }  // namespace
 
-extern "C" int arn_selftest_math(arn_ctx* c, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5) {
+extern "C" int arn_selftest_pair_records(const arn_node* nodes, uint32_t n_nodes, float* records_out, uint32_t* n_records_out) {
+    if (!nodes || !n_records_out) return ARN_E_INVALID;
+    std::vector<float> rec;
+    const uint32_t n = build_pair_records(nodes, n_nodes, &rec);
+    *n_records_out = n;
+    if (n && records_out) std::memcpy(records_out, rec.data(), rec.size() * sizeof(float));
+    return ARN_OK;
+}
+
+int arn_selftest_math(arn_ctx* c, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5) {
     if (!c || !mismatches5 || count_log2 > 32) return set_err(c, ARN_E_INVALID, "arn_selftest_math: bad argument");
     std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device);
     CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 64, c->stream));

@@ -406,6 +406,11 @@ void* arn_ctx_stream(arn_ctx* ctx);
  * both this library and the oracle use.  mismatches5 = {sin, cos, exp, log, pow}; all must be 0. */
 int arn_selftest_math(arn_ctx* ctx, uint32_t first_bits, uint32_t count_log2, uint64_t* mismatches5);
 
+/* Diagnostic (host only, no device needed): the pair records arn_scene_upload builds for k_trace's shared-memory walk of a small tree
+ * (kernels/traverse.cuh, traverse2p): 32 floats per interior node, in node order.  *n_records_out = 0 when the tree does not qualify
+ * (single leaf, or more than ARN_SMEM_NODE_BYTES / 128 interior nodes).  records_out may be NULL to query the count. */
+int arn_selftest_pair_records(const arn_node* nodes, uint32_t n_nodes, float* records_out, uint32_t* n_records_out);
+
 /* Diagnostic: the BSDF of material `m` (Material::compute_scattering with constant textures, material/{matte,plastic,glass,translucent}.rs) at a fixed local
  * frame (dpdu = x, shading normal = geometric normal = z; or, with frame9 != NULL, dpdu / shading normal / geometric normal per probe),
  * for n host-side triples (wo[3], u[2], wi[3]):

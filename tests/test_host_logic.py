@@ -156,3 +156,39 @@ def test_stratified_sampler_mode_stratifies_every_dimension_it_covers():
         a = np.zeros(n1 + 2 * n2, np.float32); b = np.zeros_like(a)
         lib.arn_oracle_sampler_draws2(C.byref(smp), 3, 4, 0, n1, n2, a.ctypes.data); lib.arn_oracle_sampler_draws2(C.byref(smp), 4, 3, 0, n1, n2, b.ctypes.data)
         assert not np.array_equal(a, b)
+
+
+def test_pair_records_of_small_trees_restate_the_nodes():
+    """arn_scene_upload re-encodes a small tree for k_trace's shared-memory walk (kernels/traverse.cuh, traverse2p): one 128-byte
+    record per interior node — per axis both children's planes in both orders, the children's reference words twice.  Checked
+    against the 32-byte nodes it is built from; a tree beyond the shared-memory budget and a single-leaf tree give no records."""
+    from arendur_b200 import scenes
+    lib = L.load()
+    hs, *_ = scenes.cornell_scene(64, 48, 2, 2)
+    nodes = hs.nodes()                                                   # (n, 8) uint32 bit patterns of arn_node
+    n = nodes.shape[0]
+    cnt = C.c_uint32(0)
+    assert lib.arn_selftest_pair_records(nodes.ctypes.data_as(C.c_void_p), n, None, C.byref(cnt)) == 0
+    n_int = (n - 1) // 2
+    assert cnt.value == n_int and n_int * 128 <= L.ARN_SMEM_NODE_BYTES
+    rec = np.zeros((n_int, 32), np.uint32)
+    assert lib.arn_selftest_pair_records(nodes.ctypes.data_as(C.c_void_p), n, rec.ctypes.data_as(C.c_void_p), C.byref(cnt)) == 0
+    interior = np.nonzero((nodes[:, 7] >> 2) == 0)[0]
+    pair_of = {int(i): k for k, i in enumerate(interior)}
+    assert len(interior) == n_int and interior[0] == 0                   # the root's record is the first
+    for i in interior:
+        r = rec[pair_of[int(i)]]
+        for slot, ch in enumerate((int(i) + 1, int(i) + int(nodes[i, 6]))):
+            bmin, bmax = nodes[ch, 0:3], nodes[ch, 3:6]
+            for a in range(3):
+                assert r[a * 8 + slot * 2] == bmin[a] and r[a * 8 + slot * 2 + 1] == bmax[a]          # direction >= 0: (min, max)
+                assert r[a * 8 + 4 + slot * 2] == bmax[a] and r[a * 8 + 4 + slot * 2 + 1] == bmin[a]  # direction < 0: (max, min)
+            leaf = (nodes[ch, 7] >> 2) != 0
+            w0 = int(nodes[ch, 6]) if leaf else pair_of[ch] * 128
+            for rep in range(2):
+                assert r[24 + rep * 4 + slot * 2] == w0 and r[25 + rep * 4 + slot * 2] == nodes[ch, 7]
+    # too large for the budget / a single leaf: no records, and the count says so
+    big, *_ = scenes.c4_box_scene(cells=14, res=16, sampledx=1, sampledy=1)
+    bn = big.nodes()
+    assert lib.arn_selftest_pair_records(bn.ctypes.data_as(C.c_void_p), bn.shape[0], None, C.byref(cnt)) == 0 and cnt.value == 0
+    assert lib.arn_selftest_pair_records(nodes[interior[-1] + 1:].ctypes.data_as(C.c_void_p), 1, None, C.byref(cnt)) == 0 and cnt.value == 0
