@@ -548,6 +548,7 @@ ARN_DEV bool slab_nf(const float2 X, const float2 Y, const float2 Z, const TravR
 }
 // 4-byte stack entries: the entry distance truncated to its upper 16 bits (it is >= 0, so truncation rounds DOWN: the pop-time
 // re-check stays conservative) over (record index << 1 | child slot) — a warp's stack level is one 128-byte line of local memory
+static_assert(ARN_SMEM_NODE_BYTES / ARN_PAIR_BYTES <= 32768u, "a stack entry keeps the record index in 15 bits");
 ARN_DEV uint32_t pair_entry(uint32_t ref, float lo) { return (__float_as_uint(lo) & 0xffff0000u) | (ref >> 6) | (ref & 1u); }      // ref = record offset (multiple of 128) | slot
 ARN_DEV bool trav_pop_p(const TravRay& r, const uint32_t* stack, int& sp, uint32_t bx, uint32_t& ref, uint32_t& w0, uint32_t& w1) {
     for (;;) {
